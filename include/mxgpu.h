@@ -1,0 +1,171 @@
+/* mxgpu.h — C ABI of the B200-native sparse x dense multiplication library (libmxgpu.so).
+ *
+ * This is the drop-in boundary for MatrixExtra's multiplication path: the ten Rcpp exports of
+ * /root/reference/src/matmul.cpp:221-483 (registered at src/RcppExports.cpp:2233-2242 and called
+ * from the S4 methods in R/matmul.R) are re-implemented on top of the entry points below by the
+ * glue in rglue/matmul_gpu_glue.cpp.  Plain pointers and sizes only; every function returns an
+ * int status (MXG_OK == 0) and never throws / longjmps; mxg_last_error() describes the failure.
+ *
+ * Conventions shared with the reference:
+ *   - CSR A is m x K: p[m+1] int32 (0-based offsets), j[nnz] int32 0-based column ids,
+ *     x[nnz] ALWAYS float64 on the host (R's dgRMatrix@x), also on the float32 path
+ *     (src/matmul.cpp:122, 154: `const double *restrict values`).
+ *   - float32 dense data is IEEE-754 binary32; R's `float` package keeps those bits in an INTEGER
+ *     matrix (src/matmul.cpp:213-214), so the glue passes INTEGER(x) as the float pointer.
+ *   - Index validity is NOT checked by the reference on this path (R/utils.R:349-410 checks only
+ *     lengths); this library validates column ids once per upload and returns MXG_ERR_INDEX
+ *     instead of faulting.
+ *   - No alpha/beta: Out is overwritten completely (the reference writes into a zero-filled
+ *     R matrix, src/matmul.cpp:197/261/323/389).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * MXG_ERR_CUDA.
+ */
+#ifndef MXGPU_H
+#define MXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---- */
+#define MXG_OK 0
+#define MXG_ERR_CUDA 1        /* a CUDA runtime call failed (no device, OOM, launch failure) */
+#define MXG_ERR_ARG 2         /* inconsistent arguments (negative sizes, NULL where data is needed, bad enum) */
+#define MXG_ERR_INDEX 3       /* CSR column index outside [0, K) or non-monotone / negative indptr */
+#define MXG_ERR_UNSUPPORTED 4 /* valid request this build does not cover */
+
+/* ---- enums (plain ints in the signatures) ---- */
+#define MXG_F64 0 /* double: R numeric matrix */
+#define MXG_F32 1 /* float : R float32@Data   */
+
+#define MXG_ROWS_CONTIGUOUS 0 /* element (r, c) at r*ld + c : "row-major" */
+#define MXG_COLS_CONTIGUOUS 1 /* element (r, c) at r + c*ld : R's native column-major */
+
+#define MXG_Y_NUMERIC 0 /* double y             : matmul_csr_dvec_numeric  src/matmul.cpp:421 */
+#define MXG_Y_INTEGER 1 /* int y, NA_INTEGER    : matmul_csr_dvec_integer  src/matmul.cpp:437 */
+#define MXG_Y_LOGICAL 2 /* int y, NA_LOGICAL    : matmul_csr_dvec_logical  src/matmul.cpp:453 */
+#define MXG_Y_FLOAT32 3 /* float y, float result: matmul_csr_dvec_float32  src/matmul.cpp:469 */
+
+/* which copies of the CSR values a device-resident handle keeps */
+#define MXG_KEEP_F64 1
+#define MXG_KEEP_F32 2
+
+typedef struct mxg_csr_s *mxg_csr_t; /* opaque device-resident CSR (or, by relabelling, CSC) */
+
+/* ================================ library state ================================================ */
+
+/* Human-readable description of the last failure on the calling thread ("" if none). */
+const char *mxg_last_error(void);
+
+/* Number of visible CUDA devices (0 and MXG_ERR_CUDA when there is none). */
+int mxg_device_count(int *count);
+
+/* Device used by subsequent calls from this thread (default: the current CUDA device). */
+int mxg_set_device(int device);
+
+/* Tuning knobs, all optional ("auto" when never set). Names: "piece" (nnz per long-row piece),
+ * "spmm_lpr" (lanes per row team), "spmm_cpl" (vectors per lane), "spmm_block_rows",
+ * "spmv_lpr", "h2d_chunk_mb".  Unknown names return MXG_ERR_ARG. */
+int mxg_set_option(const char *name, long value);
+int mxg_get_option(const char *name, long *value);
+
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches` claim). */
+unsigned long long mxg_launch_count(void);
+
+/* Release cached device memory / pinned staging held between calls. */
+int mxg_trim(void);
+
+/* ============ level 1: host buffers in, host buffers out (what the Rcpp glue calls) ============
+ * Each call uploads its operands (pinned staging ring, chunked, overlapped with compute), runs the
+ * device kernels and writes the result straight into the caller's (R-allocated) output buffer.   */
+
+/* Out = A_csr(m x K) . B, B with n columns.  Replaces gemm_csr_drm_as_drm (src/matmul.cpp:118-142,
+ * out_layout = MXG_ROWS_CONTIGUOUS, ldc >= n) and gemm_csr_drm_as_dcm (src/matmul.cpp:150-185,
+ * out_layout = MXG_COLS_CONTIGUOUS, ldc >= m) together with their typed wrappers
+ * matmul_dense_csc / tcrossprod_dense_csr / tcrossprod_csr_dense (src/matmul.cpp:188-375).
+ *   dtype     MXG_F64 | MXG_F32: element type of B and Out (x is narrowed to float first for F32,
+ *             src/matmul.cpp:53-57)
+ *   b_layout  MXG_ROWS_CONTIGUOUS: B[k, c] at k*ldb + c (what every reference entry point receives:
+ *             an (n x K) column-major R matrix, ldb = n);  MXG_COLS_CONTIGUOUS: B[k, c] at k + c*ldb
+ *             (an untransposed K x n R matrix; saves the R-side t(y) of R/matmul.R:464, 507)        */
+int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout,
+                       int m, int K, int n,
+                       const int32_t *p, const int32_t *j, const double *x,
+                       const void *B, size_t ldb,
+                       void *Out, size_t ldc);
+
+/* out[m] = A_csr(m x K) . y.  Replaces matmul_csr_dvec<> (src/matmul.cpp:381-483).
+ * ytype selects the element type of y and the NA rules of src/matmul.cpp:406-411; the result is
+ * double except for MXG_Y_FLOAT32 (float). */
+int mxg_spmv_csr(int ytype, int m, int K,
+                 const int32_t *p, const int32_t *j, const double *x,
+                 const void *y, void *out);
+
+/* Deep CSR(m x K) -> CSC conversion, bit-exact stable counting order (rows ascending inside each
+ * column, duplicates in stored order).  Replaces the `as(x, "CsparseMatrix")` that
+ * R/conversions.R:390-392 delegates to the Matrix package.  p2[K+1], i2[nnz], x2[nnz] are caller
+ * buffers; x/x2 may both be NULL for pattern matrices. */
+int mxg_csr2csc(int m, int K,
+                const int32_t *p, const int32_t *j, const double *x,
+                int32_t *p2, int32_t *i2, double *x2);
+
+/* Out(K x n) = t(A_csr(m x K)) . B(m x n): device CSR->CSC transpose followed by the gather
+ * product.  Serves crossprod(CSR, dense), t(CSR) %*% dense and (by transposition of the result
+ * layout) dense %*% CSR, which MatrixExtra leaves to the Matrix package. */
+int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout,
+                        int m, int K, int n,
+                        const int32_t *p, const int32_t *j, const double *x,
+                        const void *B, size_t ldb,
+                        void *Out, size_t ldc);
+
+/* ============ level 2: device-resident handles (repeated multiplies, benchmarks, sharding) ===== */
+
+/* Upload a host CSR once (validates indices, converts values, computes row statistics). */
+int mxg_csr_upload(int m, int K, const int32_t *p, const int32_t *j, const double *x,
+                   int keep, mxg_csr_t *handle);
+
+/* Wrap CSR arrays that already live in device memory (not copied, not freed by mxg_csr_free).
+ * d_x64 / d_x32 may be NULL individually.  Runs validation + row statistics on `stream`. */
+int mxg_csr_wrap_device(int m, int K, const int32_t *d_p, const int32_t *d_j,
+                        const double *d_x64, const float *d_x32, int validate,
+                        void *stream, mxg_csr_t *handle);
+
+int mxg_csr_free(mxg_csr_t handle);
+
+/* m, K, nnz, number of long rows, number of long-row pieces, longest row */
+int mxg_csr_info(mxg_csr_t handle, int64_t info[6]);
+
+/* Device pointers of the handle's arrays (for sharding / tests); any out pointer may be NULL. */
+int mxg_csr_device_arrays(mxg_csr_t handle, const int32_t **d_p, const int32_t **d_j,
+                          const double **d_x64, const float **d_x32);
+
+/* Same products as level 1 with every operand already in device memory; asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = legacy default stream). */
+int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,
+                 const void *d_B, size_t ldb, void *d_Out, size_t ldc, void *stream);
+
+int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream);
+
+/* New device-resident CSC of A (as a CSR handle of t(A): K rows, m columns). */
+int mxg_dev_csr2csc(mxg_csr_t A, int keep, void *stream, mxg_csr_t *At);
+
+/* Dense layout change on device: dst(c, r) = src(r, c); rows x cols elements of 4 or 8 bytes. */
+int mxg_dev_transpose_dense(int elem_size, size_t rows, size_t cols,
+                            const void *d_src, size_t ld_src, void *d_dst, size_t ld_dst, void *stream);
+
+/* nnz-balanced contiguous row blocks for multi-GPU sharding (binary search of g*nnz/G in p):
+ * row_starts[parts+1] is filled with 0 = r_0 <= r_1 <= ... <= r_parts = m.  Host indptr. */
+int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
+
+/* ============ synthetic inputs for bench.py / tests (device-side, counter-based RNG) ============
+ * Power-law row lengths, stratified sorted unique columns; see DESIGN.md "Synthetic inputs". */
+int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed,
+                  int keep, void *stream, mxg_csr_t *handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MXGPU_H */

@@ -1,0 +1,575 @@
+// capi.cu — the extern "C" surface declared in include/mxgpu.h: library state, device-resident
+// handles (level 2) and the host-buffer entry points the Rcpp glue binds (level 1).
+#include "mxg_internal.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace mxg {
+
+int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed, int keep,
+                     cudaStream_t stream, int32_t **out_p, int32_t **out_j, double **out_x64, float **out_x32,
+                     int64_t *out_nnz);
+
+// ---- per-process state: one internal stream for the level-1 calls, pool configured once per device ----
+struct DeviceState {
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+};
+static DeviceState g_dev[64];
+
+static int current_state(DeviceState **out)
+{
+    int dev = 0;
+    MXG_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(MXG_ERR_CUDA, "device ordinal %d out of range", dev);
+    DeviceState &st = g_dev[dev];
+    if (!st.ready) {
+        MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep_all = ~0ULL; // keep freed blocks cached between calls (mxg_trim releases them)
+        MXG_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+        st.ready = true;
+    }
+    *out = &st;
+    return MXG_OK;
+}
+
+static int free_handle(mxg_csr_s *h)
+{
+    if (!h) return MXG_OK;
+    if (h->owns) {
+        cudaFree(const_cast<int32_t *>(h->d_p));
+        cudaFree(const_cast<int32_t *>(h->d_j));
+        cudaFree(const_cast<double *>(h->d_x64));
+        cudaFree(const_cast<float *>(h->d_x32));
+    }
+    cudaFree(h->d_long_rows);
+    cudaFree(h->d_long_first);
+    cudaFree(h->d_long_np);
+    cudaFree(h->d_piece_row);
+    cudaFree(h->d_piece_k);
+    cudaFree(h->d_partial);
+    delete h;
+    return MXG_OK;
+}
+
+// Host CSR -> owned device handle.  All copies are issued on `stream`; returns after they completed.
+static int upload_csr(int m, int K, const int32_t *p, const int32_t *j, const double *x, int keep,
+                      cudaStream_t stream, mxg_csr_s **out)
+{
+    if (m < 0 || K < 0) return fail(MXG_ERR_ARG, "csr: negative dimension");
+    if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
+    const int32_t base = p[0];
+    const int64_t nnz = (int64_t)p[m] - (int64_t)base;
+    if (base < 0 || nnz < 0) return fail(MXG_ERR_INDEX, "csr: indptr is negative or decreasing");
+    if (nnz > 0 && !j) return fail(MXG_ERR_ARG, "csr: indices is NULL");
+    const bool want64 = (keep & MXG_KEEP_F64) != 0, want32 = (keep & MXG_KEEP_F32) != 0;
+    if (nnz > 0 && (want64 || want32) && !x) return fail(MXG_ERR_ARG, "csr: values is NULL");
+
+    mxg_csr_s *h = new mxg_csr_s();
+    h->m = m;
+    h->K = K;
+    h->nnz = nnz;
+    h->base = 0;
+    h->owns = true;
+    cudaGetDevice(&h->device);
+    int32_t *d_p = nullptr, *d_j = nullptr;
+    double *d_x64 = nullptr;
+    float *d_x32 = nullptr;
+    const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+#define MXG_UP_TRY(expr)                                                                             \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            free_handle(h);                                                                          \
+            return fail(MXG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));               \
+        }                                                                                            \
+    } while (0)
+    MXG_UP_TRY(cudaMalloc(&d_p, sizeof(int32_t) * ((size_t)m + 1)));
+    h->d_p = d_p;
+    MXG_UP_TRY(cudaMalloc(&d_j, sizeof(int32_t) * nz));
+    h->d_j = d_j;
+    if (base == 0) {
+        MXG_UP_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
+    } else {
+        // R never produces p[0] != 0 (R/utils.R:349-410 rejects it); rebase so device offsets start at 0
+        std::vector<int32_t> pr((size_t)m + 1);
+        for (int r = 0; r <= m; r++) pr[(size_t)r] = p[r] - base;
+        MXG_UP_TRY(cudaMemcpyAsync(d_p, pr.data(), sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
+        MXG_UP_TRY(cudaStreamSynchronize(stream));
+    }
+    if (nnz > 0) {
+        MXG_UP_TRY(cudaMemcpyAsync(d_j, j + base, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        if (want64) {
+            MXG_UP_TRY(cudaMalloc(&d_x64, sizeof(double) * nz));
+            h->d_x64 = d_x64;
+            MXG_UP_TRY(cudaMemcpyAsync(d_x64, x + base, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        }
+        if (want32) {
+            MXG_UP_TRY(cudaMalloc(&d_x32, sizeof(float) * nz));
+            h->d_x32 = d_x32;
+            if (d_x64) {
+                int rc = convert_f64_to_f32(d_x64, d_x32, (size_t)nnz, stream);
+                if (rc != MXG_OK) { free_handle(h); return rc; }
+            } else {
+                // stage the float64 values through pool memory in chunks and narrow them on device (K6)
+                const size_t chunk = (size_t)std::max<long>(1, options().h2d_chunk_mb) * (1u << 20) / sizeof(double);
+                double *d_tmp = nullptr;
+                const size_t c0 = std::min(chunk, (size_t)nnz);
+                const size_t c = c0 + (c0 & 1);
+                MXG_UP_TRY(cudaMallocAsync(&d_tmp, sizeof(double) * c, stream));
+                for (size_t off = 0; off < (size_t)nnz; off += c) {
+                    const size_t len = std::min(c, (size_t)nnz - off);
+                    MXG_UP_TRY(cudaMemcpyAsync(d_tmp, x + base + off, sizeof(double) * len, cudaMemcpyHostToDevice, stream));
+                    int rc = convert_f64_to_f32(d_tmp, d_x32 + off, len, stream);
+                    if (rc != MXG_OK) { free_handle(h); return rc; }
+                }
+                MXG_UP_TRY(cudaFreeAsync(d_tmp, stream));
+            }
+        }
+    }
+#undef MXG_UP_TRY
+    int rc = csr_build_stats(h, /*validate=*/1, stream); // synchronises the stream
+    if (rc != MXG_OK) {
+        free_handle(h);
+        return rc;
+    }
+    *out = h;
+    return MXG_OK;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Dense operand -> tight rows-contiguous device copy [K][ld] with ld a multiple of the 16-byte vector.
+static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const void *B, size_t ldb,
+                             cudaStream_t stream, void **d_out, size_t *ld_out)
+{
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    const size_t vec = 16 / s;
+    const size_t ld = round_up(n, vec);
+    void *d_B = nullptr;
+    MXG_CUDA_TRY(cudaMallocAsync(&d_B, std::max<size_t>(K * ld * s, 16), stream));
+    if (K > 0 && n > 0) {
+        if (b_layout == MXG_ROWS_CONTIGUOUS) {
+            if (ldb < n) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
+            if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
+            MXG_CUDA_TRY(cudaMemcpy2DAsync(d_B, ld * s, B, ldb * s, n * s, K, cudaMemcpyHostToDevice, stream));
+        } else if (b_layout == MXG_COLS_CONTIGUOUS) {
+            if (ldb < K) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
+            void *d_tmp = nullptr;
+            MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, K * n * s, stream));
+            MXG_CUDA_TRY(cudaMemcpy2DAsync(d_tmp, K * s, B, ldb * s, K * s, n, cudaMemcpyHostToDevice, stream));
+            if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
+            // d_tmp is n rows of K contiguous -> d_B is K rows of n contiguous
+            MXG_TRY(launch_transpose_dense((int)s, n, K, d_tmp, K, d_B, ld, stream));
+            MXG_CUDA_TRY(cudaFreeAsync(d_tmp, stream));
+        } else {
+            return fail(MXG_ERR_ARG, "dense operand: bad layout %d", b_layout);
+        }
+    }
+    *d_out = d_B;
+    *ld_out = ld;
+    return MXG_OK;
+}
+
+// shared tail of the two level-1 SpMM entry points: A is on the device, B/Out are host buffers
+static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
+                        void *Out, size_t ldc, cudaStream_t stream)
+{
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    const size_t vec = 16 / s;
+    const size_t rows = (size_t)A->m, K = (size_t)A->K;
+    if (rows == 0 || n == 0) return MXG_OK;
+    if (!B && K > 0) return fail(MXG_ERR_ARG, "dense operand is NULL");
+    if (!Out) return fail(MXG_ERR_ARG, "output is NULL");
+    void *d_B = nullptr, *d_Out = nullptr;
+    size_t ld_b = 0;
+    MXG_TRY(upload_dense_rows(dtype, b_layout, K, (size_t)n, B, ldb, stream, &d_B, &ld_b));
+    size_t ld_o;
+    if (out_layout == MXG_ROWS_CONTIGUOUS) {
+        if (ldc < (size_t)n) return fail(MXG_ERR_ARG, "output: ldc < n");
+        ld_o = round_up((size_t)n, vec);
+        MXG_CUDA_TRY(cudaMallocAsync(&d_Out, rows * ld_o * s, stream));
+    } else if (out_layout == MXG_COLS_CONTIGUOUS) {
+        if (ldc < rows) return fail(MXG_ERR_ARG, "output: ldc < m");
+        ld_o = rows;
+        MXG_CUDA_TRY(cudaMallocAsync(&d_Out, rows * (size_t)n * s, stream));
+    } else {
+        return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
+    }
+    MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, stream));
+    if (out_layout == MXG_ROWS_CONTIGUOUS)
+        MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, (size_t)n * s, rows, cudaMemcpyDeviceToHost, stream));
+    else
+        MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, rows * s, (size_t)n, cudaMemcpyDeviceToHost, stream));
+    MXG_CUDA_TRY(cudaFreeAsync(d_B, stream));
+    MXG_CUDA_TRY(cudaFreeAsync(d_Out, stream));
+    MXG_CUDA_TRY(cudaStreamSynchronize(stream));
+    return MXG_OK;
+}
+
+static int transpose_handle(const mxg_csr_s *A, int keep, cudaStream_t stream, mxg_csr_s **out)
+{
+    const bool w64 = (keep & MXG_KEEP_F64) && A->d_x64, w32 = (keep & MXG_KEEP_F32) && A->d_x32;
+    mxg_csr_s *t = new mxg_csr_s();
+    t->m = A->K;
+    t->K = A->m;
+    t->nnz = A->nnz;
+    t->owns = true;
+    t->device = A->device;
+    int32_t *d_p2 = nullptr, *d_i2 = nullptr;
+    double *d_x64 = nullptr;
+    float *d_x32 = nullptr;
+    const size_t nz = (size_t)(A->nnz > 0 ? A->nnz : 1);
+    cudaError_t e = cudaMalloc(&d_p2, sizeof(int32_t) * ((size_t)A->K + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_i2, sizeof(int32_t) * nz);
+    if (e == cudaSuccess && w64) e = cudaMalloc(&d_x64, sizeof(double) * nz);
+    if (e == cudaSuccess && w32) e = cudaMalloc(&d_x32, sizeof(float) * nz);
+    t->d_p = d_p2;
+    t->d_j = d_i2;
+    t->d_x64 = d_x64;
+    t->d_x32 = d_x32;
+    if (e != cudaSuccess) {
+        free_handle(t);
+        return fail(MXG_ERR_CUDA, "csr2csc: allocation failed: %s", cudaGetErrorString(e));
+    }
+    int rc = csr2csc_device(A->m, A->K, A->nnz, A->d_p, A->d_j, A->d_x64, A->d_x32, d_p2, d_i2, d_x64, d_x32, stream);
+    if (rc == MXG_OK) rc = csr_build_stats(t, /*validate=*/0, stream);
+    if (rc != MXG_OK) {
+        free_handle(t);
+        return rc;
+    }
+    *out = t;
+    return MXG_OK;
+}
+
+} // namespace mxg
+
+using namespace mxg;
+
+extern "C" {
+
+const char *mxg_last_error(void) { return last_error_ref().c_str(); }
+
+int mxg_device_count(int *count)
+{
+    if (!count) return fail(MXG_ERR_ARG, "count is NULL");
+    *count = 0;
+    MXG_CUDA_TRY(cudaGetDeviceCount(count));
+    return MXG_OK;
+}
+
+int mxg_set_device(int device)
+{
+    MXG_CUDA_TRY(cudaSetDevice(device));
+    return MXG_OK;
+}
+
+static long *option_slot(const char *name)
+{
+    Options &o = options();
+    if (!name) return nullptr;
+    if (!strcmp(name, "piece")) return &o.piece;
+    if (!strcmp(name, "spmm_lpr")) return &o.spmm_lpr;
+    if (!strcmp(name, "spmm_cpl")) return &o.spmm_cpl;
+    if (!strcmp(name, "spmm_block_rows")) return &o.spmm_block_rows;
+    if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
+    if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;
+    return nullptr;
+}
+
+int mxg_set_option(const char *name, long value)
+{
+    long *slot = option_slot(name);
+    if (!slot) return fail(MXG_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
+    *slot = value;
+    return MXG_OK;
+}
+
+int mxg_get_option(const char *name, long *value)
+{
+    long *slot = option_slot(name);
+    if (!slot || !value) return fail(MXG_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
+    *value = *slot;
+    return MXG_OK;
+}
+
+unsigned long long mxg_launch_count(void) { return g_launches.load(); }
+
+int mxg_trim(void)
+{
+    int dev = 0;
+    MXG_CUDA_TRY(cudaGetDevice(&dev));
+    MXG_CUDA_TRY(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    MXG_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return MXG_OK;
+}
+
+/* ------------------------------------ level 2: handles ---------------------------------------- */
+
+int mxg_csr_upload(int m, int K, const int32_t *p, const int32_t *j, const double *x, int keep, mxg_csr_t *handle)
+{
+    if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
+    *handle = nullptr;
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *h = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, keep, st->stream, &h));
+    *handle = h;
+    return MXG_OK;
+}
+
+int mxg_csr_wrap_device(int m, int K, const int32_t *d_p, const int32_t *d_j, const double *d_x64,
+                        const float *d_x32, int validate, void *stream, mxg_csr_t *handle)
+{
+    if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
+    *handle = nullptr;
+    if (m < 0 || K < 0 || !d_p) return fail(MXG_ERR_ARG, "csr_wrap_device: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int32_t ends[2] = {0, 0};
+    MXG_CUDA_TRY(cudaMemcpyAsync(&ends[0], d_p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MXG_CUDA_TRY(cudaMemcpyAsync(&ends[1], d_p + m, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MXG_CUDA_TRY(cudaStreamSynchronize(s));
+    if (ends[0] < 0 || ends[1] < ends[0]) return fail(MXG_ERR_INDEX, "csr_wrap_device: bad indptr");
+    mxg_csr_s *h = new mxg_csr_s();
+    h->m = m;
+    h->K = K;
+    h->base = ends[0];
+    h->nnz = (int64_t)ends[1] - ends[0];
+    h->d_p = d_p;
+    h->d_j = d_j;
+    h->d_x64 = d_x64;
+    h->d_x32 = d_x32;
+    h->owns = false;
+    cudaGetDevice(&h->device);
+    int rc = csr_build_stats(h, validate, s);
+    if (rc != MXG_OK) {
+        free_handle(h);
+        return rc;
+    }
+    *handle = h;
+    return MXG_OK;
+}
+
+int mxg_csr_free(mxg_csr_t handle) { return free_handle(handle); }
+
+int mxg_csr_info(mxg_csr_t h, int64_t info[6])
+{
+    if (!h || !info) return fail(MXG_ERR_ARG, "csr_info: NULL argument");
+    info[0] = h->m;
+    info[1] = h->K;
+    info[2] = h->nnz;
+    info[3] = h->n_long;
+    info[4] = h->n_pieces;
+    info[5] = h->max_len;
+    return MXG_OK;
+}
+
+int mxg_csr_device_arrays(mxg_csr_t h, const int32_t **d_p, const int32_t **d_j, const double **d_x64,
+                          const float **d_x32)
+{
+    if (!h) return fail(MXG_ERR_ARG, "csr_device_arrays: NULL handle");
+    if (d_p) *d_p = h->d_p;
+    if (d_j) *d_j = h->d_j;
+    if (d_x64) *d_x64 = h->d_x64;
+    if (d_x32) *d_x32 = h->d_x32;
+    return MXG_OK;
+}
+
+int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
+                 void *d_Out, size_t ldc, void *stream)
+{
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmm: NULL handle");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (b_layout == MXG_ROWS_CONTIGUOUS) return launch_spmm(A, dtype, out_layout, n, d_B, ldb, d_Out, ldc, s);
+    if (b_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "dev_spmm: bad b_layout %d", b_layout);
+    if (A->K == 0 || n <= 0) return launch_spmm(A, dtype, out_layout, n, d_B, (size_t)(n > 0 ? n : 0), d_Out, ldc, s);
+    // column-major dense operand: K5 into a temporary rows-contiguous copy first
+    const size_t sz = dtype == MXG_F64 ? 8 : 4;
+    const size_t ld = round_up((size_t)n, 16 / sz);
+    void *d_tmp = nullptr;
+    MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, (size_t)A->K * ld * sz, s));
+    if (ld != (size_t)n) MXG_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, (size_t)A->K * ld * sz, s));
+    MXG_TRY(launch_transpose_dense((int)sz, (size_t)n, (size_t)A->K, d_B, ldb, d_tmp, ld, s));
+    MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_tmp, ld, d_Out, ldc, s));
+    MXG_CUDA_TRY(cudaFreeAsync(d_tmp, s));
+    return MXG_OK;
+}
+
+int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream)
+{
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmv: NULL handle");
+    return launch_spmv(A, ytype, d_y, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_csr2csc(mxg_csr_t A, int keep, void *stream, mxg_csr_t *At)
+{
+    if (!A || !At) return fail(MXG_ERR_ARG, "dev_csr2csc: NULL argument");
+    *At = nullptr;
+    mxg_csr_s *t = nullptr;
+    MXG_TRY(transpose_handle(A, keep, static_cast<cudaStream_t>(stream), &t));
+    *At = t;
+    return MXG_OK;
+}
+
+int mxg_dev_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src, void *d_dst,
+                            size_t ld_dst, void *stream)
+{
+    return launch_transpose_dense(elem_size, rows, cols, d_src, ld_src, d_dst, ld_dst, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts)
+{
+    if (m < 0 || parts <= 0 || !p || !row_starts) return fail(MXG_ERR_ARG, "row_partition: bad arguments");
+    const int64_t base = p[0], nnz = (int64_t)p[m] - base;
+    row_starts[0] = 0;
+    for (int g = 1; g < parts; g++) {
+        // first row whose start offset reaches g/parts of the entries
+        const int64_t target = base + (nnz * g) / parts;
+        const int32_t *it = std::lower_bound(p, p + m + 1, (int32_t)std::min<int64_t>(target, INT32_MAX));
+        int r = (int)(it - p);
+        if (r > m) r = m;
+        if (nnz == 0) r = (int)(((int64_t)m * g) / parts);
+        if (r < row_starts[g - 1]) r = row_starts[g - 1];
+        row_starts[g] = r;
+    }
+    row_starts[parts] = m;
+    return MXG_OK;
+}
+
+int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed, int keep,
+                  void *stream, mxg_csr_t *handle)
+{
+    if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
+    *handle = nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int32_t *d_p = nullptr, *d_j = nullptr;
+    double *d_x64 = nullptr;
+    float *d_x32 = nullptr;
+    int64_t nnz = 0;
+    MXG_TRY(synth_csr_arrays(m, K, target_nnz, row_model, col_model, seed, keep, s, &d_p, &d_j, &d_x64, &d_x32, &nnz));
+    mxg_csr_s *h = new mxg_csr_s();
+    h->m = m;
+    h->K = K;
+    h->nnz = nnz;
+    h->base = 0;
+    h->d_p = d_p;
+    h->d_j = d_j;
+    h->d_x64 = d_x64;
+    h->d_x32 = d_x32;
+    h->owns = true;
+    cudaGetDevice(&h->device);
+    int rc = csr_build_stats(h, /*validate=*/0, s);
+    if (rc != MXG_OK) {
+        free_handle(h);
+        return rc;
+    }
+    *handle = h;
+    return MXG_OK;
+}
+
+/* ------------------------------------ level 1: host buffers ----------------------------------- */
+
+int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
+                       const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc)
+{
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
+    if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *A = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32, st->stream, &A));
+    int rc = spmm_host_io(A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream);
+    cudaStreamSynchronize(st->stream);
+    free_handle(A);
+    return rc;
+}
+
+int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
+                        const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc)
+{
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
+    if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    const int keep = dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32;
+    mxg_csr_s *A = nullptr, *At = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, keep, st->stream, &A));
+    int rc = transpose_handle(A, keep, st->stream, &At);
+    cudaStreamSynchronize(st->stream);
+    free_handle(A);
+    if (rc != MXG_OK) return rc;
+    rc = spmm_host_io(At, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream);
+    cudaStreamSynchronize(st->stream);
+    free_handle(At);
+    return rc;
+}
+
+int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *y, void *out)
+{
+    if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *A = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, MXG_KEEP_F64, st->stream, &A));
+    int rc = MXG_OK;
+    if (m > 0) {
+        const size_t ys = ytype == MXG_Y_NUMERIC ? 8 : 4;
+        const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
+        void *d_y = nullptr, *d_out = nullptr;
+        cudaStream_t s = st->stream;
+        auto body = [&]() -> int {
+            if (!out) return fail(MXG_ERR_ARG, "output is NULL");
+            if (K > 0 && !y) return fail(MXG_ERR_ARG, "vector is NULL");
+            MXG_CUDA_TRY(cudaMallocAsync(&d_y, std::max<size_t>((size_t)K * ys, 16), s));
+            MXG_CUDA_TRY(cudaMallocAsync(&d_out, (size_t)m * os, s));
+            if (K > 0) MXG_CUDA_TRY(cudaMemcpyAsync(d_y, y, (size_t)K * ys, cudaMemcpyHostToDevice, s));
+            MXG_TRY(launch_spmv(A, ytype, d_y, d_out, s));
+            MXG_CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)m * os, cudaMemcpyDeviceToHost, s));
+            MXG_CUDA_TRY(cudaFreeAsync(d_y, s));
+            MXG_CUDA_TRY(cudaFreeAsync(d_out, s));
+            MXG_CUDA_TRY(cudaStreamSynchronize(s));
+            return MXG_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st->stream);
+    free_handle(A);
+    return rc;
+}
+
+int mxg_csr2csc(int m, int K, const int32_t *p, const int32_t *j, const double *x, int32_t *p2, int32_t *i2, double *x2)
+{
+    if (!p2) return fail(MXG_ERR_ARG, "p2 is NULL");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    const bool vals = x && x2;
+    mxg_csr_s *A = nullptr, *At = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, vals ? x : nullptr, vals ? MXG_KEEP_F64 : 0, st->stream, &A));
+    int rc = transpose_handle(A, MXG_KEEP_F64, st->stream, &At);
+    if (rc == MXG_OK) {
+        cudaStream_t s = st->stream;
+        auto body = [&]() -> int {
+            MXG_CUDA_TRY(cudaMemcpyAsync(p2, At->d_p, sizeof(int32_t) * ((size_t)K + 1), cudaMemcpyDeviceToHost, s));
+            if (At->nnz > 0) {
+                if (!i2) return fail(MXG_ERR_ARG, "i2 is NULL");
+                MXG_CUDA_TRY(cudaMemcpyAsync(i2, At->d_j, sizeof(int32_t) * (size_t)At->nnz, cudaMemcpyDeviceToHost, s));
+                if (vals) MXG_CUDA_TRY(cudaMemcpyAsync(x2, At->d_x64, sizeof(double) * (size_t)At->nnz, cudaMemcpyDeviceToHost, s));
+            }
+            MXG_CUDA_TRY(cudaStreamSynchronize(s));
+            return MXG_OK;
+        };
+        rc = body();
+    }
+    cudaStreamSynchronize(st->stream);
+    free_handle(A);
+    free_handle(At);
+    return rc;
+}
+
+} /* extern "C" */

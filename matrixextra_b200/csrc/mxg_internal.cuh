@@ -1,0 +1,111 @@
+// mxg_internal.cuh — shared declarations of libmxgpu.so (not part of the public C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/mxgpu.h"
+
+namespace mxg {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: every public entry point returns a status; the message is kept per thread
+// ------------------------------------------------------------------------------------------------
+std::string &last_error_ref();
+int fail(int code, const char *fmt, ...);
+
+#define MXG_CUDA_TRY(expr)                                                                           \
+    do {                                                                                             \
+        cudaError_t mxg_e_ = (expr);                                                                 \
+        if (mxg_e_ != cudaSuccess)                                                                   \
+            return ::mxg::fail(MXG_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,    \
+                               cudaGetErrorString(mxg_e_));                                          \
+    } while (0)
+
+#define MXG_TRY(expr)                       \
+    do {                                    \
+        int mxg_rc_ = (expr);               \
+        if (mxg_rc_ != MXG_OK) return mxg_rc_; \
+    } while (0)
+
+extern std::atomic<unsigned long long> g_launches;
+
+// launch + count + cheap launch-error check (no sync)
+#define MXG_LAUNCH(kernel, grid, block, smem, stream, ...)                                           \
+    do {                                                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                  \
+        ::mxg::g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        MXG_CUDA_TRY(cudaGetLastError());                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// options (mxg_set_option)
+// ------------------------------------------------------------------------------------------------
+struct Options {
+    long piece = 1024;        // nnz per long-row piece; rows longer than this are split
+    long spmm_lpr = 0;        // 0 = auto
+    long spmm_cpl = 0;        // 0 = auto
+    long spmm_block_rows = 0; // 0 = auto
+    long spmv_lpr = 0;        // 0 = auto
+    long h2d_chunk_mb = 64;   // staging chunk of the level-1 pipeline
+};
+Options &options();
+
+// ------------------------------------------------------------------------------------------------
+// device-resident CSR
+// ------------------------------------------------------------------------------------------------
+} // namespace mxg
+
+struct mxg_csr_s {
+    int device = 0;
+    int m = 0, K = 0;
+    int64_t nnz = 0;
+    int32_t base = 0; // p[0] (0 for every valid R matrix; kept so offsets stay exact otherwise)
+    const int32_t *d_p = nullptr;
+    const int32_t *d_j = nullptr;
+    const double *d_x64 = nullptr;
+    const float *d_x32 = nullptr;
+    bool owns = false; // arrays were allocated by the library
+
+    // row statistics (K7)
+    int piece = 1024;
+    int max_len = 0;
+    int n_long = 0;
+    int n_pieces = 0;
+    int32_t *d_long_rows = nullptr;  // [n_long] row id
+    int32_t *d_long_first = nullptr; // [n_long] first piece slot
+    int32_t *d_long_np = nullptr;    // [n_long] number of pieces
+    int32_t *d_piece_row = nullptr;  // [n_pieces]
+    int32_t *d_piece_k = nullptr;    // [n_pieces] piece number inside its row
+
+    // partial-sum workspace for long rows (grow-only)
+    void *d_partial = nullptr;
+    size_t partial_bytes = 0;
+};
+
+namespace mxg {
+
+// layout.cu
+int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream);
+int convert_f64_to_f32(const double *d_src, float *d_dst, size_t n, cudaStream_t stream);
+int exclusive_scan_i32(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t stream); // out[i] = sum in[0..i)
+int ensure_partial(mxg_csr_s *h, size_t bytes);
+
+// spmm.cu
+int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
+                void *d_Out, size_t ldc, cudaStream_t stream);
+// spmv.cu
+int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream);
+// transpose.cu
+int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src,
+                           void *d_dst, size_t ld_dst, cudaStream_t stream);
+int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t *d_j,
+                   const double *d_x64, const float *d_x32,
+                   int32_t *d_p2, int32_t *d_i2, double *d_x64o, float *d_x32o, cudaStream_t stream);
+
+inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+} // namespace mxg

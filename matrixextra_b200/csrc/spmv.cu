@@ -1,0 +1,290 @@
+// spmv.cu — K3: CSR x dense vector for sm_100a.  Replaces matmul_csr_dvec<> (src/matmul.cpp:381-419)
+// and its four exports (421-483), including the NA rules for integer / logical vectors (406-411).
+//
+// A team of LPR lanes owns a row; its lanes stride over the row's stored entries (coalesced index and
+// value loads, U=4 independent gathers of y in flight per lane), then a width-LPR butterfly adds the
+// lane sums.  Teams of a warp run in lock-step over the longest row.  Rows longer than `piece`
+// entries use the same piece tables as the SpMM kernels: one warp per piece writes a partial sum and
+// a fix-up pass adds a row's pieces in piece order (deterministic, no atomics).
+// The sum is a tree over lanes instead of the reference's left-to-right chain: identical up to
+// reassociation (<= 1e-12 relative for fp64, see tests).  Accumulation is always in double; the
+// float32 variant narrows once at the end (the reference narrows after every term, 403/476).
+// Bound: HBM for the streamed CSR (12 B per entry) plus one 32-byte L2 sector per gathered y element.
+#include "mxg_internal.cuh"
+
+#include <limits.h>
+
+namespace mxg {
+
+__device__ __forceinline__ double na_real()
+{
+    return __longlong_as_double(0x7FF00000000007A2LL); // R's NA_real_ (payload 1954)
+}
+
+template <int YTYPE>
+struct YTraits;
+template <>
+struct YTraits<MXG_Y_NUMERIC> {
+    typedef double elem;
+    typedef double out;
+    static __device__ __forceinline__ double value(double v, bool &na) { return v; }
+};
+template <>
+struct YTraits<MXG_Y_INTEGER> {
+    typedef int elem;
+    typedef double out;
+    static __device__ __forceinline__ double value(int v, bool &na)
+    {
+        if (v == INT_MIN) { na = true; return na_real(); }
+        return (double)v;
+    }
+};
+template <>
+struct YTraits<MXG_Y_LOGICAL> {
+    typedef int elem;
+    typedef double out;
+    static __device__ __forceinline__ double value(int v, bool &na)
+    {
+        if (v == INT_MIN) { na = true; return na_real(); }
+        return v != 0 ? 1.0 : 0.0;
+    }
+};
+template <>
+struct YTraits<MXG_Y_FLOAT32> {
+    typedef float elem;
+    typedef float out;
+    static __device__ __forceinline__ double value(float v, bool &na) { return (double)v; }
+};
+
+// lane-strided partial dot product of entries [a, b); maxlen = warp-wide max of (b - a)
+template <int YTYPE, typename XT, int LPR>
+__device__ __forceinline__ double team_dot(const int a, const int b, const int maxlen, const int l,
+                                           const int32_t *__restrict__ j, const XT *__restrict__ x,
+                                           const typename YTraits<YTYPE>::elem *__restrict__ y, bool &na)
+{
+    constexpr int U = 4;
+    double acc = 0.0;
+    for (int e0 = 0; e0 < maxlen; e0 += LPR * U) {
+        int jj[U];
+        double xx[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int e = a + e0 + u * LPR + l;
+            ok[u] = e < b;
+            jj[u] = 0;
+            xx[u] = 0.0;
+            if (ok[u]) {
+                jj[u] = __ldg(j + e);
+                xx[u] = (double)__ldg(x + e);
+            }
+        }
+        double yy[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            yy[u] = 0.0;
+            if (ok[u]) yy[u] = YTraits<YTYPE>::value(__ldg(y + jj[u]), na);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ok[u]) acc = fma(xx[u], yy[u], acc);
+    }
+    return acc;
+}
+
+template <int LPR>
+__device__ __forceinline__ double team_reduce(double v)
+{
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d, LPR);
+    return v;
+}
+
+template <int LPR>
+__device__ __forceinline__ bool team_any(bool f)
+{
+    int v = f ? 1 : 0;
+#pragma unroll
+    for (int d = LPR / 2; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d, LPR);
+    return v != 0;
+}
+
+template <int YTYPE>
+__device__ __forceinline__ void store_result(typename YTraits<YTYPE>::out *out, int row, double v, bool na)
+{
+    // a row that met an NA keeps R's NA payload (x86 propagates it through the reference's sum)
+    if (na && v != v) v = na_real();
+    out[row] = (typename YTraits<YTYPE>::out)v;
+}
+
+struct SpmvArgs {
+    int m;
+    const int32_t *p;
+    const int32_t *j;
+    const void *x;
+    const void *y;
+    void *out;
+    int piece;
+    int n_pieces;
+    int piece_blocks;
+    const int32_t *piece_row;
+    const int32_t *piece_k;
+    double *partial;   // [n_pieces]
+    int *partial_na;   // [n_pieces]
+    int rows_per_team; // rows each team walks inside its CTA
+};
+
+template <int YTYPE, typename XT, int LPR>
+__global__ void __launch_bounds__(256) k_spmv(const SpmvArgs g)
+{
+    typedef typename YTraits<YTYPE>::elem YE;
+    typedef typename YTraits<YTYPE>::out OE;
+    constexpr int TEAMS = 256 / LPR;
+    const int32_t *__restrict__ p = g.p;
+    const int32_t *__restrict__ j = g.j;
+    const XT *__restrict__ x = static_cast<const XT *>(g.x);
+    const YE *__restrict__ y = static_cast<const YE *>(g.y);
+    OE *__restrict__ out = static_cast<OE *>(g.out);
+
+    if ((int)blockIdx.x < g.piece_blocks) {
+        // one full warp per long-row piece
+        const int lane = threadIdx.x & 31;
+        const int pc = blockIdx.x * 8 + (threadIdx.x >> 5);
+        if (pc >= g.n_pieces) return; // warp-uniform
+        const int row = g.piece_row[pc];
+        const int a = p[row] + g.piece_k[pc] * g.piece;
+        const int b = min(a + g.piece, p[row + 1]);
+        bool na = false;
+        double acc = team_dot<YTYPE, XT, 32>(a, b, b - a, lane, j, x, y, na);
+        acc = team_reduce<32>(acc);
+        na = team_any<32>(na);
+        if (lane == 0) {
+            g.partial[pc] = acc;
+            g.partial_na[pc] = na ? 1 : 0;
+        }
+        return;
+    }
+
+    const int team = threadIdx.x / LPR;
+    const int l = threadIdx.x % LPR;
+    const int rb = blockIdx.x - g.piece_blocks;
+    const int block_rows = TEAMS * g.rows_per_team;
+    const int row0 = rb * block_rows;
+    for (int base = 0; base < block_rows; base += TEAMS) {
+        const int row = row0 + base + team;
+        int a = 0, b = 0;
+        bool store = false;
+        if (row < g.m) {
+            a = p[row];
+            b = p[row + 1];
+            store = true;
+            if (b - a > g.piece) {
+                b = a;
+                store = false;
+            }
+        }
+        const int maxlen = __reduce_max_sync(0xffffffffu, b - a);
+        bool na = false;
+        double acc = team_dot<YTYPE, XT, LPR>(a, b, maxlen, l, j, x, y, na);
+        acc = team_reduce<LPR>(acc);
+        na = team_any<LPR>(na);
+        if (store && l == 0) store_result<YTYPE>(out, row, acc, na);
+    }
+}
+
+template <int YTYPE>
+__global__ void __launch_bounds__(128) k_spmv_fixup(int n_long, const int32_t *__restrict__ long_rows,
+                                                    const int32_t *__restrict__ long_first,
+                                                    const int32_t *__restrict__ long_np,
+                                                    const double *__restrict__ partial,
+                                                    const int *__restrict__ partial_na,
+                                                    typename YTraits<YTYPE>::out *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_long) return;
+    const int first = long_first[i], np = long_np[i];
+    double s = 0.0;
+    bool na = false;
+    for (int k = 0; k < np; k++) {
+        s += partial[first + k];
+        na = na || (partial_na[first + k] != 0);
+    }
+    store_result<YTYPE>(out, long_rows[i], s, na);
+}
+
+template <int YTYPE, typename XT>
+static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, void *d_out, cudaStream_t stream)
+{
+    SpmvArgs args;
+    args.m = A->m;
+    args.p = A->d_p;
+    args.j = A->d_j;
+    args.x = d_x;
+    args.y = d_y;
+    args.out = d_out;
+    args.piece = A->piece;
+    args.n_pieces = A->n_pieces;
+    args.piece_blocks = ceil_div_i(A->n_pieces, 8);
+    args.piece_row = A->d_piece_row;
+    args.piece_k = A->d_piece_k;
+    args.partial = nullptr;
+    args.partial_na = nullptr;
+    if (A->n_pieces > 0) {
+        // doubles first, flags after (16 bytes per piece reserved)
+        MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * 16));
+        args.partial = static_cast<double *>(A->d_partial);
+        args.partial_na = reinterpret_cast<int *>(static_cast<double *>(A->d_partial) + A->n_pieces);
+    }
+
+    int lpr = (int)options().spmv_lpr;
+    if (lpr <= 0) {
+        // team size from the mean row length: enough entries per lane to amortise the butterfly
+        const double mean = A->m > 0 ? (double)A->nnz / (double)A->m : 0.0;
+        if (mean <= 6) lpr = 2;
+        else if (mean <= 12) lpr = 4;
+        else if (mean <= 48) lpr = 8;
+        else if (mean <= 192) lpr = 16;
+        else lpr = 32;
+    }
+    args.rows_per_team = 4;
+#define MXG_SPMV(L)                                                                              \
+    if (lpr == L) {                                                                              \
+        const int block_rows = (256 / L) * args.rows_per_team;                                   \
+        const int grid = args.piece_blocks + ceil_div_i(A->m, block_rows);                       \
+        MXG_LAUNCH((k_spmv<YTYPE, XT, L>), grid, 256, 0, stream, args);                          \
+    } else
+    MXG_SPMV(2) MXG_SPMV(4) MXG_SPMV(8) MXG_SPMV(16) MXG_SPMV(32)
+    {
+        return fail(MXG_ERR_ARG, "spmv: unsupported team size %d", lpr);
+    }
+#undef MXG_SPMV
+    if (A->n_long > 0) {
+        MXG_LAUNCH((k_spmv_fixup<YTYPE>), ceil_div_i(A->n_long, 128), 128, 0, stream, A->n_long, A->d_long_rows,
+                   A->d_long_first, A->d_long_np, args.partial, args.partial_na,
+                   static_cast<typename YTraits<YTYPE>::out *>(d_out));
+    }
+    return MXG_OK;
+}
+
+template <int YTYPE>
+static int spmv_values(const mxg_csr_s *A, const void *d_y, void *d_out, cudaStream_t stream)
+{
+    if (A->d_x64) return spmv_dispatch<YTYPE, double>(A, A->d_x64, d_y, d_out, stream);
+    if (A->d_x32 && YTYPE == MXG_Y_FLOAT32) return spmv_dispatch<YTYPE, float>(A, A->d_x32, d_y, d_out, stream);
+    if (A->nnz == 0) return spmv_dispatch<YTYPE, double>(A, nullptr, d_y, d_out, stream);
+    return fail(MXG_ERR_UNSUPPORTED, "spmv: handle holds no float64 values");
+}
+
+int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream)
+{
+    if (A->m == 0) return MXG_OK;
+    switch (ytype) {
+    case MXG_Y_NUMERIC: return spmv_values<MXG_Y_NUMERIC>(A, d_y, d_out, stream);
+    case MXG_Y_INTEGER: return spmv_values<MXG_Y_INTEGER>(A, d_y, d_out, stream);
+    case MXG_Y_LOGICAL: return spmv_values<MXG_Y_LOGICAL>(A, d_y, d_out, stream);
+    case MXG_Y_FLOAT32: return spmv_values<MXG_Y_FLOAT32>(A, d_y, d_out, stream);
+    default: return fail(MXG_ERR_ARG, "spmv: bad ytype %d", ytype);
+    }
+}
+
+} // namespace mxg

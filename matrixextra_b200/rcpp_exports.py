@@ -1,0 +1,141 @@
+"""Python mirror of the ten Rcpp exports on the multiplication path, with the reference's names,
+argument order and array layouts (src/matmul.cpp:221-483; R wrappers R/RcppExports.R:132-170),
+implemented on the CUDA library through the level-1 (host buffers) C ABI.
+
+This file plays the role of rglue/matmul_gpu_glue.cpp (the real Rcpp glue, which cannot be executed
+in an image without R): same dimension inference from the argument shapes, same zero-copy borrowing
+of inputs, a freshly allocated column-major output, errors raised from mxg_last_error().
+``nthreads`` and ``ncols_Y`` are accepted and ignored, as ``ncols_Y`` already is in the reference
+(src/matmul.cpp:259).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_ROWS_CONTIGUOUS, MXG_Y_FLOAT32, MXG_Y_INTEGER,
+                   MXG_Y_LOGICAL, MXG_Y_NUMERIC)
+
+
+def _vp(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _csr(p, j, x):
+    return (np.ascontiguousarray(p, dtype=np.int32), np.ascontiguousarray(j, dtype=np.int32),
+            np.ascontiguousarray(x, dtype=np.float64))
+
+
+def _fmat(a, dtype):
+    a = np.asarray(a, dtype=dtype)
+    if a.ndim != 2:
+        raise ValueError("expected a matrix")
+    return np.asfortranarray(a)
+
+
+def _dense_times_tcsr(X_colmajor, indptr, indices, values, dtype):
+    """Out(a x rows, column-major) = X(a x K) . t(S) where S is given by rows (CSR) — the kernel call of
+    matmul_dense_csc / tcrossprod_dense_csr (src/matmul.cpp:188-281): a rows-contiguous product with
+    n = nrow(X), ldb = ldc = nrow(X)."""
+    np_t = np.float64 if dtype == MXG_F64 else np.float32
+    X = _fmat(X_colmajor, np_t)
+    p, j, x = _csr(indptr, indices, values)
+    a, K = X.shape
+    rows = p.size - 1
+    out = np.empty((a, rows), dtype=np_t, order="F")
+    _lib.call("mxg_spmm_csr_dense", dtype, MXG_ROWS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, rows, K, a,
+              _vp(p), _vp(j), _vp(x), _vp(X), max(a, 1), _vp(out), max(a, 1))
+    return out
+
+
+def matmul_dense_csc_numeric(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1):
+    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F64)
+
+
+def matmul_dense_csc_float32(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1):
+    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F32)
+
+
+def tcrossprod_dense_csr_numeric(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0):
+    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F64)
+
+
+def tcrossprod_dense_csr_float32(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0):
+    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F32)
+
+
+def _csr_times_tdense(indptr, indices, values, Y_colmajor, dtype):
+    """Out(m x n, column-major) = A_csr(m x K) . t(Y), Y (n x K) column-major — tcrossprod_csr_dense
+    (src/matmul.cpp:316-343): column-major output with ldb = nrow(Y), ldc = m."""
+    np_t = np.float64 if dtype == MXG_F64 else np.float32
+    Y = _fmat(Y_colmajor, np_t)
+    p, j, x = _csr(indptr, indices, values)
+    n, K = Y.shape
+    m = p.size - 1
+    out = np.empty((m, n), dtype=np_t, order="F")
+    _lib.call("mxg_spmm_csr_dense", dtype, MXG_COLS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, m, K, n,
+              _vp(p), _vp(j), _vp(x), _vp(Y), max(n, 1), _vp(out), max(m, 1))
+    return out
+
+
+def tcrossprod_csr_dense_numeric(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1):
+    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F64)
+
+
+def tcrossprod_csr_dense_float32(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1):
+    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F32)
+
+
+def _csr_dvec(indptr, indices, values, y, ytype, y_np, out_np):
+    p, j, x = _csr(indptr, indices, values)
+    y = np.ascontiguousarray(y, dtype=y_np)
+    m = p.size - 1
+    out = np.empty(m, dtype=out_np)
+    # the reference takes K from nowhere (it trusts the indices); here K = length(y) bounds them
+    _lib.call("mxg_spmv_csr", ytype, m, int(y.size), _vp(p), _vp(j), _vp(x), _vp(y), _vp(out))
+    return out
+
+
+def matmul_csr_dvec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_NUMERIC, np.float64, np.float64)
+
+
+def matmul_csr_dvec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_INTEGER, np.int32, np.float64)
+
+
+def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_LOGICAL, np.int32, np.float64)
+
+
+def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32)
+
+
+# ---- additions beyond the reference's exports -----------------------------
+
+def csr_to_csc(m, K, indptr, indices, values):
+    """Deep CSR -> CSC on device, bit-exact with Matrix's `as(x, "CsparseMatrix")` (R/conversions.R:390-392)."""
+    p, j, x = _csr(indptr, indices, values)
+    p2 = np.empty(K + 1, dtype=np.int32)
+    i2 = np.empty(j.size, dtype=np.int32)
+    x2 = np.empty(j.size, dtype=np.float64)
+    _lib.call("mxg_csr2csc", int(m), int(K), _vp(p), _vp(j), _vp(x), _vp(p2), _vp(i2), _vp(x2))
+    return p2, i2, x2
+
+
+def crossprod_csr_dense(indptr, indices, values, ncols_X, Y_colmajor, dtype=MXG_F64):
+    """Out(K x n, column-major) = t(A_csr(m x K)) . Y(m x n): device transpose + gather product."""
+    np_t = np.float64 if dtype == MXG_F64 else np.float32
+    Y = _fmat(Y_colmajor, np_t)
+    p, j, x = _csr(indptr, indices, values)
+    m, n = Y.shape
+    if p.size - 1 != m:
+        raise ValueError("Matrix dimensions do not match.")
+    K = int(ncols_X)
+    out = np.empty((K, n), dtype=np_t, order="F")
+    _lib.call("mxg_spmm_csrT_dense", dtype, MXG_COLS_CONTIGUOUS, MXG_COLS_CONTIGUOUS, m, K, n,
+              _vp(p), _vp(j), _vp(x), _vp(Y), max(m, 1), _vp(out), max(K, 1))
+    return out

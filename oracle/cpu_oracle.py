@@ -205,6 +205,7 @@ class Ref:
         self.max_threads = int(self.lib.mxref_max_threads())
         self.nthreads = int(nthreads or 1)
         self.lib.mxref_last_result.restype = C.c_void_p
+        self.copy_result = True  # bench.py sets False: time the reference without an extra result copy
         self.lib.mxref_last_result.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
 
     @staticmethod
@@ -219,7 +220,7 @@ class Ref:
             return np.zeros((nr.value, nc.value), dtype=dtype, order="F")
         buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr)
         arr = np.frombuffer(buf, dtype=dtype).reshape((nr.value, nc.value), order="F")
-        return arr.copy(order="F") if copy else arr
+        return arr.copy(order="F") if (copy and self.copy_result) else arr
 
     def _dense_first(self, fn, X, dtype, p, j, x, nt, extra=()):
         X = _fdense(X, dtype)

@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Kernel-variant sweep on device-resident synthetic inputs (development tool, not a bench line).
+Prints one JSON object per measurement to stdout."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from bench import WORKLOADS, _time_ms, w_alg_bytes  # noqa: E402
+from matrixextra_b200 import _lib  # noqa: E402
+from matrixextra_b200._lib import (MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_KEEP_F32, MXG_KEEP_F64,  # noqa: E402
+                                   MXG_ROWS_CONTIGUOUS)
+from matrixextra_b200.device import DeviceCSR  # noqa: E402
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--what", default="spmm32,spmm64,spmv,piece,transpose")
+    args = ap.parse_args()
+    what = set(args.what.split(","))
+    torch.cuda.set_device(0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    wl = WORKLOADS["cfg3"]
+    m, K, n = wl["m"], wl["K"], 64
+
+    def spmm_case(A, dtype, layout, n, tag, **opts):
+        tdt = torch.float32 if dtype == MXG_F32 else torch.float64
+        s = 4 if dtype == MXG_F32 else 8
+        B = torch.randn(A.K, n, device="cuda", dtype=tdt, generator=g)
+        out = torch.empty(A.m * n, device="cuda", dtype=tdt)
+        for k, v in opts.items():
+            _lib.set_option(k, v)
+        try:
+            ms = _time_ms(lambda: A.spmm(B, out, n, dtype, layout), args.steps, 3)
+            emit(case=tag, n=n, dtype="f32" if dtype == MXG_F32 else "f64", layout=layout, opts=opts, ms=ms,
+                 gflops=2.0 * A.nnz * n / ms / 1e6, eff_gbps=w_alg_bytes(A.m, A.K, A.nnz, n, s) / ms / 1e6)
+        except Exception as e:  # noqa: BLE001
+            emit(case=tag, opts=opts, error=str(e))
+        for k in opts:
+            _lib.set_option(k, 0)
+
+    if what & {"spmm32", "spmm64", "piece"}:
+        A = DeviceCSR.synth(m, K, wl["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32 | MXG_KEEP_F64)
+        emit(case="matrix", m=A.m, K=A.K, nnz=A.nnz, n_long=A.n_long, n_pieces=A.n_pieces, max_len=A.max_len)
+        if "spmm32" in what:
+            for lpr, cpl in ((16, 1), (8, 2), (32, 1), (4, 2), (16, 2)):
+                for br in (0, 32, 128):
+                    spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm", spmm_lpr=lpr, spmm_cpl=cpl, spmm_block_rows=br)
+            spmm_case(A, MXG_F32, MXG_COLS_CONTIGUOUS, 64, "cfg3_f32_cm")
+            for nn in (8, 16, 32, 128, 256):
+                spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, nn, "f32_rm_n")
+        if "spmm64" in what:
+            for lpr, cpl in ((32, 1), (16, 2), (8, 2), (16, 1)):
+                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm", spmm_lpr=lpr, spmm_cpl=cpl)
+            spmm_case(A, MXG_F64, MXG_COLS_CONTIGUOUS, 64, "k64_f64_cm")
+            for nn in (8, 16, 32, 128):
+                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, nn, "f64_rm_n")
+        A.free()
+        if "piece" in what:
+            for piece in (256, 512, 2048, 4096, 65536):
+                _lib.set_option("piece", piece)
+                A = DeviceCSR.synth(m, K, wl["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32)
+                spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, f"cfg3_f32_rm_piece{piece}")
+                A.free()
+            _lib.set_option("piece", 1024)
+
+    if "spmv" in what:
+        w2 = WORKLOADS["cfg2"]
+        for piece in (1024, 4096):
+            _lib.set_option("piece", piece)
+            A = DeviceCSR.synth(w2["m"], w2["K"], w2["nnz"], 1, 0, seed=1002, keep=MXG_KEEP_F64)
+            y = torch.randn(A.K, device="cuda", dtype=torch.float64, generator=g)
+            o = torch.empty(A.m, device="cuda", dtype=torch.float64)
+            for lpr in (4, 8, 16, 32):
+                _lib.set_option("spmv_lpr", lpr)
+                ms = _time_ms(lambda: A.spmv(y, o), args.steps, 3)
+                emit(case="cfg2_spmv", piece=piece, lpr=lpr, ms=ms, gflops=2.0 * A.nnz / ms / 1e6,
+                     eff_gbps=w_alg_bytes(A.m, A.K, A.nnz, 1, 8) / ms / 1e6)
+            _lib.set_option("spmv_lpr", 0)
+            A.free()
+        _lib.set_option("piece", 1024)
+
+    if "transpose" in what:
+        w4 = WORKLOADS["cfg4"]
+        A = DeviceCSR.synth(w4["m"], w4["K"], w4["nnz"], 1, 0, seed=1004, keep=MXG_KEEP_F64)
+
+        def tr():
+            t = A.transpose(keep=MXG_KEEP_F64)
+            t.free()
+        ms = _time_ms(tr, 3, 1)
+        emit(case="cfg4_transpose", ms=ms, alg_gbps=(24 * A.nnz + 4 * (A.m + A.K + 2)) / ms / 1e6)
+        A.free()
+
+    # raw copy bandwidth on this box for context (same method as MEASURED_PEAKS.json)
+    a = torch.empty(1 << 30, device="cuda", dtype=torch.bfloat16)
+    b = torch.empty_like(a)
+    ms = _time_ms(lambda: b.copy_(a), 10, 3)
+    emit(case="copy_bw", gbps=2 * a.numel() * 2 / ms / 1e6)
+
+
+if __name__ == "__main__":
+    main()
