@@ -142,6 +142,10 @@ int mxg_csr_info(mxg_csr_t handle, int64_t info[6]);
 int mxg_csr_device_arrays(mxg_csr_t handle, const int32_t **d_p, const int32_t **d_j,
                           const double **d_x64, const float **d_x32);
 
+/* Copy the handle's arrays back to host buffers (any of them may be NULL): p[m+1] rebased to start at 0,
+ * j[nnz], x[nnz] (float64; widened from the float32 copy when only that is kept). */
+int mxg_csr_download(mxg_csr_t handle, int32_t *p, int32_t *j, double *x);
+
 /* Same products as level 1 with every operand already in device memory; asynchronous on `stream`
  * (a cudaStream_t passed as void*, NULL = legacy default stream). */
 int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,

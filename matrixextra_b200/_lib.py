@@ -43,6 +43,7 @@ _SIGNATURES = {
     "mxg_csr_free": [_vp],
     "mxg_csr_info": [_vp, C.POINTER(_i64)],
     "mxg_csr_device_arrays": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "mxg_csr_download": [_vp, _vp, _vp, _vp],
     "mxg_dev_spmm": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_spmv": [_vp, _i32, _vp, _vp, _vp],
     "mxg_dev_csr2csc": [_vp, _i32, _vp, C.POINTER(_vp)],

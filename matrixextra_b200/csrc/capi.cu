@@ -381,6 +381,32 @@ int mxg_csr_device_arrays(mxg_csr_t h, const int32_t **d_p, const int32_t **d_j,
     return MXG_OK;
 }
 
+int mxg_csr_download(mxg_csr_t h, int32_t *p, int32_t *j, double *x)
+{
+    if (!h) return fail(MXG_ERR_ARG, "csr_download: NULL handle");
+    MXG_CUDA_TRY(cudaDeviceSynchronize());
+    if (p) {
+        MXG_CUDA_TRY(cudaMemcpy(p, h->d_p, sizeof(int32_t) * ((size_t)h->m + 1), cudaMemcpyDeviceToHost));
+        if (h->base != 0)
+            for (int r = 0; r <= h->m; r++) p[r] -= h->base;
+    }
+    if (h->nnz > 0) {
+        if (j) MXG_CUDA_TRY(cudaMemcpy(j, h->d_j + h->base, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+        if (x) {
+            if (h->d_x64) {
+                MXG_CUDA_TRY(cudaMemcpy(x, h->d_x64 + h->base, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+            } else if (h->d_x32) {
+                std::vector<float> tmp((size_t)h->nnz);
+                MXG_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_x32 + h->base, sizeof(float) * (size_t)h->nnz, cudaMemcpyDeviceToHost));
+                for (size_t e = 0; e < (size_t)h->nnz; e++) x[e] = (double)tmp[e];
+            } else {
+                for (size_t e = 0; e < (size_t)h->nnz; e++) x[e] = 1.0; // pattern matrix
+            }
+        }
+    }
+    return MXG_OK;
+}
+
 int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
                  void *d_Out, size_t ldc, void *stream)
 {

@@ -112,8 +112,9 @@ __device__ __forceinline__ bool team_any(bool f)
 template <int YTYPE>
 __device__ __forceinline__ void store_result(typename YTraits<YTYPE>::out *out, int row, double v, bool na)
 {
-    // a row that met an NA keeps R's NA payload (x86 propagates it through the reference's sum)
-    if (na && v != v) v = na_real();
+    // a row that met an NA keeps R's NA payload: x86 propagates NA_real_ through the reference's sum as
+    // the quieted NaN 0x7FF80000000007A2 (low word still 1954, so R's is.na() holds)
+    if (na && v != v) v = __longlong_as_double(0x7FF80000000007A2LL);
     out[row] = (typename YTraits<YTYPE>::out)v;
 }
 

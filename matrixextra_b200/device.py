@@ -78,18 +78,12 @@ class DeviceCSR:
 
     def to_host(self):
         """Copy indptr / indices / float64 values back (tests, CPU-baseline sampling)."""
-        import torch
-        d_p, d_j, d_x64, d_x32 = self.device_arrays()
-        p = _copy_from_device(d_p, self.m + 1, np.int32)
-        base = int(p[0])
-        j = _copy_from_device(d_j + 4 * base, self.nnz, np.int32)
-        if d_x64:
-            x = _copy_from_device(d_x64 + 8 * base, self.nnz, np.float64)
-        elif d_x32:
-            x = _copy_from_device(d_x32 + 4 * base, self.nnz, np.float32).astype(np.float64)
-        else:
-            x = np.ones(self.nnz)
-        return p - base, j, x
+        p = np.empty(self.m + 1, dtype=np.int32)
+        j = np.empty(self.nnz, dtype=np.int32)
+        x = np.empty(self.nnz, dtype=np.float64)
+        _lib.call("mxg_csr_download", self._h, C.c_void_p(p.ctypes.data), C.c_void_p(j.ctypes.data),
+                  C.c_void_p(x.ctypes.data))
+        return p, j, x
 
     # -- products -----------------------------------------------------------------------------------
     def spmm(self, B_t, out_t, n, dtype, out_layout=MXG_ROWS_CONTIGUOUS, b_layout=MXG_ROWS_CONTIGUOUS,
@@ -110,21 +104,6 @@ class DeviceCSR:
         h = C.c_void_p()
         _lib.call("mxg_dev_csr2csc", self._h, int(keep), _stream_ptr(stream), C.byref(h))
         return DeviceCSR(h.value)
-
-
-def _copy_from_device(addr: int, count: int, dtype) -> np.ndarray:
-    import torch
-    out = np.empty(count, dtype=dtype)
-    if count == 0:
-        return out
-    nbytes = out.nbytes
-    # torch is only used as a cudaMemcpy here
-    cudart = torch.cuda.cudart()
-    torch.cuda.synchronize()
-    rc = cudart.cudaMemcpy(out.ctypes.data, addr, nbytes, 2)  # cudaMemcpyDeviceToHost
-    if int(rc) != 0:
-        raise RuntimeError(f"cudaMemcpy D2H failed: {rc}")
-    return out
 
 
 def row_partition(p_host: np.ndarray, parts: int) -> np.ndarray:

@@ -1,0 +1,59 @@
+"""CPU tests of the host-side mirror of R/matmul.R: dispatch table, dimension checks and their
+messages, class handling — everything that runs before the first CUDA call."""
+import numpy as np
+import pytest
+
+from helpers import rsparsematrix
+
+
+def test_dimension_checks_fire_before_any_device_work():
+    from matrixextra_b200 import crossprod, dgCMatrix, dgRMatrix, float32, matmul, tcrossprod
+    A = dgRMatrix.from_scipy(rsparsematrix(10, 7, 0.3, 0))
+    Ac = dgCMatrix.from_scipy(rsparsematrix(7, 5, 0.3, 0, "csc"))
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):  # R/matmul.R:144-145
+        matmul(A, np.zeros((8, 3), order="F"))
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):
+        tcrossprod(A, np.zeros((3, 8), order="F"))
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):
+        tcrossprod(np.zeros((3, 8), order="F"), A)
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):
+        matmul(np.zeros((3, 8), order="F"), Ac)
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):
+        crossprod(A, np.zeros((11, 2), order="F"))
+    with pytest.raises(ValueError, match="Matrix dimensions do not match."):
+        tcrossprod(A, float32(np.zeros((3, 8), dtype=np.float32)))
+    with pytest.raises(ValueError, match="Matrix-vector dimensions do not match."):  # R/matmul.R:546-547
+        matmul(A, np.zeros(8))
+    with pytest.raises(TypeError):
+        matmul(A, A)
+    with pytest.raises(NotImplementedError):  # single-column outer product: outside the scoped path
+        matmul(dgRMatrix.from_scipy(rsparsematrix(5, 1, 0.9, 1)), np.zeros(1))
+
+
+def test_check_valid_matrix_messages():
+    from matrixextra_b200.classes import check_valid_matrix, dgRMatrix
+    ok = dgRMatrix([0, 1, 2], [0, 1], [1.0, 2.0], (2, 2))
+    check_valid_matrix(ok)
+    with pytest.raises(ValueError, match="'p' doesn't match with dimension"):
+        check_valid_matrix(dgRMatrix([0, 1, 2], [0, 1], [1.0, 2.0], (3, 2)))
+    with pytest.raises(ValueError, match="'p' has bad start/end"):
+        check_valid_matrix(dgRMatrix([1, 1, 2], [0, 1], [1.0, 2.0], (2, 2)))
+    with pytest.raises(ValueError, match="lengths of indices and values differ"):
+        check_valid_matrix(dgRMatrix([0, 1, 2], [0, 1], [1.0], (2, 2)))
+
+
+def test_shallow_transpose_relabels_without_copying():
+    from matrixextra_b200 import dgCMatrix, dgRMatrix, t_shallow
+    A = dgRMatrix.from_scipy(rsparsematrix(6, 4, 0.5, 2))
+    At = t_shallow(A)
+    assert isinstance(At, dgCMatrix) and At.Dim == (4, 6)
+    assert At.p is A.p and At.i is A.j and At.x is A.x
+    assert np.array_equal(At.to_scipy().toarray(), A.to_scipy().toarray().T)
+    assert isinstance(t_shallow(At), dgRMatrix)
+
+
+def test_float32_container_keeps_column_major_binary32():
+    from matrixextra_b200 import float32
+    f = float32(np.arange(6, dtype=np.float64).reshape(2, 3))
+    assert f.Data.dtype == np.float32 and f.Data.flags.f_contiguous and not f.is_vector()
+    assert float32(np.zeros(4)).is_vector()
