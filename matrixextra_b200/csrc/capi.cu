@@ -40,18 +40,22 @@ static int current_state(DeviceState **out)
 static int free_handle(mxg_csr_s *h)
 {
     if (!h) return MXG_OK;
+    // stream-ordered frees on the handle's stream: cheap (pool) and ordered after the handle's own work;
+    // the caller guarantees nothing on OTHER streams still uses the handle
+    cudaStream_t s = h->stream;
+    auto rel = [s](const void *q) { if (q) cudaFreeAsync(const_cast<void *>(q), s); };
     if (h->owns) {
-        cudaFree(const_cast<int32_t *>(h->d_p));
-        cudaFree(const_cast<int32_t *>(h->d_j));
-        cudaFree(const_cast<double *>(h->d_x64));
-        cudaFree(const_cast<float *>(h->d_x32));
+        rel(h->d_p);
+        rel(h->d_j);
+        rel(h->d_x64);
+        rel(h->d_x32);
     }
-    cudaFree(h->d_long_rows);
-    cudaFree(h->d_long_first);
-    cudaFree(h->d_long_np);
-    cudaFree(h->d_piece_row);
-    cudaFree(h->d_piece_k);
-    cudaFree(h->d_partial);
+    rel(h->d_long_rows);
+    rel(h->d_long_first);
+    rel(h->d_long_np);
+    rel(h->d_piece_row);
+    rel(h->d_piece_k);
+    rel(h->d_partial);
     delete h;
     return MXG_OK;
 }
@@ -88,9 +92,10 @@ static int upload_csr(int m, int K, const int32_t *p, const int32_t *j, const do
             return fail(MXG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));               \
         }                                                                                            \
     } while (0)
-    MXG_UP_TRY(cudaMalloc(&d_p, sizeof(int32_t) * ((size_t)m + 1)));
+    h->stream = stream;
+    MXG_UP_TRY(cudaMallocAsync(&d_p, sizeof(int32_t) * ((size_t)m + 1), stream));
     h->d_p = d_p;
-    MXG_UP_TRY(cudaMalloc(&d_j, sizeof(int32_t) * nz));
+    MXG_UP_TRY(cudaMallocAsync(&d_j, sizeof(int32_t) * nz, stream));
     h->d_j = d_j;
     if (base == 0) {
         MXG_UP_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, stream));
@@ -104,12 +109,12 @@ static int upload_csr(int m, int K, const int32_t *p, const int32_t *j, const do
     if (nnz > 0) {
         MXG_UP_TRY(cudaMemcpyAsync(d_j, j + base, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
         if (want64) {
-            MXG_UP_TRY(cudaMalloc(&d_x64, sizeof(double) * nz));
+            MXG_UP_TRY(cudaMallocAsync(&d_x64, sizeof(double) * nz, stream));
             h->d_x64 = d_x64;
             MXG_UP_TRY(cudaMemcpyAsync(d_x64, x + base, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
         }
         if (want32) {
-            MXG_UP_TRY(cudaMalloc(&d_x32, sizeof(float) * nz));
+            MXG_UP_TRY(cudaMallocAsync(&d_x32, sizeof(float) * nz, stream));
             h->d_x32 = d_x32;
             if (d_x64) {
                 int rc = convert_f64_to_f32(d_x64, d_x32, (size_t)nnz, stream);
@@ -224,10 +229,11 @@ static int transpose_handle(const mxg_csr_s *A, int keep, cudaStream_t stream, m
     double *d_x64 = nullptr;
     float *d_x32 = nullptr;
     const size_t nz = (size_t)(A->nnz > 0 ? A->nnz : 1);
-    cudaError_t e = cudaMalloc(&d_p2, sizeof(int32_t) * ((size_t)A->K + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_i2, sizeof(int32_t) * nz);
-    if (e == cudaSuccess && w64) e = cudaMalloc(&d_x64, sizeof(double) * nz);
-    if (e == cudaSuccess && w32) e = cudaMalloc(&d_x32, sizeof(float) * nz);
+    t->stream = stream;
+    cudaError_t e = cudaMallocAsync(&d_p2, sizeof(int32_t) * ((size_t)A->K + 1), stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_i2, sizeof(int32_t) * nz, stream);
+    if (e == cudaSuccess && w64) e = cudaMallocAsync(&d_x64, sizeof(double) * nz, stream);
+    if (e == cudaSuccess && w32) e = cudaMallocAsync(&d_x32, sizeof(float) * nz, stream);
     t->d_p = d_p2;
     t->d_j = d_i2;
     t->d_x64 = d_x64;
@@ -346,6 +352,7 @@ int mxg_csr_wrap_device(int m, int K, const int32_t *d_p, const int32_t *d_j, co
     h->d_x64 = d_x64;
     h->d_x32 = d_x32;
     h->owns = false;
+    h->stream = s;
     cudaGetDevice(&h->device);
     int rc = csr_build_stats(h, validate, s);
     if (rc != MXG_OK) {

@@ -242,6 +242,7 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
 {
     h->piece = (int)options().piece;
     if (h->piece < 32) h->piece = 32;
+    h->stream = stream;
     h->max_len = h->n_long = h->n_pieces = 0;
     if (h->m == 0) return MXG_OK;
     int *d_stats = nullptr;
@@ -270,11 +271,11 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
     h->n_long = stats[2];
     h->n_pieces = stats[3];
     if (h->n_long > 0) {
-        MXG_CUDA_TRY(cudaMalloc(&h->d_long_rows, sizeof(int32_t) * (size_t)h->n_long));
-        MXG_CUDA_TRY(cudaMalloc(&h->d_long_first, sizeof(int32_t) * (size_t)h->n_long));
-        MXG_CUDA_TRY(cudaMalloc(&h->d_long_np, sizeof(int32_t) * (size_t)h->n_long));
-        MXG_CUDA_TRY(cudaMalloc(&h->d_piece_row, sizeof(int32_t) * (size_t)h->n_pieces));
-        MXG_CUDA_TRY(cudaMalloc(&h->d_piece_k, sizeof(int32_t) * (size_t)h->n_pieces));
+        MXG_CUDA_TRY(cudaMallocAsync(&h->d_long_rows, sizeof(int32_t) * (size_t)h->n_long, stream));
+        MXG_CUDA_TRY(cudaMallocAsync(&h->d_long_first, sizeof(int32_t) * (size_t)h->n_long, stream));
+        MXG_CUDA_TRY(cudaMallocAsync(&h->d_long_np, sizeof(int32_t) * (size_t)h->n_long, stream));
+        MXG_CUDA_TRY(cudaMallocAsync(&h->d_piece_row, sizeof(int32_t) * (size_t)h->n_pieces, stream));
+        MXG_CUDA_TRY(cudaMallocAsync(&h->d_piece_k, sizeof(int32_t) * (size_t)h->n_pieces, stream));
         MXG_LAUNCH(k_fill_long_tables, grid, 256, 0, stream, h->m, h->d_p, h->piece, d_stats, h->d_long_rows,
                    h->d_long_first, h->d_long_np, h->d_piece_row, h->d_piece_k);
     }
@@ -285,14 +286,15 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
 int ensure_partial(mxg_csr_s *h, size_t bytes)
 {
     if (bytes <= h->partial_bytes) return MXG_OK;
+    // the previous buffer may still be in use by kernels in flight on other streams
+    MXG_CUDA_TRY(cudaDeviceSynchronize());
     if (h->d_partial) {
-        // the previous buffer may still be in use by kernels in flight
-        MXG_CUDA_TRY(cudaDeviceSynchronize());
-        MXG_CUDA_TRY(cudaFree(h->d_partial));
+        MXG_CUDA_TRY(cudaFreeAsync(h->d_partial, h->stream));
         h->d_partial = nullptr;
         h->partial_bytes = 0;
     }
-    MXG_CUDA_TRY(cudaMalloc(&h->d_partial, bytes));
+    MXG_CUDA_TRY(cudaMallocAsync(&h->d_partial, bytes, h->stream));
+    MXG_CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->partial_bytes = bytes;
     return MXG_OK;
 }

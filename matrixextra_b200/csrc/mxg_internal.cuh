@@ -69,6 +69,7 @@ struct mxg_csr_s {
     const double *d_x64 = nullptr;
     const float *d_x32 = nullptr;
     bool owns = false; // arrays were allocated by the library
+    cudaStream_t stream = nullptr; // every allocation of this handle is stream-ordered on this stream (async pool)
 
     // row statistics (K7)
     int piece = 1024;

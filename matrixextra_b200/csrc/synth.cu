@@ -152,7 +152,7 @@ int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_mo
     if (grid > 148 * 8) grid = 148 * 8;
 
     int32_t *d_len = nullptr, *d_p = nullptr;
-    MXG_CUDA_TRY(cudaMalloc(&d_p, sizeof(int32_t) * ((size_t)m + 1)));
+    MXG_CUDA_TRY(cudaMallocAsync(&d_p, sizeof(int32_t) * ((size_t)m + 1), stream));
     MXG_CUDA_TRY(cudaMallocAsync(&d_len, sizeof(int32_t) * ((size_t)m + 1), stream));
     MXG_CUDA_TRY(cudaMemsetAsync(d_len, 0, sizeof(int32_t) * ((size_t)m + 1), stream));
 
@@ -201,9 +201,9 @@ int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_mo
     int32_t *d_j = nullptr;
     double *d_x64 = nullptr;
     float *d_x32 = nullptr;
-    MXG_CUDA_TRY(cudaMalloc(&d_j, sizeof(int32_t) * (nnz ? nnz : 1)));
-    if (keep & MXG_KEEP_F64) MXG_CUDA_TRY(cudaMalloc(&d_x64, sizeof(double) * (nnz ? nnz : 1)));
-    if (keep & MXG_KEEP_F32) MXG_CUDA_TRY(cudaMalloc(&d_x32, sizeof(float) * (nnz ? nnz : 1)));
+    MXG_CUDA_TRY(cudaMallocAsync(&d_j, sizeof(int32_t) * (nnz ? nnz : 1), stream));
+    if (keep & MXG_KEEP_F64) MXG_CUDA_TRY(cudaMallocAsync(&d_x64, sizeof(double) * (nnz ? nnz : 1), stream));
+    if (keep & MXG_KEEP_F32) MXG_CUDA_TRY(cudaMallocAsync(&d_x32, sizeof(float) * (nnz ? nnz : 1), stream));
     int gf = ceil_div_i(m, 8);
     if (gf > 148 * 32) gf = 148 * 32;
     if (d_x64 && d_x32)

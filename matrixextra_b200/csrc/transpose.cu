@@ -8,12 +8,14 @@
 //   1. histogram  : count[c] += 1 for every entry (integer atomics commute => deterministic),
 //                   exclusive scan -> p2[K+1];
 //   2. row expand : rowid[e] = r for e in [p[r], p[r+1]);
-//   3. stable LSD radix sort of (column key, entry id e) by 8-bit digits, least significant first:
-//        per pass  a) per-tile digit histogram, b) scan over (digit, tile), c) scatter where each
-//        warp ranks its 32 consecutive entries with __match_any_sync — ranks follow entry order, so
-//        every pass is stable; ceil(log2(K)/8) passes;
-//   4. gather     : i2[q] = rowid[e_q], x2[q] = x[e_q] for the sorted entry ids.
-// All of it is HBM-bound integer traffic; nothing here belongs on tensor cores.
+//   3. stable LSD radix sort of the records (column key, row id, value) by 8-bit digits of the key,
+//      least significant first, ceil(log2(K)/8) passes.  Per pass:
+//        a) per-tile digit histogram (4096-entry tiles), b) exclusive scan over (digit, tile),
+//        c) scatter: every warp ranks its 32 consecutive entries with __match_any_sync against
+//           per-warp digit counters, so ranks follow entry order (=> each pass is stable); the tile is
+//           then re-ordered by digit in shared memory and written out as contiguous runs, i.e. with
+//           coalesced stores.  The last pass writes straight into i2 / x2.
+// All of it is HBM-bound integer/byte traffic; nothing here belongs on tensor cores.
 #include "mxg_internal.cuh"
 
 namespace mxg {
@@ -89,8 +91,8 @@ __global__ void __launch_bounds__(256) k_expand_rows(int m, const int32_t *__res
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_STEPS = 16;                     // 32-entry steps per warp
-constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;     // 512 consecutive entries per warp
+constexpr int RS_STEPS = 16;                      // 32-entry steps per warp
+constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;      // 512 consecutive entries per warp
 constexpr int RS_TILE = RS_WARPS * RS_WARP_ITEMS; // 4096 entries per CTA
 constexpr int RS_BINS = 256;
 
@@ -111,81 +113,133 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(size_t n, const int32
     hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = bins[threadIdx.x];
 }
 
-// c) stable scatter.  offs = exclusive scan of hist (digit-major), i.e. the first destination of
-//    (digit d, tile t).  src_ids == nullptr means "entry id = position" (first pass).
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const int32_t *__restrict__ keys,
-                                                              const int32_t *__restrict__ src_ids, int shift,
-                                                              const int32_t *__restrict__ offs, int ntiles,
-                                                              int32_t *__restrict__ keys_out, int32_t *__restrict__ ids_out)
+struct RadixIO {
+    const int32_t *keys_in;
+    const int32_t *rows_in;
+    const double *x64_in;
+    const float *x32_in;
+    int32_t *keys_out; // nullptr on the last pass
+    int32_t *rows_out;
+    double *x64_out;
+    float *x32_out;
+};
+
+constexpr size_t radix_smem_bytes(bool h64, bool h32)
 {
-    __shared__ int wcnt[RS_WARPS][RS_BINS]; // per-warp running digit counts, then per-warp bases
+    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(int) * (RS_WARPS * RS_BINS + 2 * RS_BINS);
+}
+
+// c) stable scatter.  offs = exclusive scan of hist (digit-major): first destination of (digit, tile).
+template <bool H64, bool H32>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const RadixIO io, int shift,
+                                                              const int32_t *__restrict__ offs, int ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_x64 = reinterpret_cast<double *>(smem_raw);                                   // [RS_TILE] if H64
+    int *s_key = reinterpret_cast<int *>(smem_raw + (H64 ? (size_t)RS_TILE * 8 : 0));       // [RS_TILE]
+    int *s_row = s_key + RS_TILE;                                                            // [RS_TILE]
+    float *s_x32 = reinterpret_cast<float *>(s_row + RS_TILE);                               // [RS_TILE] if H32
+    int *wcnt = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));              // [RS_WARPS][RS_BINS]
+    int *dig_off = wcnt + RS_WARPS * RS_BINS;                                                // [RS_BINS] tile-local digit starts
+    int *gdelta = dig_off + RS_BINS;                                                         // [RS_BINS] global - local
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) wcnt[i] = 0;
     __syncthreads();
 
-    const size_t w0 = (size_t)blockIdx.x * RS_TILE + (size_t)warp * RS_WARP_ITEMS;
+    const size_t t0 = (size_t)blockIdx.x * RS_TILE;
+    const size_t w0 = t0 + (size_t)warp * RS_WARP_ITEMS;
     int key[RS_STEPS];
     int rank[RS_STEPS]; // rank of the entry among same-digit entries of this warp, in entry order
     const unsigned lt_mask = (1u << lane) - 1u;
+    int *my_cnt = wcnt + warp * RS_BINS;
 #pragma unroll
     for (int s = 0; s < RS_STEPS; s++) {
         const size_t e = w0 + (size_t)s * 32 + lane;
         const bool valid = e < n;
-        key[s] = valid ? __ldg(keys + e) : 0;
-        // invalid lanes get a digit no real lane can have inside the match (bit 8 set)
+        key[s] = valid ? __ldg(io.keys_in + e) : 0;
+        // invalid lanes get a digit no real lane can have (bit 8 set) so they never match a real one
         const int d = valid ? ((key[s] >> shift) & (RS_BINS - 1)) : RS_BINS;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         int before = 0;
-        if (valid) before = wcnt[warp][d];
+        if (valid) before = my_cnt[d];
         __syncwarp();
         rank[s] = before + __popc(peers & lt_mask);
-        if (valid && (peers & lt_mask) == 0) wcnt[warp][d] = before + __popc(peers); // lowest peer updates
+        if (valid && (peers & lt_mask) == 0) my_cnt[d] = before + __popc(peers); // lowest peer updates
         __syncwarp();
     }
     __syncthreads();
-    // turn per-warp counts into per-warp destination bases: global base of (digit, tile) + counts of lower warps
     {
+        // per-warp counts -> per-warp starts inside the digit; digit totals -> tile-local digit starts
         const int d = threadIdx.x; // RS_THREADS == RS_BINS
-        int run = offs[(size_t)d * ntiles + blockIdx.x];
+        int run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
-            const int c = wcnt[w][d];
-            wcnt[w][d] = run;
+            const int c = wcnt[w * RS_BINS + d];
+            wcnt[w * RS_BINS + d] = run;
             run += c;
         }
+        // block-wide exclusive scan of `run` over the 256 digits
+        __shared__ int warp_tot[RS_WARPS];
+        int incl = run;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++)
+            if (w < warp) wbase += warp_tot[w];
+        const int excl = wbase + incl - run;
+        dig_off[d] = excl;
+        gdelta[d] = offs[(size_t)d * ntiles + blockIdx.x] - excl;
     }
     __syncthreads();
+    // re-order the tile by digit in shared memory (payload read coalesced from global)
 #pragma unroll
     for (int s = 0; s < RS_STEPS; s++) {
         const size_t e = w0 + (size_t)s * 32 + lane;
         if (e < n) {
             const int d = (key[s] >> shift) & (RS_BINS - 1);
-            const int dst = wcnt[warp][d] + rank[s];
-            if (keys_out) keys_out[dst] = key[s];
-            ids_out[dst] = src_ids ? __ldg(src_ids + e) : (int32_t)e;
+            const int pos = dig_off[d] + my_cnt[d] + rank[s];
+            s_key[pos] = key[s];
+            s_row[pos] = __ldg(io.rows_in + e);
+            if (H64) s_x64[pos] = __ldg(io.x64_in + e);
+            if (H32) s_x32[pos] = __ldg(io.x32_in + e);
         }
+    }
+    __syncthreads();
+    const int tile_n = (int)((n - t0) < (size_t)RS_TILE ? (n - t0) : (size_t)RS_TILE);
+    for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+        const int k = s_key[i];
+        const int dst = i + gdelta[(k >> shift) & (RS_BINS - 1)];
+        if (io.keys_out) io.keys_out[dst] = k;
+        io.rows_out[dst] = s_row[i];
+        if (H64) io.x64_out[dst] = s_x64[i];
+        if (H32) io.x32_out[dst] = s_x32[i];
     }
 }
 
-template <bool HAS64, bool HAS32>
-__global__ void __launch_bounds__(256) k_csc_gather(size_t nnz, const int32_t *__restrict__ ids, const int32_t *__restrict__ rowid,
-                                                    const double *__restrict__ x64, const float *__restrict__ x32,
-                                                    int32_t *__restrict__ i2, double *__restrict__ x64o, float *__restrict__ x32o)
+template <bool H64, bool H32>
+static int launch_radix_scatter(size_t n, const RadixIO &io, int shift, const int32_t *offs, int ntiles, cudaStream_t stream)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += stride) {
-        const int e = __ldg(ids + q);
-        i2[q] = __ldg(rowid + e);
-        if (HAS64) x64o[q] = __ldg(x64 + e);
-        if (HAS32) x32o[q] = __ldg(x32 + e);
+    constexpr size_t smem = radix_smem_bytes(H64, H32);
+    static bool configured = false;
+    if (!configured) {
+        MXG_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<H64, H32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
     }
+    MXG_LAUNCH((k_radix_scatter<H64, H32>), ntiles, RS_THREADS, smem, stream, n, io, shift, offs, ntiles);
+    return MXG_OK;
 }
 
 int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t *d_j, const double *d_x64,
                    const float *d_x32, int32_t *d_p2, int32_t *d_i2, double *d_x64o, float *d_x32o,
                    cudaStream_t stream)
 {
-    // p2: histogram + scan (count has K+1 slots so the scan output is the full pointer array)
     MXG_CUDA_TRY(cudaMemsetAsync(d_p2, 0, sizeof(int32_t) * ((size_t)K + 1), stream));
     if (nnz == 0) return MXG_OK;
     if (m <= 0 || K <= 0) return fail(MXG_ERR_ARG, "csr2csc: entries in an empty matrix");
@@ -194,76 +248,81 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     MXG_CUDA_TRY(cudaMemcpyAsync(&base, d_p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     MXG_CUDA_TRY(cudaStreamSynchronize(stream));
     const int32_t *j = d_j + base;
+    const size_t n = (size_t)nnz;
+    const bool h64 = d_x64 && d_x64o, h32 = d_x32 && d_x32o;
+    const double *x64 = h64 ? d_x64 + base : nullptr;
+    const float *x32 = h32 ? d_x32 + base : nullptr;
 
+    // p2: histogram + scan (count has K+1 slots so the scan output is the full pointer array)
     int32_t *d_count = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_count, sizeof(int32_t) * ((size_t)K + 1), stream));
     MXG_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * ((size_t)K + 1), stream));
     int g = ceil_div_i(nnz, 256 * 4);
     if (g > 148 * 32) g = 148 * 32;
-    MXG_LAUNCH(k_col_histogram, g, 256, 0, stream, (size_t)nnz, j, d_count);
+    MXG_LAUNCH(k_col_histogram, g, 256, 0, stream, n, j, d_count);
     MXG_TRY(exclusive_scan_i32(d_count, d_p2, (size_t)K + 1, stream));
     MXG_CUDA_TRY(cudaFreeAsync(d_count, stream));
 
     // row ids per entry
     int32_t *d_rowid = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_rowid, sizeof(int32_t) * (size_t)nnz, stream));
+    MXG_CUDA_TRY(cudaMallocAsync(&d_rowid, sizeof(int32_t) * n, stream));
     int gr = ceil_div_i(m, 8);
     if (gr > 148 * 32) gr = 148 * 32;
     MXG_LAUNCH(k_expand_rows, gr, 256, 0, stream, m, d_p, base, d_rowid);
 
-    // LSD radix passes over the column key
+    // LSD radix passes over the column key, records = (key, row, values)
     int bits = 0;
     while (bits < 31 && ((int64_t)1 << bits) < (int64_t)K) bits++;
     int passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
     const int ntiles = ceil_div_i(nnz, RS_TILE);
-    int32_t *d_hist = nullptr, *d_keyA = nullptr, *d_keyB = nullptr, *d_idA = nullptr, *d_idB = nullptr;
     const size_t hist_n = (size_t)RS_BINS * (size_t)ntiles;
+    int32_t *d_hist = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_hist, sizeof(int32_t) * hist_n, stream));
-    MXG_CUDA_TRY(cudaMallocAsync(&d_idA, sizeof(int32_t) * (size_t)nnz, stream));
-    if (passes > 1) {
-        MXG_CUDA_TRY(cudaMallocAsync(&d_keyA, sizeof(int32_t) * (size_t)nnz, stream));
-        MXG_CUDA_TRY(cudaMallocAsync(&d_idB, sizeof(int32_t) * (size_t)nnz, stream));
+    // ping-pong record buffers (only as many as the pass count needs)
+    struct Rec { int32_t *key = nullptr, *row = nullptr; double *x64 = nullptr; float *x32 = nullptr; } buf[2];
+    const int nbuf = passes >= 3 ? 2 : (passes == 2 ? 1 : 0);
+    for (int b = 0; b < nbuf; b++) {
+        MXG_CUDA_TRY(cudaMallocAsync(&buf[b].key, sizeof(int32_t) * n, stream));
+        MXG_CUDA_TRY(cudaMallocAsync(&buf[b].row, sizeof(int32_t) * n, stream));
+        if (h64) MXG_CUDA_TRY(cudaMallocAsync(&buf[b].x64, sizeof(double) * n, stream));
+        if (h32) MXG_CUDA_TRY(cudaMallocAsync(&buf[b].x32, sizeof(float) * n, stream));
     }
-    if (passes > 2) MXG_CUDA_TRY(cudaMallocAsync(&d_keyB, sizeof(int32_t) * (size_t)nnz, stream));
 
-    const int32_t *keys_in = j;
-    const int32_t *ids_in = nullptr;
-    int32_t *key_bufs[2] = {d_keyA, d_keyB};
-    int32_t *id_bufs[2] = {d_idA, d_idB};
+    RadixIO io;
+    io.keys_in = j;
+    io.rows_in = d_rowid;
+    io.x64_in = x64;
+    io.x32_in = x32;
     for (int pass = 0; pass < passes; pass++) {
         const int shift = pass * 8;
         const bool last = pass == passes - 1;
-        int32_t *keys_out = last ? nullptr : key_bufs[pass & 1];
-        int32_t *ids_out = id_bufs[pass & 1];
-        MXG_LAUNCH(k_radix_hist, ntiles, RS_THREADS, 0, stream, (size_t)nnz, keys_in, shift, d_hist, ntiles);
+        const Rec &o = buf[pass & 1];
+        io.keys_out = last ? nullptr : o.key;
+        io.rows_out = last ? d_i2 : o.row;
+        io.x64_out = last ? d_x64o : o.x64;
+        io.x32_out = last ? d_x32o : o.x32;
+        MXG_LAUNCH(k_radix_hist, ntiles, RS_THREADS, 0, stream, n, io.keys_in, shift, d_hist, ntiles);
         MXG_TRY(exclusive_scan_i32(d_hist, d_hist, hist_n, stream));
-        MXG_LAUNCH(k_radix_scatter, ntiles, RS_THREADS, 0, stream, (size_t)nnz, keys_in, ids_in, shift, d_hist, ntiles,
-                   keys_out, ids_out);
-        keys_in = keys_out;
-        ids_in = ids_out;
+        int rc;
+        if (h64 && h32) rc = launch_radix_scatter<true, true>(n, io, shift, d_hist, ntiles, stream);
+        else if (h64) rc = launch_radix_scatter<true, false>(n, io, shift, d_hist, ntiles, stream);
+        else if (h32) rc = launch_radix_scatter<false, true>(n, io, shift, d_hist, ntiles, stream);
+        else rc = launch_radix_scatter<false, false>(n, io, shift, d_hist, ntiles, stream);
+        MXG_TRY(rc);
+        io.keys_in = io.keys_out;
+        io.rows_in = io.rows_out;
+        io.x64_in = io.x64_out;
+        io.x32_in = io.x32_out;
     }
 
-    const int32_t *d_sorted_ids = ids_in;
-    int gg = ceil_div_i(nnz, 256 * 4);
-    if (gg > 148 * 32) gg = 148 * 32;
-    const double *x64 = d_x64 ? d_x64 + base : nullptr;
-    const float *x32 = d_x32 ? d_x32 + base : nullptr;
-    const bool h64 = x64 && d_x64o, h32 = x32 && d_x32o;
-    if (h64 && h32)
-        MXG_LAUNCH((k_csc_gather<true, true>), gg, 256, 0, stream, (size_t)nnz, d_sorted_ids, d_rowid, x64, x32, d_i2, d_x64o, d_x32o);
-    else if (h64)
-        MXG_LAUNCH((k_csc_gather<true, false>), gg, 256, 0, stream, (size_t)nnz, d_sorted_ids, d_rowid, x64, x32, d_i2, d_x64o, d_x32o);
-    else if (h32)
-        MXG_LAUNCH((k_csc_gather<false, true>), gg, 256, 0, stream, (size_t)nnz, d_sorted_ids, d_rowid, x64, x32, d_i2, d_x64o, d_x32o);
-    else
-        MXG_LAUNCH((k_csc_gather<false, false>), gg, 256, 0, stream, (size_t)nnz, d_sorted_ids, d_rowid, x64, x32, d_i2, d_x64o, d_x32o);
-
     MXG_CUDA_TRY(cudaFreeAsync(d_hist, stream));
-    MXG_CUDA_TRY(cudaFreeAsync(d_idA, stream));
-    if (d_keyA) MXG_CUDA_TRY(cudaFreeAsync(d_keyA, stream));
-    if (d_idB) MXG_CUDA_TRY(cudaFreeAsync(d_idB, stream));
-    if (d_keyB) MXG_CUDA_TRY(cudaFreeAsync(d_keyB, stream));
+    for (int b = 0; b < nbuf; b++) {
+        MXG_CUDA_TRY(cudaFreeAsync(buf[b].key, stream));
+        MXG_CUDA_TRY(cudaFreeAsync(buf[b].row, stream));
+        if (buf[b].x64) MXG_CUDA_TRY(cudaFreeAsync(buf[b].x64, stream));
+        if (buf[b].x32) MXG_CUDA_TRY(cudaFreeAsync(buf[b].x32, stream));
+    }
     MXG_CUDA_TRY(cudaFreeAsync(d_rowid, stream));
     return MXG_OK;
 }

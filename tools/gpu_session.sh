@@ -15,12 +15,20 @@ for w in $WHAT; do
     bench) timeout 900 python bench.py --steps 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json ;;
     benchref) timeout 600 python bench.py --impl reference --steps 3 > gpurun_out/${TAG}_benchref.json 2> gpurun_out/${TAG}_benchref.err; echo "benchref rc=$?"; cat gpurun_out/${TAG}_benchref.json ;;
     sweep) timeout 900 python tools/sweep.py > gpurun_out/${TAG}_sweep.jsonl 2> gpurun_out/${TAG}_sweep.err; echo "sweep rc=$?"; tail -3 gpurun_out/${TAG}_sweep.err ;;
+    ncufull)
+      timeout 600 ncu --set full --clock-control none --import-source on -k k_spmm -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmm \
+        python bench.py --steps 2 --warmup 1 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_ncu_spmm.log 2>&1; echo "ncu-spmm rc=$?"
+      timeout 600 ncu --set full --clock-control none --import-source on -k k_spmv -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmv \
+        python bench.py --workload cfg2 --steps 2 --warmup 1 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_ncu_spmv.log 2>&1; echo "ncu-spmv rc=$?"
+      timeout 600 ncu --set full --clock-control none --import-source on -k k_spmm -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmm_f64 \
+        python bench.py --workload k64f64 --steps 2 --warmup 1 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_ncu_spmm64.log 2>&1; echo "ncu-spmm64 rc=$?"
+      ;;
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_spmm|k_spmv|k_radix|k_csc|k_col|k_expand|k_scan|k_transpose' -c 300 --csv \
         --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --skip-e2e --skip-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu-launches rc=$?"
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_spmm<' -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmm \
+      timeout 600 ncu --set full --clock-control none --import-source on -k k_spmm -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmm \
         python bench.py --steps 2 --warmup 1 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_ncu_spmm.log 2>&1; echo "ncu-spmm rc=$?"
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_spmv<' -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmv \
+      timeout 600 ncu --set full --clock-control none --import-source on -k k_spmv -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_spmv \
         python bench.py --workload cfg2 --steps 2 --warmup 1 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_ncu_spmv.log 2>&1; echo "ncu-spmv rc=$?"
       ;;
   esac
