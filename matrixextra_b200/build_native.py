@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "layout.cu", "spmm.cu", "spmv.cu", "transpose.cu", "synth.cu"]
+SOURCES = ["capi.cu", "layout.cu", "pipeline.cu", "spmm.cu", "spmv.cu", "transpose.cu", "synth.cu"]
 LIB = os.path.join(CSRC, "libmxgpu.so")
 
 NVCC_FLAGS = [

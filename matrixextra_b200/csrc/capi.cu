@@ -12,14 +12,10 @@ int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_mo
                      cudaStream_t stream, int32_t **out_p, int32_t **out_j, double **out_x64, float **out_x32,
                      int64_t *out_nnz);
 
-// ---- per-process state: one internal stream for the level-1 calls, pool configured once per device ----
-struct DeviceState {
-    bool ready = false;
-    cudaStream_t stream = nullptr;
-};
+// ---- per-process state: internal streams for the level-1 calls, pool configured once per device ----
 static DeviceState g_dev[64];
 
-static int current_state(DeviceState **out)
+int current_state(DeviceState **out)
 {
     int dev = 0;
     MXG_CUDA_TRY(cudaGetDevice(&dev));
@@ -27,6 +23,8 @@ static int current_state(DeviceState **out)
     DeviceState &st = g_dev[dev];
     if (!st.ready) {
         MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.h2d, cudaStreamNonBlocking));
+        MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.d2h, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long keep_all = ~0ULL; // keep freed blocks cached between calls (mxg_trim releases them)
@@ -280,10 +278,12 @@ static long *option_slot(const char *name)
     if (!name) return nullptr;
     if (!strcmp(name, "piece")) return &o.piece;
     if (!strcmp(name, "spmm_lpr")) return &o.spmm_lpr;
-    if (!strcmp(name, "spmm_cpl")) return &o.spmm_cpl;
-    if (!strcmp(name, "spmm_block_rows")) return &o.spmm_block_rows;
+    if (!strcmp(name, "spmm_unroll")) return &o.spmm_unroll;
+    if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
     if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;
+    if (!strcmp(name, "pipeline")) return &o.pipeline;
+    if (!strcmp(name, "pipe_chunk_nnz")) return &o.pipe_chunk_nnz;
     return nullptr;
 }
 
@@ -513,8 +513,13 @@ int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout, int m, int K, in
 {
     if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
     if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    if (m < 0 || K < 0) return fail(MXG_ERR_ARG, "csr: negative dimension");
+    if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
     DeviceState *st;
     MXG_TRY(current_state(&st));
+    // every valid R matrix has p[0] == 0 (R/utils.R:349-410): streamed, chunk-overlapped path
+    if (p[0] == 0 && options().pipeline != 0)
+        return pipeline_spmm(st, dtype, out_layout, b_layout, m, K, n, p, j, x, B, ldb, Out, ldc);
     mxg_csr_s *A = nullptr;
     MXG_TRY(upload_csr(m, K, p, j, x, dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32, st->stream, &A));
     int rc = spmm_host_io(A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream);
@@ -546,8 +551,11 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, i
 int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *y, void *out)
 {
     if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
+    if (m < 0 || K < 0) return fail(MXG_ERR_ARG, "csr: negative dimension");
+    if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
     DeviceState *st;
     MXG_TRY(current_state(&st));
+    if (p[0] == 0 && options().pipeline != 0) return pipeline_spmv(st, ytype, m, K, p, j, x, y, out);
     mxg_csr_s *A = nullptr;
     MXG_TRY(upload_csr(m, K, p, j, x, MXG_KEEP_F64, st->stream, &A));
     int rc = MXG_OK;

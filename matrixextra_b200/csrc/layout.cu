@@ -53,14 +53,26 @@ __global__ void __launch_bounds__(256) k_f64_to_f32(const double *__restrict__ s
     if (i == 0 && (n & 1)) dst[n - 1] = __double2float_rn(src[n - 1]);
 }
 
+// element-wise variant for destinations that start at an odd element (row chunks of the streamed path)
+__global__ void __launch_bounds__(256) k_f64_to_f32_scalar(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = __double2float_rn(__ldg(src + k));
+}
+
 int convert_f64_to_f32(const double *d_src, float *d_dst, size_t n, cudaStream_t stream)
 {
     if (n == 0) return MXG_OK;
     const bool aligned = (((uintptr_t)d_src & 15) == 0) && (((uintptr_t)d_dst & 7) == 0);
-    if (!aligned) return fail(MXG_ERR_ARG, "convert_f64_to_f32: unaligned buffers");
-    int grid = ceil_div_i((long long)(n / 2 + 1), 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    MXG_LAUNCH(k_f64_to_f32, grid, 256, 0, stream, d_src, d_dst, n);
+    if (aligned) {
+        int grid = ceil_div_i((long long)(n / 2 + 1), 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        MXG_LAUNCH(k_f64_to_f32, grid, 256, 0, stream, d_src, d_dst, n);
+    } else {
+        int grid = ceil_div_i((long long)n, 256 * 4);
+        if (grid > 148 * 16) grid = 148 * 16;
+        MXG_LAUNCH(k_f64_to_f32_scalar, grid, 256, 0, stream, d_src, d_dst, n);
+    }
     return MXG_OK;
 }
 
@@ -212,6 +224,28 @@ __global__ void __launch_bounds__(256) k_check_indices(size_t nnz, const int32_t
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicOr(&stats[0], 2);
+}
+
+// Streamed path: the flag is a lone device int that later kernels of the same stream test (mxg_csr_s::d_abort).
+__global__ void __launch_bounds__(256) k_check_indices_flag(size_t nnz, const int32_t *__restrict__ j, int K, int *__restrict__ flag)
+{
+    int bad = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+        const int c = __ldg(j + e);
+        bad |= (c < 0 || c >= K);
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr(flag, 1);
+}
+
+int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream)
+{
+    if (nnz == 0) return MXG_OK;
+    int g = ceil_div_i((long long)nnz, 256 * 8);
+    if (g > 148 * 16) g = 148 * 16;
+    MXG_LAUNCH(k_check_indices_flag, g, 256, 0, stream, nnz, d_j, K, d_flag);
+    return MXG_OK;
 }
 
 // Which slot a long row gets is decided by atomics (arbitrary), but a row's pieces are contiguous and

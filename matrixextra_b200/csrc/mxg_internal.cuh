@@ -46,11 +46,13 @@ extern std::atomic<unsigned long long> g_launches;
 // ------------------------------------------------------------------------------------------------
 struct Options {
     long piece = 1024;        // nnz per long-row piece; rows longer than this are split
-    long spmm_lpr = 0;        // 0 = auto
-    long spmm_cpl = 0;        // 0 = auto
-    long spmm_block_rows = 0; // 0 = auto
+    long spmm_lpr = 0;        // lanes per row of B; 0 = auto
+    long spmm_unroll = 0;     // gathers in flight per sub-team (4 | 8); 0 = auto
+    long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
     long spmv_lpr = 0;        // 0 = auto
-    long h2d_chunk_mb = 64;   // staging chunk of the level-1 pipeline
+    long h2d_chunk_mb = 64;   // staging chunk of the value narrowing in mxg_csr_upload
+    long pipe_chunk_nnz = 0;  // stored entries (and rows) per chunk of the streamed path; 0 = auto (nnz/16, >= 1 Mi)
+    long pipeline = 1;        // level-1 products: 1 = streamed row chunks (pipeline.cu), 0 = upload-all-then-compute
 };
 Options &options();
 
@@ -85,9 +87,30 @@ struct mxg_csr_s {
     // partial-sum workspace for long rows (grow-only)
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
+
+    // device flag set by the index validation of the streamed (level-1) path: kernels that see it non-zero
+    // return at once instead of gathering through an out-of-range column id
+    const int *d_abort = nullptr;
 };
 
 namespace mxg {
+
+// per-device state of the host-buffer (level-1) entry points: three streams so that uploads, kernels and
+// downloads of consecutive row chunks overlap (PCIe is full duplex)
+struct DeviceState {
+    bool ready = false;
+    cudaStream_t stream = nullptr; // kernels (and everything of the non-pipelined calls)
+    cudaStream_t h2d = nullptr;
+    cudaStream_t d2h = nullptr;
+};
+int current_state(DeviceState **out);
+
+// pipeline.cu: streamed level-1 products (host CSR with p[0] == 0)
+int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
+                  const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc);
+int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
+                  const void *y, void *out);
+int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream);
 
 // layout.cu
 int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream);

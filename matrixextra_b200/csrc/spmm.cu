@@ -71,63 +71,77 @@ __device__ __forceinline__ void st_pack(T *p, const Pack<T, V> &v)
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
-// One team accumulates entries [a, b) of its row.  maxlen is the warp-wide maximum of (b - a).
-template <typename T, int V, int LPR, int CPL>
-__device__ __forceinline__ void team_gather(Pack<T, V> (&acc)[CPL], const int a, const int b, const int maxlen,
-                                            const int l, const int32_t *__restrict__ j, const T *__restrict__ x,
-                                            const T *__restrict__ B, const size_t ldb, const int (&col)[CPL],
-                                            const bool (&cok)[CPL])
+// ------------------------------------------------------------------------------------------------
+// One WARP owns one row at a time.  Its 32 lanes form SPLIT = 32 / LPR sub-teams of LPR lanes; lane l
+// of a sub-team owns CPL vectors of V output columns, sub-team s takes the row's entries
+// s, s + SPLIT, s + 2 SPLIT, ... (so a gather instruction of the warp fetches SPLIT whole rows of B),
+// and the sub-team sums are added by a butterfly when the row ends.  With SPLIT == 1 (n*sizeof(T)
+// >= 512 bytes) the sum is the reference's left-to-right chain; otherwise it is SPLIT interleaved
+// chains plus a log2(SPLIT) tree — the reassociation the fp tolerances (1e-12 / 1e-5) allow for.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SPMM_THREADS = 128;
+constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+constexpr int SPMM_CM_RPW = 8; // rows per warp of a column-major CTA tile (tile = 32 rows)
+
+// Entries pos .. pos + cnt - 1 (cnt <= 32, one per lane in jj / xx) of the current row.
+template <typename T, int V, int LPR, int CPL, int U>
+__device__ __forceinline__ void batch_gather(Pack<T, V> (&acc)[CPL], const int jj, const T xx, const int cnt,
+                                             const int sub, const T *__restrict__ B, const size_t ldb,
+                                             const int (&col)[CPL], const bool (&cok)[CPL])
 {
-    constexpr int U = 4;
-    static_assert(LPR % U == 0, "LPR must be a multiple of the gather unroll");
-    for (int e0 = 0; e0 < maxlen; e0 += LPR) {
-        const int e = a + e0 + l;
-        int jj = 0;
-        T xx = T(0);
-        if (e < b) {
-            jj = __ldg(j + e);
-            xx = __ldg(x + e);
+    constexpr int SPLIT = 32 / LPR;
+    for (int k = 0; k < cnt; k += SPLIT * U) { // warp-uniform trip count
+        const T *src[U];
+        T xk[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int idx = k + u * SPLIT + sub;
+            const int jk = __shfl_sync(FULL, jj, idx & 31);
+            xk[u] = __shfl_sync(FULL, xx, idx & 31);
+            ok[u] = idx < cnt;
+            src[u] = B + (size_t)jk * ldb;
         }
-        const int cnt = b - (a + e0);           // entries this team still has (may be <= 0)
-        const int kmax = min(LPR, maxlen - e0); // warp-uniform
-        for (int k = 0; k < kmax; k += U) {
-            int jk[U];
-            T xk[U];
-            bool ok[U];
+        Pack<T, V> bv[U][CPL];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                jk[u] = __shfl_sync(0xffffffffu, jj, k + u, LPR);
-                xk[u] = __shfl_sync(0xffffffffu, xx, k + u, LPR);
-                ok[u] = (k + u) < cnt;
-            }
-            Pack<T, V> bv[U][CPL];
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-            for (int u = 0; u < U; u++) {
+            for (int c = 0; c < CPL; c++)
+                if (ok[u] && cok[c]) bv[u][c] = ld_ro<T, V>(src[u] + col[c]);
+        }
 #pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    if (ok[u] && cok[c]) bv[u][c] = ld_ro<T, V>(B + (size_t)jk[u] * ldb + col[c]);
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int c = 0; c < CPL; c++)
+                if (ok[u] && cok[c]) {
+#pragma unroll
+                    for (int i = 0; i < V; i++) acc[c].v[i] = fma_t(xk[u], bv[u][c].v[i], acc[c].v[i]);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-#pragma unroll
-                for (int c = 0; c < CPL; c++) {
-                    if (ok[u] && cok[c]) {
-#pragma unroll
-                        for (int i = 0; i < V; i++) acc[c].v[i] = fma_t(xk[u], bv[u][c].v[i], acc[c].v[i]);
-                    }
-                }
-            }
         }
     }
 }
 
-template <int LPR>
-struct TeamGeom {
-    static constexpr int THREADS = 256;
-    static constexpr int TEAMS = THREADS / LPR;
-    static constexpr int BR = TEAMS > 32 ? TEAMS : 32; // rows of a column-major CTA tile
-};
+template <typename T, int V, int LPR, int CPL>
+__device__ __forceinline__ void subteam_reduce(Pack<T, V> (&acc)[CPL])
+{
+#pragma unroll
+    for (int d = LPR; d < 32; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < CPL; c++)
+#pragma unroll
+            for (int i = 0; i < V; i++) acc[c].v[i] += __shfl_xor_sync(FULL, acc[c].v[i], d);
+    }
+}
+
+template <typename T, int V, int CPL>
+__device__ __forceinline__ void zero_acc(Pack<T, V> (&acc)[CPL])
+{
+#pragma unroll
+    for (int c = 0; c < CPL; c++)
+#pragma unroll
+        for (int i = 0; i < V; i++) acc[c].v[i] = T(0);
+}
 
 struct SpmmArgs {
     int m, n;
@@ -138,21 +152,26 @@ struct SpmmArgs {
     size_t ldb;
     void *Out;
     size_t ldc;
-    int block_rows; // rows per CTA (row-major output); column-major uses TeamGeom::BR
+    int rpw; // consecutive rows per warp (<= 31; column-major output uses SPMM_CM_RPW)
     int piece;
     int n_pieces;
     int piece_blocks;
     const int32_t *piece_row;
     const int32_t *piece_k;
     void *partial; // [n_pieces][n]
+    const int *abort; // optional device flag: non-zero => the column ids failed validation, do nothing
 };
 
-template <typename T, int V, int LPR, int CPL, bool COLMAJOR>
-__global__ void __launch_bounds__(256) k_spmm(const SpmmArgs g)
+// Grid: x = [piece CTAs | row CTAs], y = column blocks of NB = LPR*V*CPL output columns.
+// A row CTA owns SPMM_WARPS * rpw consecutive rows, rpw consecutive rows per warp.  A warp walks its rows
+// batch by batch (32 stored entries per batch, loaded coalesced); the (index, value) batch that follows
+// the one being gathered — in the same row or at the start of the next — is already in flight, so the
+// only exposed latencies are the gathers themselves, U whole-row gathers deep per sub-team.
+template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR>
+__global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
 {
-    constexpr int TEAMS = TeamGeom<LPR>::TEAMS;
-    constexpr int BR = TeamGeom<LPR>::BR;
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
+    constexpr int BR = SPMM_WARPS * SPMM_CM_RPW;
     constexpr int TLD = BR + 1;
     __shared__ T tile[COLMAJOR ? NB * TLD : 1];
 
@@ -163,8 +182,9 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmArgs g)
     T *__restrict__ Out = static_cast<T *>(g.Out);
 
     const int lane = threadIdx.x & 31;
-    const int team = threadIdx.x / LPR;
-    const int l = threadIdx.x % LPR;
+    const int warp = threadIdx.x >> 5;
+    const int sub = lane / LPR;
+    const int l = lane % LPR;
     const int col0 = blockIdx.y * NB;
 
     int col[CPL];
@@ -175,24 +195,37 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmArgs g)
         cok[c] = col[c] < g.n; // n % V == 0 on the vector path, so a vector is entirely in or out
     }
 
+    if (g.abort != nullptr && *g.abort != 0) return; // whole grid, before any barrier
+
+    Pack<T, V> acc[CPL];
+    zero_acc<T, V, CPL>(acc);
+
     if ((int)blockIdx.x < g.piece_blocks) {
-        // ---- long-row pieces: partial sums to the workspace -------------------------------------
-        const int pc = blockIdx.x * TEAMS + team;
-        int a = 0, b = 0;
-        if (pc < g.n_pieces) {
-            const int row = g.piece_row[pc];
-            const int r0 = p[row], r1 = p[row + 1];
-            a = r0 + g.piece_k[pc] * g.piece;
-            b = min(a + g.piece, r1);
+        // ---- long-row pieces: one warp per piece, partial sums to the workspace -----------------------
+        const int pc = blockIdx.x * SPMM_WARPS + warp;
+        if (pc >= g.n_pieces) return; // warp-uniform, no barrier in this section
+        const int row = g.piece_row[pc];
+        const int a = p[row] + g.piece_k[pc] * g.piece;
+        const int b = min(a + g.piece, p[row + 1]);
+        int cj = 0;
+        T cx = T(0);
+        if (a + lane < b) {
+            cj = __ldg(j + a + lane);
+            cx = __ldg(x + a + lane);
         }
-        const int maxlen = __reduce_max_sync(0xffffffffu, b - a);
-        Pack<T, V> acc[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; c++)
-#pragma unroll
-            for (int i = 0; i < V; i++) acc[c].v[i] = T(0);
-        team_gather<T, V, LPR, CPL>(acc, a, b, maxlen, l, j, x, B, g.ldb, col, cok);
-        if (pc < g.n_pieces) {
+        for (int pos = a; pos < b; pos += 32) {
+            int nj = 0;
+            T nx = T(0);
+            if (pos + 32 + lane < b) {
+                nj = __ldg(j + pos + 32 + lane);
+                nx = __ldg(x + pos + 32 + lane);
+            }
+            batch_gather<T, V, LPR, CPL, U>(acc, cj, cx, min(32, b - pos), sub, B, g.ldb, col, cok);
+            cj = nj;
+            cx = nx;
+        }
+        subteam_reduce<T, V, LPR, CPL>(acc);
+        if (sub == 0) {
             T *dst = static_cast<T *>(g.partial) + (size_t)pc * g.n;
 #pragma unroll
             for (int c = 0; c < CPL; c++)
@@ -202,61 +235,93 @@ __global__ void __launch_bounds__(256) k_spmm(const SpmmArgs g)
     }
 
     const int rb = blockIdx.x - g.piece_blocks;
-    const int block_rows = COLMAJOR ? BR : g.block_rows;
-    const int row0 = rb * block_rows;
+    const int rpw = COLMAJOR ? SPMM_CM_RPW : g.rpw;
+    const int row0 = (rb * SPMM_WARPS + warp) * rpw;
+    const int nr = min(rpw, g.m - row0); // rows this warp owns (<= 0: none)
 
-    for (int base = 0; base < block_rows; base += TEAMS) {
-        const int rl = base + team;
-        const int row = row0 + rl;
-        int a = 0, b = 0;
-        bool store = false;
-        if (rl < block_rows && row < g.m) {
-            a = p[row];
-            b = p[row + 1];
-            store = true;
-            if (b - a > g.piece) { // long row: handled by the piece section + fix-up
-                b = a;
-                store = false;
-            }
+    if (nr > 0) {
+        int pv = 0;
+        if (lane <= nr) pv = __ldg(p + row0 + lane);
+        // row rr: entries [ra, re); rows longer than a piece are left to the piece section + fix-up kernel
+        auto bounds = [&](const int rr, int &ra, int &re, bool &rskip) {
+            ra = __shfl_sync(FULL, pv, rr);
+            const int rb_ = __shfl_sync(FULL, pv, rr + 1);
+            rskip = (rb_ - ra) > g.piece;
+            re = rskip ? ra : rb_;
+        };
+        int r = 0, a, e;
+        bool skip;
+        bounds(0, a, e, skip);
+        int pos = a;
+        int cj = 0;
+        T cx = T(0);
+        if (pos + lane < e) {
+            cj = __ldg(j + pos + lane);
+            cx = __ldg(x + pos + lane);
         }
-        const int maxlen = __reduce_max_sync(0xffffffffu, b - a);
-        Pack<T, V> acc[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; c++)
-#pragma unroll
-            for (int i = 0; i < V; i++) acc[c].v[i] = T(0);
-        team_gather<T, V, LPR, CPL>(acc, a, b, maxlen, l, j, x, B, g.ldb, col, cok);
-        if (store) {
-            if (COLMAJOR) {
-#pragma unroll
-                for (int c = 0; c < CPL; c++)
-                    if (cok[c]) {
-#pragma unroll
-                        for (int i = 0; i < V; i++) tile[(col[c] - col0 + i) * TLD + rl] = acc[c].v[i];
-                    }
-            } else {
-                T *dst = Out + (size_t)row * g.ldc;
-#pragma unroll
-                for (int c = 0; c < CPL; c++)
-                    if (cok[c]) st_pack<T, V>(dst + col[c], acc[c]);
+        while (true) {
+            const int cnt = min(32, e - pos); // <= 0 for a row without (eligible) entries
+            // where the next batch starts: further along this row, or at the start of the next one
+            int npos = pos + 32, nrow = r, na = a, ne = e;
+            bool nskip = skip;
+            const bool last = npos >= e;
+            if (last) {
+                nrow = r + 1;
+                if (nrow < nr) {
+                    bounds(nrow, na, ne, nskip);
+                    npos = na;
+                }
             }
+            int nj = 0;
+            T nx = T(0);
+            if (nrow < nr && npos + lane < ne) {
+                nj = __ldg(j + npos + lane);
+                nx = __ldg(x + npos + lane);
+            }
+            batch_gather<T, V, LPR, CPL, U>(acc, cj, cx, cnt, sub, B, g.ldb, col, cok);
+            if (last) {
+                if (!skip) {
+                    subteam_reduce<T, V, LPR, CPL>(acc);
+                    if (sub == 0) {
+                        if (COLMAJOR) {
+                            const int rl = warp * SPMM_CM_RPW + r;
+#pragma unroll
+                            for (int c = 0; c < CPL; c++)
+                                if (cok[c]) {
+#pragma unroll
+                                    for (int i = 0; i < V; i++) tile[(col[c] - col0 + i) * TLD + rl] = acc[c].v[i];
+                                }
+                        } else {
+                            T *dst = Out + (size_t)(row0 + r) * g.ldc;
+#pragma unroll
+                            for (int c = 0; c < CPL; c++)
+                                if (cok[c]) st_pack<T, V>(dst + col[c], acc[c]);
+                        }
+                    }
+                }
+                zero_acc<T, V, CPL>(acc);
+                if (nrow >= nr) break;
+            }
+            r = nrow;
+            a = na;
+            e = ne;
+            skip = nskip;
+            pos = npos;
+            cj = nj;
+            cx = nx;
         }
     }
 
     if (COLMAJOR) {
         __syncthreads();
-        const int warp = threadIdx.x >> 5;
+        const int tile_row0 = rb * BR;
+        const int row = tile_row0 + lane; // BR == 32: one tile row per lane
         const int ncols = min(NB, g.n - col0);
-#pragma unroll
-        for (int rr = 0; rr < BR; rr += 32) {
-            const int rl = rr + lane;
-            const int row = row0 + rl;
-            bool w = row < g.m;
-            if (w) w = (p[row + 1] - p[row]) <= g.piece; // long rows are written by the fix-up kernel
-            if (w) {
-                T *dst = Out + (size_t)row;
-                for (int c = warp; c < ncols; c += 8) dst[(size_t)(col0 + c) * g.ldc] = tile[c * TLD + rl];
-            }
+        bool w = row < g.m;
+        if (w) w = (p[row + 1] - p[row]) <= g.piece; // long rows are written by the fix-up kernel
+        if (w) {
+            T *dst = Out + (size_t)row;
+            for (int c = warp; c < ncols; c += SPMM_WARPS) dst[(size_t)(col0 + c) * g.ldc] = tile[c * TLD + lane];
         }
     }
 }
@@ -289,34 +354,31 @@ __global__ void __launch_bounds__(256) k_fill_zero_2d(T *__restrict__ Out, size_
         Out[(i / cols) * ld + (i % cols)] = T(0);
 }
 
-template <typename T, int V, int LPR, int CPL, bool COLMAJOR>
+template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR>
 static int launch_variant(const SpmmArgs &args, int row_blocks, cudaStream_t stream)
 {
     constexpr int NB = LPR * V * CPL;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
-    MXG_LAUNCH((k_spmm<T, V, LPR, CPL, COLMAJOR>), grid, 256, 0, stream, args);
+    MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR>), grid, SPMM_THREADS, 0, stream, args);
     return MXG_OK;
 }
 
 template <typename T, int V, bool COLMAJOR>
-static int dispatch_geom(int lpr, int cpl, SpmmArgs &args, cudaStream_t stream)
+static int dispatch_geom(int lpr, int cpl, int unroll, SpmmArgs &args, cudaStream_t stream)
 {
-    const int teams = 256 / lpr;
-    int block_rows;
-    if (COLMAJOR) {
-        block_rows = teams > 32 ? teams : 32;
-    } else {
-        block_rows = (int)options().spmm_block_rows;
-        if (block_rows <= 0) block_rows = teams * 4;
-        block_rows = ((block_rows + teams - 1) / teams) * teams;
+    int rpw = COLMAJOR ? SPMM_CM_RPW : (int)options().spmm_rpw;
+    if (rpw <= 0) rpw = 8;
+    if (rpw > 31) rpw = 31;
+    args.rpw = rpw;
+    args.piece_blocks = ceil_div_i(args.n_pieces, SPMM_WARPS);
+    const int row_blocks = ceil_div_i(args.m, SPMM_WARPS * rpw);
+#define MXG_GEOM(L, C)                                                                                   \
+    if (lpr == L && cpl == C) {                                                                          \
+        if (V > 1 && unroll == 8) return launch_variant<T, V, L, C, (V > 1 ? 8 : 4), COLMAJOR>(args, row_blocks, stream); \
+        if (V > 1 && unroll == 2) return launch_variant<T, V, L, C, (V > 1 ? 2 : 4), COLMAJOR>(args, row_blocks, stream); \
+        return launch_variant<T, V, L, C, 4, COLMAJOR>(args, row_blocks, stream);                        \
     }
-    args.block_rows = block_rows;
-    args.piece_blocks = ceil_div_i(args.n_pieces, teams);
-    const int row_blocks = ceil_div_i(args.m, block_rows);
-#define MXG_GEOM(L, C)                                                              \
-    if (lpr == L && cpl == C) return launch_variant<T, V, L, C, COLMAJOR>(args, row_blocks, stream);
-    MXG_GEOM(4, 1) MXG_GEOM(4, 2) MXG_GEOM(8, 1) MXG_GEOM(8, 2)
-    MXG_GEOM(16, 1) MXG_GEOM(16, 2) MXG_GEOM(32, 1) MXG_GEOM(32, 2)
+    MXG_GEOM(4, 1) MXG_GEOM(8, 1) MXG_GEOM(16, 1) MXG_GEOM(32, 1) MXG_GEOM(32, 2)
 #undef MXG_GEOM
     return fail(MXG_ERR_ARG, "spmm: unsupported team geometry lpr=%d cpl=%d", lpr, cpl);
 }
@@ -349,15 +411,17 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     const int V = vec ? VEC : 1;
     const int nvec = n / V;
 
+    // lanes per row: the smallest power of two covering the row of B (>= 4), two vectors per lane when a
+    // row is wider than one warp; wider still => several column blocks (grid.y), re-reading the CSR
     int lpr = (int)options().spmm_lpr;
-    int cpl = (int)options().spmm_cpl;
     if (lpr <= 0) {
         lpr = pow2_at_least(nvec);
         if (lpr < 4) lpr = 4;
         if (lpr > 32) lpr = 32;
     }
-    if (cpl <= 0) cpl = (nvec > lpr) ? 2 : 1;
-    if (cpl > 2) cpl = 2;
+    const int cpl = (lpr == 32 && nvec > 32) ? 2 : 1;
+    int unroll = (int)options().spmm_unroll;
+    if (unroll <= 0) unroll = 4;
 
     SpmmArgs args;
     args.m = A->m;
@@ -374,6 +438,7 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.piece_row = A->d_piece_row;
     args.piece_k = A->d_piece_k;
     args.partial = nullptr;
+    args.abort = A->d_abort;
     if (A->n_pieces > 0) {
         MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * (size_t)n * sizeof(T)));
         args.partial = A->d_partial;
@@ -381,11 +446,11 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
 
     int rc;
     if (vec) {
-        rc = colmajor ? dispatch_geom<T, VEC, true>(lpr, cpl, args, stream)
-                      : dispatch_geom<T, VEC, false>(lpr, cpl, args, stream);
+        rc = colmajor ? dispatch_geom<T, VEC, true>(lpr, cpl, unroll, args, stream)
+                      : dispatch_geom<T, VEC, false>(lpr, cpl, unroll, args, stream);
     } else {
-        rc = colmajor ? dispatch_geom<T, 1, true>(lpr, cpl, args, stream)
-                      : dispatch_geom<T, 1, false>(lpr, cpl, args, stream);
+        rc = colmajor ? dispatch_geom<T, 1, true>(lpr, cpl, unroll, args, stream)
+                      : dispatch_geom<T, 1, false>(lpr, cpl, unroll, args, stream);
     }
     MXG_TRY(rc);
 

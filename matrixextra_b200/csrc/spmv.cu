@@ -133,6 +133,7 @@ struct SpmvArgs {
     double *partial;   // [n_pieces]
     int *partial_na;   // [n_pieces]
     int rows_per_team; // rows each team walks inside its CTA
+    const int *abort;  // optional device flag: non-zero => the column ids failed validation, do nothing
 };
 
 template <int YTYPE, typename XT, int LPR>
@@ -146,6 +147,8 @@ __global__ void __launch_bounds__(256) k_spmv(const SpmvArgs g)
     const XT *__restrict__ x = static_cast<const XT *>(g.x);
     const YE *__restrict__ y = static_cast<const YE *>(g.y);
     OE *__restrict__ out = static_cast<OE *>(g.out);
+
+    if (g.abort != nullptr && *g.abort != 0) return;
 
     if ((int)blockIdx.x < g.piece_blocks) {
         // one full warp per long-row piece
@@ -230,6 +233,7 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, voi
     args.piece_k = A->d_piece_k;
     args.partial = nullptr;
     args.partial_na = nullptr;
+    args.abort = A->d_abort;
     if (A->n_pieces > 0) {
         // doubles first, flags after (16 bytes per piece reserved)
         MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * 16));

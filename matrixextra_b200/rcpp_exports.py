@@ -35,7 +35,17 @@ def _fmat(a, dtype):
     return np.asfortranarray(a)
 
 
-def _dense_times_tcsr(X_colmajor, indptr, indices, values, dtype):
+def _result(shape, np_t, out):
+    """The freshly allocated column-major result (what Rcpp returns), or the caller's buffer: ``out=`` is an
+    addition of this mirror so that a caller can hand in page-locked memory and reuse it across calls."""
+    if out is None:
+        return np.empty(shape, dtype=np_t, order="F")
+    if out.shape != tuple(shape) or out.dtype != np_t or not out.flags.f_contiguous or not out.flags.writeable:
+        raise ValueError("out= must be a writeable column-major array of the result's shape and type")
+    return out
+
+
+def _dense_times_tcsr(X_colmajor, indptr, indices, values, dtype, out=None):
     """Out(a x rows, column-major) = X(a x K) . t(S) where S is given by rows (CSR) — the kernel call of
     matmul_dense_csc / tcrossprod_dense_csr (src/matmul.cpp:188-281): a rows-contiguous product with
     n = nrow(X), ldb = ldc = nrow(X)."""
@@ -44,29 +54,29 @@ def _dense_times_tcsr(X_colmajor, indptr, indices, values, dtype):
     p, j, x = _csr(indptr, indices, values)
     a, K = X.shape
     rows = p.size - 1
-    out = np.empty((a, rows), dtype=np_t, order="F")
+    out = _result((a, rows), np_t, out)
     _lib.call("mxg_spmm_csr_dense", dtype, MXG_ROWS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, rows, K, a,
               _vp(p), _vp(j), _vp(x), _vp(X), max(a, 1), _vp(out), max(a, 1))
     return out
 
 
-def matmul_dense_csc_numeric(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1):
-    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F64)
+def matmul_dense_csc_numeric(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1, out=None):
+    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F64, out)
 
 
-def matmul_dense_csc_float32(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1):
-    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F32)
+def matmul_dense_csc_float32(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1, out=None):
+    return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F32, out)
 
 
-def tcrossprod_dense_csr_numeric(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0):
-    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F64)
+def tcrossprod_dense_csr_numeric(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0, out=None):
+    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F64, out)
 
 
-def tcrossprod_dense_csr_float32(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0):
-    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F32)
+def tcrossprod_dense_csr_float32(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0, out=None):
+    return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F32, out)
 
 
-def _csr_times_tdense(indptr, indices, values, Y_colmajor, dtype):
+def _csr_times_tdense(indptr, indices, values, Y_colmajor, dtype, out=None):
     """Out(m x n, column-major) = A_csr(m x K) . t(Y), Y (n x K) column-major — tcrossprod_csr_dense
     (src/matmul.cpp:316-343): column-major output with ldb = nrow(Y), ldc = m."""
     np_t = np.float64 if dtype == MXG_F64 else np.float32
@@ -74,44 +84,44 @@ def _csr_times_tdense(indptr, indices, values, Y_colmajor, dtype):
     p, j, x = _csr(indptr, indices, values)
     n, K = Y.shape
     m = p.size - 1
-    out = np.empty((m, n), dtype=np_t, order="F")
+    out = _result((m, n), np_t, out)
     _lib.call("mxg_spmm_csr_dense", dtype, MXG_COLS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, m, K, n,
               _vp(p), _vp(j), _vp(x), _vp(Y), max(n, 1), _vp(out), max(m, 1))
     return out
 
 
-def tcrossprod_csr_dense_numeric(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1):
-    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F64)
+def tcrossprod_csr_dense_numeric(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1, out=None):
+    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F64, out)
 
 
-def tcrossprod_csr_dense_float32(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1):
-    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F32)
+def tcrossprod_csr_dense_float32(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1, out=None):
+    return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F32, out)
 
 
-def _csr_dvec(indptr, indices, values, y, ytype, y_np, out_np):
+def _csr_dvec(indptr, indices, values, y, ytype, y_np, out_np, out=None):
     p, j, x = _csr(indptr, indices, values)
     y = np.ascontiguousarray(y, dtype=y_np)
     m = p.size - 1
-    out = np.empty(m, dtype=out_np)
+    out = _result((m,), out_np, out)
     # the reference takes K from nowhere (it trusts the indices); here K = length(y) bounds them
     _lib.call("mxg_spmv_csr", ytype, m, int(y.size), _vp(p), _vp(j), _vp(x), _vp(y), _vp(out))
     return out
 
 
-def matmul_csr_dvec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
-    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_NUMERIC, np.float64, np.float64)
+def matmul_csr_dvec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_NUMERIC, np.float64, np.float64, out)
 
 
-def matmul_csr_dvec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
-    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_INTEGER, np.int32, np.float64)
+def matmul_csr_dvec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_INTEGER, np.int32, np.float64, out)
 
 
-def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
-    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_LOGICAL, np.int32, np.float64)
+def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_LOGICAL, np.int32, np.float64, out)
 
 
-def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1):
-    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32)
+def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+    return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32, out)
 
 
 # ---- additions beyond the reference's exports -----------------------------

@@ -227,6 +227,81 @@ def test_reference_fixture_csr(rx, port):
 
 
 # ---------------------------------------------------------------------------------------------------
+# the streamed level-1 path (row chunks over three streams, csrc/pipeline.cu)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def tiny_chunks():
+    """Force the streamed path to cut small inputs into many row chunks (odd entry offsets, chunks with and
+    without long rows, more chunks than value staging buffers)."""
+    from matrixextra_b200 import _lib
+    old = (_lib.get_option("pipe_chunk_nnz"), _lib.get_option("piece"))
+    _lib.set_option("pipe_chunk_nnz", 777)
+    _lib.set_option("piece", 64)
+    yield
+    _lib.set_option("pipe_chunk_nnz", old[0])
+    _lib.set_option("piece", old[1])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_streamed_chunks_match_oracle_and_whole_upload(rx, port, tiny_chunks, dtype):
+    from matrixextra_b200 import _lib
+    p, j, x = powerlaw_csr(3000, 900, 12, seed=21, cap=850)  # ~36k entries -> ~45 chunks, several long rows
+    assert np.diff(p).max() > 64 and p[-1] > 30 * 777
+    rng = np.random.default_rng(21)
+    sfx = _sfx(dtype)
+    for n in (24, 7):
+        X = np.asfortranarray(rng.standard_normal((n, 900)).astype(dtype))
+        got_rm = getattr(rx, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 900)       # rows-contiguous output
+        got_cm = getattr(rx, "tcrossprod_csr_dense_" + sfx)(p, j, x, X, 1)            # column-major output
+        assert rel_err(got_rm, getattr(port, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 900)) <= _tol(dtype)
+        assert rel_err(got_cm, getattr(port, "tcrossprod_csr_dense_" + sfx)(p, j, x, X, 1)) <= _tol(dtype)
+        assert np.array_equal(got_rm.T, got_cm)  # both layouts hold identical bits
+        _lib.set_option("pipeline", 0)
+        try:
+            whole = getattr(rx, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 900)
+        finally:
+            _lib.set_option("pipeline", 1)
+        assert np.array_equal(whole, got_rm)  # chunking never changes a bit: every row is one warp's sum
+        # caller-provided result buffer (bench.py hands in page-locked memory)
+        buf = np.empty((n, 3000), dtype=dtype, order="F")
+        res = getattr(rx, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 900, out=buf)
+        assert res is buf and np.array_equal(buf, got_rm)
+
+
+def test_streamed_spmv_with_na_and_errors(rx, port, tiny_chunks):
+    from matrixextra_b200._lib import MXG_ERR_INDEX, MxgError
+    p, j, x = powerlaw_csr(4000, 700, 9, seed=22, cap=650)
+    rng = np.random.default_rng(22)
+    y = rng.standard_normal(700)
+    assert rel_err(rx.matmul_csr_dvec_numeric(p, j, x, y, 1), port.matmul_csr_dvec_numeric(p, j, x, y, 1)) <= FP64_TOL
+    yi = rng.integers(-5, 5, 700).astype(np.int32)
+    yi[::37] = NA_INT
+    got, want = rx.matmul_csr_dvec_integer(p, j, x, yi, 1), port.matmul_csr_dvec_integer(p, j, x, yi, 1)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert rel_err(got[ok], want[ok]) <= FP64_TOL
+    yf = rng.standard_normal(700).astype(np.float32)
+    assert rel_err(rx.matmul_csr_dvec_float32(p, j, x, yf, 1), port.matmul_csr_dvec_float32(p, j, x, yf, 1)) <= FP32_TOL
+    # a bad column id in a late chunk: an error code, never a fault, and the library keeps working afterwards
+    jb = j.copy()
+    jb[-5] = 700
+    with pytest.raises(MxgError) as ei:
+        rx.matmul_csr_dvec_numeric(p, jb, x, y, 1)
+    assert ei.value.code == MXG_ERR_INDEX
+    X = np.asfortranarray(rng.standard_normal((16, 700)))
+    jb[-5] = -1
+    with pytest.raises(MxgError) as ei:
+        rx.tcrossprod_dense_csr_numeric(X, p, jb, x, 1, 700)
+    assert ei.value.code == MXG_ERR_INDEX
+    pb = p.copy()
+    pb[100] = pb[101] + 1  # decreasing indptr
+    with pytest.raises(MxgError) as ei:
+        rx.tcrossprod_dense_csr_numeric(X, pb, j, x, 1, 700)
+    assert ei.value.code == MXG_ERR_INDEX
+    assert rel_err(rx.matmul_csr_dvec_numeric(p, j, x, y, 1), port.matmul_csr_dvec_numeric(p, j, x, y, 1)) <= FP64_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
 # CSR -> CSC (bit-exact) and the products built on it
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(1, 1, 1.0), (50, 1, 0.5), (1, 300, 0.5), (300, 255, 0.1), (300, 256, 0.1),
