@@ -54,6 +54,7 @@ static int free_handle(mxg_csr_s *h)
     rel(h->d_piece_row);
     rel(h->d_piece_k);
     rel(h->d_partial);
+    rel(h->d_seg);
     delete h;
     return MXG_OK;
 }
@@ -278,7 +279,8 @@ static long *option_slot(const char *name)
     if (!name) return nullptr;
     if (!strcmp(name, "piece")) return &o.piece;
     if (!strcmp(name, "spmm_lpr")) return &o.spmm_lpr;
-    if (!strcmp(name, "spmm_unroll")) return &o.spmm_unroll;
+    if (!strcmp(name, "spmm_panel_mb")) return &o.spmm_panel_mb;
+    if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
     if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;

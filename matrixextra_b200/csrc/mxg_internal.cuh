@@ -47,7 +47,8 @@ extern std::atomic<unsigned long long> g_launches;
 struct Options {
     long piece = 1024;        // nnz per long-row piece; rows longer than this are split
     long spmm_lpr = 0;        // lanes per row of B; 0 = auto
-    long spmm_unroll = 0;     // gathers in flight per sub-team (4 | 8); 0 = auto
+    long spmm_panel_mb = 0;   // column-panel size of the dense operand in MiB; 0 = no panels (default)
+    long spmm_panel_cols = 0; // force a panel width in columns of A (tests / sweeps); 0 = by size
     long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
     long spmv_lpr = 0;        // 0 = auto
     long h2d_chunk_mb = 64;   // staging chunk of the value narrowing in mxg_csr_upload
@@ -87,6 +88,10 @@ struct mxg_csr_s {
     // partial-sum workspace for long rows (grow-only)
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
+
+    // column-panel split table of the SpMM kernels (spmm.cu: plan_panels), cached per panel width
+    int32_t *d_seg = nullptr; // [(seg_panels - 1)][m]
+    int seg_panels = 0, seg_width = 0;
 
     // device flag set by the index validation of the streamed (level-1) path: kernels that see it non-zero
     // return at once instead of gathering through an out-of-range column id

@@ -340,6 +340,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
         const size_t r0 = (size_t)cs.plan.chunk_row[(size_t)c], nr = (size_t)h.m;
         char *d_o = d_Out + (out_layout == MXG_ROWS_CONTIGUOUS ? r0 * ld_o * s : r0 * s);
         MXG_TRY(launch_spmm(&h, dtype, out_layout, n, d_B, ld_b, d_o, ld_o, st->stream));
+        if (h.d_seg) MXG_CUDA_TRY(cudaFreeAsync(h.d_seg, st->stream)); // the chunk's column-panel table
         MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)c], st->stream));
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
         char *h_o = static_cast<char *>(Out) + (out_layout == MXG_ROWS_CONTIGUOUS ? r0 * ldc * s : r0 * s);

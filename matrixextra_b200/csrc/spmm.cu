@@ -21,6 +21,8 @@
 // the streamed CSR arrays and the output; no tensor cores (unstructured, not a dense contraction).
 #include "mxg_internal.cuh"
 
+#include <algorithm>
+
 namespace mxg {
 
 template <typename T, int V>
@@ -67,6 +69,45 @@ __device__ __forceinline__ void st_pack(T *p, const Pack<T, V> &v)
 {
     *reinterpret_cast<Pack<T, V> *>(p) = v;
 }
+
+// streaming (evict-first) accesses for data that is touched once per launch: the CSR arrays and the output
+// rows must not push rows of the dense operand out of L2
+__device__ __forceinline__ Pack<float, 4> ld_stream(const float *p, Pack<float, 4> *)
+{
+    const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+    Pack<float, 4> r;
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    return r;
+}
+__device__ __forceinline__ Pack<double, 2> ld_stream(const double *p, Pack<double, 2> *)
+{
+    const double2 t = __ldcs(reinterpret_cast<const double2 *>(p));
+    Pack<double, 2> r;
+    r.v[0] = t.x; r.v[1] = t.y;
+    return r;
+}
+__device__ __forceinline__ Pack<float, 1> ld_stream(const float *p, Pack<float, 1> *)
+{
+    Pack<float, 1> r;
+    r.v[0] = __ldcs(p);
+    return r;
+}
+__device__ __forceinline__ Pack<double, 1> ld_stream(const double *p, Pack<double, 1> *)
+{
+    Pack<double, 1> r;
+    r.v[0] = __ldcs(p);
+    return r;
+}
+__device__ __forceinline__ void st_stream(float *p, const Pack<float, 4> &v)
+{
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+}
+__device__ __forceinline__ void st_stream(double *p, const Pack<double, 2> &v)
+{
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(v.v[0], v.v[1]));
+}
+__device__ __forceinline__ void st_stream(float *p, const Pack<float, 1> &v) { __stcs(p, v.v[0]); }
+__device__ __forceinline__ void st_stream(double *p, const Pack<double, 1> &v) { __stcs(p, v.v[0]); }
 
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
@@ -160,6 +201,10 @@ struct SpmmArgs {
     const int32_t *piece_k;
     void *partial; // [n_pieces][n]
     const int *abort; // optional device flag: non-zero => the column ids failed validation, do nothing
+    // column panels (PANELS kernels): this launch handles the entries with column id in
+    // [panel * panel_width, (panel + 1) * panel_width); seg[(q - 1) * m + r] = first entry of row r in panel q
+    const int32_t *seg;
+    int panel, n_panels, panel_width;
 };
 
 // Grid: x = [piece CTAs | row CTAs], y = column blocks of NB = LPR*V*CPL output columns.
@@ -167,13 +212,20 @@ struct SpmmArgs {
 // batch by batch (32 stored entries per batch, loaded coalesced); the (index, value) batch that follows
 // the one being gathered — in the same row or at the start of the next — is already in flight, so the
 // only exposed latencies are the gathers themselves, U whole-row gathers deep per sub-team.
-template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR>
-__global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
+//
+// PANELS: the dense operand is wider than L2, so the product runs as one launch per COLUMN PANEL of A (a slab
+// of rows of B small enough to stay L2-resident): launch q adds, for every row, the entries whose column lies
+// in panel q to the output row (read-modify-write from the second panel on; rows without entries in the
+// panel are not touched).  Entries are consumed in stored order panel after panel, so for sorted rows the sum
+// order is unchanged; for unsorted rows the split points still partition the row (see k_panel_segments).
+template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS>
+__global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? 8 : 4) k_spmm(const SpmmArgs g)
 {
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
     constexpr int BR = SPMM_WARPS * SPMM_CM_RPW;
     constexpr int TLD = BR + 1;
     __shared__ T tile[COLMAJOR ? NB * TLD : 1];
+    __shared__ unsigned char s_write[COLMAJOR ? BR : 1]; // tile rows this launch has to write
 
     const int32_t *__restrict__ p = g.p;
     const int32_t *__restrict__ j = g.j;
@@ -207,18 +259,23 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
         const int row = g.piece_row[pc];
         const int a = p[row] + g.piece_k[pc] * g.piece;
         const int b = min(a + g.piece, p[row + 1]);
+        if (PANELS) {
+            // a piece (<= `piece` consecutive entries of one row) runs in the launch of its first entry's panel
+            const int pq = min(__ldg(j + a) / g.panel_width, g.n_panels - 1);
+            if (pq != g.panel) return;
+        }
         int cj = 0;
         T cx = T(0);
         if (a + lane < b) {
-            cj = __ldg(j + a + lane);
-            cx = __ldg(x + a + lane);
+            cj = __ldcs(j + a + lane);
+            cx = __ldcs(x + a + lane);
         }
         for (int pos = a; pos < b; pos += 32) {
             int nj = 0;
             T nx = T(0);
             if (pos + 32 + lane < b) {
-                nj = __ldg(j + pos + 32 + lane);
-                nx = __ldg(x + pos + 32 + lane);
+                nj = __ldcs(j + pos + 32 + lane);
+                nx = __ldcs(x + pos + 32 + lane);
             }
             batch_gather<T, V, LPR, CPL, U>(acc, cj, cx, min(32, b - pos), sub, B, g.ldb, col, cok);
             cj = nj;
@@ -239,15 +296,35 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
     const int row0 = (rb * SPMM_WARPS + warp) * rpw;
     const int nr = min(rpw, g.m - row0); // rows this warp owns (<= 0: none)
 
+    const bool first_panel = !PANELS || g.panel == 0;
+    if (COLMAJOR) {
+        if (lane < SPMM_CM_RPW) s_write[warp * SPMM_CM_RPW + lane] = 0;
+        __syncwarp();
+    }
+
     if (nr > 0) {
-        int pv = 0;
+        int pv = 0, sa = 0, se = 0;
         if (lane <= nr) pv = __ldg(p + row0 + lane);
+        if (PANELS) {
+            const int pnext = __shfl_down_sync(FULL, pv, 1);
+            if (lane < nr) {
+                const size_t r_ = (size_t)row0 + lane;
+                sa = g.panel > 0 ? __ldg(g.seg + (size_t)(g.panel - 1) * g.m + r_) : pv;
+                se = g.panel < g.n_panels - 1 ? __ldg(g.seg + (size_t)g.panel * g.m + r_) : pnext;
+            }
+        }
         // row rr: entries [ra, re); rows longer than a piece are left to the piece section + fix-up kernel
         auto bounds = [&](const int rr, int &ra, int &re, bool &rskip) {
-            ra = __shfl_sync(FULL, pv, rr);
-            const int rb_ = __shfl_sync(FULL, pv, rr + 1);
-            rskip = (rb_ - ra) > g.piece;
-            re = rskip ? ra : rb_;
+            const int rp0 = __shfl_sync(FULL, pv, rr);
+            const int rp1 = __shfl_sync(FULL, pv, rr + 1);
+            rskip = (rp1 - rp0) > g.piece;
+            if (PANELS) {
+                ra = __shfl_sync(FULL, sa, rr);
+                re = rskip ? ra : __shfl_sync(FULL, se, rr);
+            } else {
+                ra = rp0;
+                re = rskip ? ra : rp1;
+            }
         };
         int r = 0, a, e;
         bool skip;
@@ -256,11 +333,18 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
         int cj = 0;
         T cx = T(0);
         if (pos + lane < e) {
-            cj = __ldg(j + pos + lane);
-            cx = __ldg(x + pos + lane);
+            cj = __ldcs(j + pos + lane);
+            cx = __ldcs(x + pos + lane);
         }
+        Pack<T, V> prev[CPL]; // later panels: the output row so far, fetched while the row's gathers are in flight
         while (true) {
             const int cnt = min(32, e - pos); // <= 0 for a row without (eligible) entries
+            if (PANELS && !COLMAJOR && !first_panel && pos == a && e > a && sub == 0) {
+                const T *src = Out + (size_t)(row0 + r) * g.ldc;
+#pragma unroll
+                for (int c = 0; c < CPL; c++)
+                    if (cok[c]) prev[c] = ld_stream(src + col[c], (Pack<T, V> *)nullptr);
+            }
             // where the next batch starts: further along this row, or at the start of the next one
             int npos = pos + 32, nrow = r, na = a, ne = e;
             bool nskip = skip;
@@ -275,16 +359,18 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
             int nj = 0;
             T nx = T(0);
             if (nrow < nr && npos + lane < ne) {
-                nj = __ldg(j + npos + lane);
-                nx = __ldg(x + npos + lane);
+                nj = __ldcs(j + npos + lane);
+                nx = __ldcs(x + npos + lane);
             }
             batch_gather<T, V, LPR, CPL, U>(acc, cj, cx, cnt, sub, B, g.ldb, col, cok);
             if (last) {
-                if (!skip) {
+                // the first panel writes every (short) row, later panels only the rows they have entries for
+                if (!skip && (first_panel || e > a)) {
                     subteam_reduce<T, V, LPR, CPL>(acc);
                     if (sub == 0) {
                         if (COLMAJOR) {
                             const int rl = warp * SPMM_CM_RPW + r;
+                            if (l == 0) s_write[rl] = 1;
 #pragma unroll
                             for (int c = 0; c < CPL; c++)
                                 if (cok[c]) {
@@ -295,7 +381,13 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
                             T *dst = Out + (size_t)(row0 + r) * g.ldc;
 #pragma unroll
                             for (int c = 0; c < CPL; c++)
-                                if (cok[c]) st_pack<T, V>(dst + col[c], acc[c]);
+                                if (cok[c]) {
+                                    if (!first_panel) {
+#pragma unroll
+                                        for (int i = 0; i < V; i++) acc[c].v[i] = prev[c].v[i] + acc[c].v[i];
+                                    }
+                                    st_stream(dst + col[c], acc[c]);
+                                }
                         }
                     }
                 }
@@ -317,12 +409,39 @@ __global__ void __launch_bounds__(SPMM_THREADS) k_spmm(const SpmmArgs g)
         const int tile_row0 = rb * BR;
         const int row = tile_row0 + lane; // BR == 32: one tile row per lane
         const int ncols = min(NB, g.n - col0);
-        bool w = row < g.m;
-        if (w) w = (p[row + 1] - p[row]) <= g.piece; // long rows are written by the fix-up kernel
-        if (w) {
+        // long rows are written by the fix-up kernel, rows without entries in a later panel stay as they are
+        if (row < g.m && s_write[lane]) {
             T *dst = Out + (size_t)row;
-            for (int c = warp; c < ncols; c += SPMM_WARPS) dst[(size_t)(col0 + c) * g.ldc] = tile[c * TLD + lane];
+            for (int c = warp; c < ncols; c += SPMM_WARPS) {
+                T v = tile[c * TLD + lane];
+                T *q = dst + (size_t)(col0 + c) * g.ldc;
+                if (!first_panel) v = __ldcs(q) + v;
+                __stcs(q, v);
+            }
         }
+    }
+}
+
+// seg[(q - 1) * m + r] = first entry of row r whose column id is >= q * width, q = 1 .. P-1, searched from the
+// previous split point on: the P segments always partition the row's entries, sorted or not (for unsorted rows
+// only the L2 locality of the panels suffers, never the result).
+__global__ void __launch_bounds__(256) k_panel_segments(int m, const int32_t *__restrict__ p, const int32_t *__restrict__ j,
+                                                        int width, int n_panels, int32_t *__restrict__ seg)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    int lo = p[r];
+    const int hi = p[r + 1];
+    for (int q = 1; q < n_panels; q++) {
+        const int target = q * width;
+        int a = lo, b = hi; // first e in [lo, hi) with j[e] >= target
+        while (a < b) {
+            const int mid = a + ((b - a) >> 1);
+            if (__ldg(j + mid) < target) a = mid + 1;
+            else b = mid;
+        }
+        lo = a;
+        seg[(size_t)(q - 1) * m + r] = lo;
     }
 }
 
@@ -355,16 +474,23 @@ __global__ void __launch_bounds__(256) k_fill_zero_2d(T *__restrict__ Out, size_
 }
 
 template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR>
-static int launch_variant(const SpmmArgs &args, int row_blocks, cudaStream_t stream)
+static int launch_variant(SpmmArgs &args, int row_blocks, cudaStream_t stream)
 {
     constexpr int NB = LPR * V * CPL;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
-    MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR>), grid, SPMM_THREADS, 0, stream, args);
+    if (args.n_panels <= 1) {
+        MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false>), grid, SPMM_THREADS, 0, stream, args);
+        return MXG_OK;
+    }
+    for (int q = 0; q < args.n_panels; q++) {
+        args.panel = q;
+        MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, true>), grid, SPMM_THREADS, 0, stream, args);
+    }
     return MXG_OK;
 }
 
 template <typename T, int V, bool COLMAJOR>
-static int dispatch_geom(int lpr, int cpl, int unroll, SpmmArgs &args, cudaStream_t stream)
+static int dispatch_geom(int lpr, int cpl, SpmmArgs &args, cudaStream_t stream)
 {
     int rpw = COLMAJOR ? SPMM_CM_RPW : (int)options().spmm_rpw;
     if (rpw <= 0) rpw = 8;
@@ -373,11 +499,7 @@ static int dispatch_geom(int lpr, int cpl, int unroll, SpmmArgs &args, cudaStrea
     args.piece_blocks = ceil_div_i(args.n_pieces, SPMM_WARPS);
     const int row_blocks = ceil_div_i(args.m, SPMM_WARPS * rpw);
 #define MXG_GEOM(L, C)                                                                                   \
-    if (lpr == L && cpl == C) {                                                                          \
-        if (V > 1 && unroll == 8) return launch_variant<T, V, L, C, (V > 1 ? 8 : 4), COLMAJOR>(args, row_blocks, stream); \
-        if (V > 1 && unroll == 2) return launch_variant<T, V, L, C, (V > 1 ? 2 : 4), COLMAJOR>(args, row_blocks, stream); \
-        return launch_variant<T, V, L, C, 4, COLMAJOR>(args, row_blocks, stream);                        \
-    }
+    if (lpr == L && cpl == C) return launch_variant<T, V, L, C, 4, COLMAJOR>(args, row_blocks, stream);
     MXG_GEOM(4, 1) MXG_GEOM(8, 1) MXG_GEOM(16, 1) MXG_GEOM(32, 1) MXG_GEOM(32, 2)
 #undef MXG_GEOM
     return fail(MXG_ERR_ARG, "spmm: unsupported team geometry lpr=%d cpl=%d", lpr, cpl);
@@ -388,6 +510,50 @@ static int pow2_at_least(int v)
     int r = 1;
     while (r < v) r <<= 1;
     return r;
+}
+
+// Column panels pay when the dense operand overflows L2 (every stored entry then re-fetches its row of B from
+// HBM) and the extra read-modify-write passes over the output cost less than those re-fetches:
+//   saved  ~ nnz * row_bytes * (1 - L2 / B_bytes) / 2      extra ~ m * row_bytes * (2 P - 2)
+// The split table is cached in the handle (one table per panel width).
+static int plan_panels(mxg_csr_s *A, size_t b_bytes, cudaStream_t stream, SpmmArgs &args)
+{
+    const long forced_cols = options().spmm_panel_cols;
+    long panel_mb = options().spmm_panel_mb;
+    // Off unless asked for: measured on B200 (profiles/README.md, r01 v3 sweep) the read-modify-write passes and
+    // the short per-panel row segments cost more than the saved HBM re-fetches of B at the BASELINE shapes
+    // (cfg3 fp32 k=64: 3.24 ms without panels, 3.56 / 4.05 / 5.9 ms with 128 / 64 / 32 MiB panels).
+    if (panel_mb <= 0 && forced_cols <= 0) return MXG_OK;
+    if (A->K <= 1 || A->m <= 0 || A->nnz <= 0) return MXG_OK;
+    int width;
+    if (forced_cols > 0) {
+        width = (int)std::min<long>(forced_cols, A->K);
+    } else {
+        const size_t panel_bytes = (size_t)panel_mb << 20;
+        if (b_bytes <= panel_bytes + panel_bytes / 2) return MXG_OK; // fits L2 well enough
+        int P = (int)((b_bytes + panel_bytes - 1) / panel_bytes);
+        if (P > 32) return MXG_OK;
+        const double saved = 0.5 * (double)A->nnz * (1.0 - (double)panel_bytes / (double)b_bytes);
+        const double extra = (double)A->m * (2.0 * P - 2.0);
+        if (extra >= saved) return MXG_OK;
+        width = (A->K + P - 1) / P;
+    }
+    if (width < 1) width = 1;
+    const int P = (A->K + width - 1) / width;
+    if (P <= 1) return MXG_OK;
+    if (P > 64) return fail(MXG_ERR_ARG, "spmm: more than 64 column panels requested");
+    if (A->d_seg == nullptr || A->seg_width != width || A->seg_panels != P) {
+        if (A->d_seg) MXG_CUDA_TRY(cudaFreeAsync(A->d_seg, stream));
+        A->d_seg = nullptr;
+        MXG_CUDA_TRY(cudaMallocAsync(&A->d_seg, sizeof(int32_t) * (size_t)(P - 1) * (size_t)A->m, stream));
+        A->seg_width = width;
+        A->seg_panels = P;
+        MXG_LAUNCH(k_panel_segments, ceil_div_i(A->m, 256), 256, 0, stream, A->m, A->d_p, A->d_j, width, P, A->d_seg);
+    }
+    args.seg = A->d_seg;
+    args.n_panels = P;
+    args.panel_width = width;
+    return MXG_OK;
 }
 
 template <typename T>
@@ -420,8 +586,6 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
         if (lpr > 32) lpr = 32;
     }
     const int cpl = (lpr == 32 && nvec > 32) ? 2 : 1;
-    int unroll = (int)options().spmm_unroll;
-    if (unroll <= 0) unroll = 4;
 
     SpmmArgs args;
     args.m = A->m;
@@ -439,6 +603,11 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.piece_k = A->d_piece_k;
     args.partial = nullptr;
     args.abort = A->d_abort;
+    args.seg = nullptr;
+    args.panel = 0;
+    args.n_panels = 1;
+    args.panel_width = A->K > 0 ? A->K : 1;
+    MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
     if (A->n_pieces > 0) {
         MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * (size_t)n * sizeof(T)));
         args.partial = A->d_partial;
@@ -446,11 +615,11 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
 
     int rc;
     if (vec) {
-        rc = colmajor ? dispatch_geom<T, VEC, true>(lpr, cpl, unroll, args, stream)
-                      : dispatch_geom<T, VEC, false>(lpr, cpl, unroll, args, stream);
+        rc = colmajor ? dispatch_geom<T, VEC, true>(lpr, cpl, args, stream)
+                      : dispatch_geom<T, VEC, false>(lpr, cpl, args, stream);
     } else {
-        rc = colmajor ? dispatch_geom<T, 1, true>(lpr, cpl, unroll, args, stream)
-                      : dispatch_geom<T, 1, false>(lpr, cpl, unroll, args, stream);
+        rc = colmajor ? dispatch_geom<T, 1, true>(lpr, cpl, args, stream)
+                      : dispatch_geom<T, 1, false>(lpr, cpl, args, stream);
     }
     MXG_TRY(rc);
 

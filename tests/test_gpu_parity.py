@@ -227,6 +227,53 @@ def test_reference_fixture_csr(rx, port):
 
 
 # ---------------------------------------------------------------------------------------------------
+# column panels of the SpMM kernels (one launch per L2-sized slab of the dense operand, csrc/spmm.cu)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(params=[7, 64, 333])
+def narrow_panels(request):
+    """Force column panels a few columns wide so that small inputs run 2 .. 60 read-modify-write launches."""
+    from matrixextra_b200 import _lib
+    old = (_lib.get_option("spmm_panel_cols"), _lib.get_option("piece"))
+    _lib.set_option("spmm_panel_cols", request.param)
+    _lib.set_option("piece", 48)
+    yield request.param
+    _lib.set_option("spmm_panel_cols", old[0])
+    _lib.set_option("piece", old[1])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_column_panels_match_oracle(rx, port, narrow_panels, dtype):
+    p, j, x = powerlaw_csr(1500, 400, 10, seed=31, cap=390)  # rows longer than a piece span many panels
+    assert np.diff(p).max() > 48
+    rng = np.random.default_rng(31)
+    sfx = _sfx(dtype)
+    for n in (64, 20, 5):
+        X = np.asfortranarray(rng.standard_normal((n, 400)).astype(dtype))
+        got_rm = getattr(rx, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 400)
+        got_cm = getattr(rx, "tcrossprod_csr_dense_" + sfx)(p, j, x, X, 1)
+        assert rel_err(got_rm, getattr(port, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, 400)) <= _tol(dtype)
+        assert rel_err(got_cm, getattr(port, "tcrossprod_csr_dense_" + sfx)(p, j, x, X, 1)) <= _tol(dtype)
+        assert np.array_equal(got_rm.T, got_cm)
+
+
+def test_column_panels_unsorted_rows_and_empty_rows(rx, port, narrow_panels):
+    # unsorted columns with duplicates: the split points still partition every row, so only locality suffers
+    rng = np.random.default_rng(32)
+    m, K, n = 700, 300, 16
+    lens = rng.integers(0, 40, m)
+    lens[::9] = 0
+    p = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    j = rng.integers(0, K, p[-1]).astype(np.int32)
+    x = rng.standard_normal(p[-1])
+    X = np.asfortranarray(rng.standard_normal((n, K)))
+    got = rx.tcrossprod_dense_csr_numeric(X, p, j, x, 1, K)
+    assert rel_err(got, port.tcrossprod_dense_csr_numeric(X, p, j, x, 1, K)) <= FP64_TOL
+    assert np.all(got[:, lens == 0] == 0.0) and not np.signbit(got[:, lens == 0]).any()  # exact +0.0 rows
+    gotc = rx.tcrossprod_csr_dense_numeric(p, j, x, X, 1)
+    assert np.array_equal(got.T, gotc)
+
+
+# ---------------------------------------------------------------------------------------------------
 # the streamed level-1 path (row chunks over three streams, csrc/pipeline.cu)
 # ---------------------------------------------------------------------------------------------------
 @pytest.fixture()
