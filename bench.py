@@ -233,21 +233,39 @@ def run_ours(args):
     g = torch.Generator(device="cuda").manual_seed(4242)  # replicated dense operand: same on every rank
     op = wl["op"]
     At = None
+    out_rows = K if op == "crossprod" else m
+    # N > 1: the products store every finished row into ALL ranks' results over NVLink (PeerResult), so the
+    # all-gather of north_star subsystem 4 is fused into the kernel; crossprod keeps the NCCL collective
+    fused = world > 1 and op in ("spmv", "dense_tcsr", "csr_dense")
+    peer = None
     if op == "spmv":
         dense = torch.randn(K, device="cuda", dtype=torch.float64, generator=g)
-        out_all = torch.empty(world * m, device="cuda", dtype=torch.float64)
+        shape_all, dt_all = (world * m,), torch.float64
     elif op == "crossprod":
         dense = torch.randn(m, n, device="cuda", dtype=tdt, generator=g)  # Y rows-contiguous [m][n]
-        out_all = torch.empty(world * K, n, device="cuda", dtype=tdt)
+        shape_all, dt_all = (world * K, n), tdt
     else:
         dense = torch.randn(K, n, device="cuda", dtype=tdt, generator=g)  # (n x K) column-major R matrix
-        out_all = torch.empty(world * m, n, device="cuda", dtype=tdt)
-    out_rows = K if op == "crossprod" else m
+        shape_all, dt_all = (world * m, n), tdt
+    if fused:
+        from matrixextra_b200.sharded import PeerResult
+        peer = PeerResult(int(np.prod(shape_all)) * (8 if dt_all == torch.float64 else 4), dist, rank, world)
+        out_all = peer.tensor(shape_all, dt_all)
+    else:
+        out_all = torch.empty(shape_all, device="cuda", dtype=dt_all)
     out_local = out_all[rank * out_rows:(rank + 1) * out_rows]
     colmajor_tmp = None
     if op == "csr_dense":
-        # column-major (R layout) output block m x n, ldc = m
+        # column-major (R layout) output block m x n, ldc = m  (N = 1, and the compute-only / NCCL variants)
         colmajor_tmp = torch.empty(n, m, device="cuda", dtype=tdt)
+    dst = ldc_all = None
+    if fused:
+        if op == "spmv":
+            dst = peer.dst_ptrs(rank * m * 8)
+        elif op == "dense_tcsr":
+            dst, ldc_all = peer.dst_ptrs(rank * m * n * s), n
+        else:  # one global column-major (world*m x n) matrix: this rank owns rows [rank*m, (rank+1)*m)
+            dst, ldc_all = peer.dst_ptrs(rank * m * s), world * m
 
     def compute():
         nonlocal At
@@ -264,11 +282,23 @@ def run_ours(args):
             At.spmm(dense, out_local, n, mdt, MXG_ROWS_CONTIGUOUS)
 
     def step(with_gather=True):
+        if fused and with_gather:
+            if op == "spmv":
+                A.spmv_bcast(dense, dst)
+            else:
+                A.spmm_bcast(dense, dst, n, mdt, MXG_ROWS_CONTIGUOUS if op == "dense_tcsr" else MXG_COLS_CONTIGUOUS, ldc=ldc_all)
+            peer.barrier()  # device-side: every rank's rows have landed when the stream gets past this
+            return
         compute()
         if world > 1 and with_gather:
-            # row-major blocks gather in place; column-major (R layout) blocks are gathered block by block
             src = colmajor_tmp if op == "csr_dense" else out_local
             dist.all_gather_into_tensor(out_all.view(-1), src.view(-1))
+
+    def nccl_step():
+        # the unfused baseline: product into the local block, then one NCCL all-gather of the blocks
+        compute()
+        src = colmajor_tmp if op == "csr_dense" else out_local
+        dist.all_gather_into_tensor(nccl_all.view(-1), src.contiguous().view(-1))
 
     def timed(fn, steps):
         if world > 1:
@@ -297,6 +327,15 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_compute = timed(lambda: step(False), args.steps) if world > 1 else ms_total
+    ms_nccl = None
+    if fused:
+        nccl_all = torch.empty(shape_all, device="cuda", dtype=dt_all)
+        for _ in range(2):
+            nccl_step()
+        ms_nccl = timed(nccl_step, args.steps) / args.steps
+        del nccl_all
+        if peer.failed():
+            raise SystemExit("peer barrier timed out")
 
     nnz_all = nnz
     if world > 1:
@@ -320,7 +359,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": wl["dtype"], "data": "synthetic (device-generated, Philox4x32-10; SURVEY.md 8d)",
         "config": {"workload": wl["desc"], "rows_per_gpu": m, "cols": K, "nnz_per_gpu": nnz, "n": n,
-                   "parallelism": f"row-block shards x{world}, replicated dense operand, NCCL all-gather of output blocks"
+                   "parallelism": (f"row-block shards x{world}, replicated dense operand, all-gather of the output row blocks "
+                                   + ("fused into the product kernel (NVLink peer stores)" if fused else "by NCCL"))
                    if world > 1 else "single GPU",
                    "l2_policy": "operands (CSR %.0f MB + dense %.0f MB + out %.0f MB) exceed the 126 MB L2; no flush needed"
                    % (nnz * (4 + s) / 1e6, s * K * n / 1e6, s * out_rows * n / 1e6),
@@ -333,6 +373,11 @@ def run_ours(args):
                              % ((nnz * (4 + s) + 4 * (m + 1) + s * nnz * n + s * m * n) / 1e9)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if world > 1:
+        result["allgather"] = ({"how": "fused: every finished row is stored into all ranks' results over NVLink by the product "
+                                       "kernel (mxg_dev_spmm_bcast) + device-side flag barrier", "ms_per_step": ms_step,
+                                "nccl_after_compute_ms_per_step": ms_nccl, "bytes_received_per_gpu": int((world - 1) * out_rows * n * s)}
+                               if fused else {"how": "NCCL all_gather_into_tensor after the product", "ms_per_step": ms_step})
 
     # ---- end to end through the reference-facing entry point with host buffers (rank-local) ----------
     e2e = None
@@ -409,6 +454,9 @@ def run_ours(args):
             if name and name != args.workload:
                 result["others"][name] = quick_kernel_bench(name, args)
 
+    if peer is not None:
+        del out_all, out_local
+        peer.close(dist)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

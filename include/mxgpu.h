@@ -49,6 +49,9 @@ extern "C" {
 #define MXG_Y_LOGICAL 2 /* int y, NA_LOGICAL    : matmul_csr_dvec_logical  src/matmul.cpp:453 */
 #define MXG_Y_FLOAT32 3 /* float y, float result: matmul_csr_dvec_float32  src/matmul.cpp:469 */
 
+/* most result buffers one product can write (the local one + the peer-mapped ones of the other GPUs of a box) */
+#define MXG_MAX_DST 8
+
 /* which copies of the CSR values a device-resident handle keeps */
 #define MXG_KEEP_F64 1
 #define MXG_KEEP_F32 2
@@ -153,6 +156,31 @@ int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,
                  const void *d_B, size_t ldb, void *d_Out, size_t ldc, void *stream);
 
 int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream);
+
+/* Multi-GPU form of the two products (north_star subsystem 4; no counterpart in the reference, which is one
+ * process on shared memory: the OpenMP row loop of src/matmul.cpp:132-136 is the decomposition kept here).
+ * The CSR is split into row blocks, one per GPU; every finished output row is stored into ALL n_dst result
+ * buffers — d_outs[0] the local one, the others the peers' buffers mapped with mxg_ipc_open (or plain
+ * pointers after cudaDeviceEnablePeerAccess in a single process) — so the all-gather of the row blocks
+ * travels over NVLink store by store while the product is still running.  Every d_outs[g] already points
+ * at this block's first row inside rank g's full result and shares the leading dimension ldc. */
+int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
+                       int n_dst, void *const *d_outs, size_t ldc, void *stream);
+int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream);
+
+/* Device memory that can be shared with the other processes of the box, and its handles (cudaIpc*). */
+int mxg_dev_alloc(size_t bytes, void **d_ptr);
+int mxg_dev_free(void *d_ptr);
+int mxg_ipc_export(const void *d_ptr, unsigned char handle[64]);
+int mxg_ipc_open(const unsigned char handle[64], void **d_ptr);
+int mxg_ipc_close(void *d_ptr);
+
+/* Completion barrier of a bcast step, stream-ordered and device-side: stores `epoch` into slot `rank` of every
+ * peer's flag array (peer_flags[g] = rank g's array of `world` ints, peer-mapped; peer_flags[rank] = the local
+ * array) and waits until every local slot has reached `epoch`.  After it, all ranks' rows have landed in the
+ * local result.  Gives up after ~10 s and raises the sticky flag readable with mxg_dev_barrier_failed(). */
+int mxg_dev_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, void *stream);
+int mxg_dev_barrier_failed(int *failed);
 
 /* New device-resident CSC of A (as a CSR handle of t(A): K rows, m columns). */
 int mxg_dev_csr2csc(mxg_csr_t A, int keep, void *stream, mxg_csr_t *At);

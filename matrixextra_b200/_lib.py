@@ -46,6 +46,15 @@ _SIGNATURES = {
     "mxg_csr_download": [_vp, _vp, _vp, _vp],
     "mxg_dev_spmm": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_spmv": [_vp, _i32, _vp, _vp, _vp],
+    "mxg_dev_spmm_bcast": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
+    "mxg_dev_spmv_bcast": [_vp, _i32, _vp, _i32, _vp, _vp],
+    "mxg_dev_alloc": [_sz, C.POINTER(_vp)],
+    "mxg_dev_free": [_vp],
+    "mxg_ipc_export": [_vp, _vp],
+    "mxg_ipc_open": [_vp, C.POINTER(_vp)],
+    "mxg_ipc_close": [_vp],
+    "mxg_dev_peer_barrier": [_i32, _i32, _vp, _i32, _vp],
+    "mxg_dev_barrier_failed": [C.POINTER(C.c_int)],
     "mxg_dev_csr2csc": [_vp, _i32, _vp, C.POINTER(_vp)],
     "mxg_dev_transpose_dense": [_i32, _sz, _sz, _vp, _sz, _vp, _sz, _vp],
     "mxg_row_partition": [_i32, _vp, _i32, _vp],

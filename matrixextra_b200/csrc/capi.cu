@@ -436,6 +436,71 @@ int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, co
     return MXG_OK;
 }
 
+int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
+                       int n_dst, void *const *d_outs, size_t ldc, void *stream)
+{
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmm_bcast: NULL handle");
+    if (b_layout != MXG_ROWS_CONTIGUOUS) return fail(MXG_ERR_UNSUPPORTED, "dev_spmm_bcast: the dense operand must be rows-contiguous");
+    return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream)
+{
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmv_bcast: NULL handle");
+    return launch_spmv_multi(A, ytype, d_y, n_dst, d_outs, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_alloc(size_t bytes, void **d_ptr)
+{
+    if (!d_ptr) return fail(MXG_ERR_ARG, "dev_alloc: NULL argument");
+    *d_ptr = nullptr;
+    MXG_CUDA_TRY(cudaMalloc(d_ptr, bytes > 0 ? bytes : 16)); // not pool memory: cudaIpcGetMemHandle needs cudaMalloc
+    return MXG_OK;
+}
+
+int mxg_dev_free(void *d_ptr)
+{
+    if (d_ptr) MXG_CUDA_TRY(cudaFree(d_ptr));
+    return MXG_OK;
+}
+
+int mxg_ipc_export(const void *d_ptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!d_ptr || !handle) return fail(MXG_ERR_ARG, "ipc_export: NULL argument");
+    cudaIpcMemHandle_t h;
+    MXG_CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle, &h, 64);
+    return MXG_OK;
+}
+
+int mxg_ipc_open(const unsigned char handle[64], void **d_ptr)
+{
+    if (!d_ptr || !handle) return fail(MXG_ERR_ARG, "ipc_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *d_ptr = nullptr;
+    MXG_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MXG_OK;
+}
+
+int mxg_ipc_close(void *d_ptr)
+{
+    if (d_ptr) MXG_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return MXG_OK;
+}
+
+int mxg_dev_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, void *stream)
+{
+    return launch_peer_barrier(rank, world, peer_flags, epoch, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_barrier_failed(int *failed)
+{
+    if (!failed) return fail(MXG_ERR_ARG, "barrier_failed: NULL argument");
+    return peer_barrier_failed(failed);
+}
+
 int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream)
 {
     if (!A) return fail(MXG_ERR_ARG, "dev_spmv: NULL handle");

@@ -317,6 +317,54 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
     return MXG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-GPU completion barrier of the bcast products.  Launched behind the product kernel on the same
+// stream, so the product's peer stores are complete (kernel boundary) before the flag stores are issued;
+// one lane per peer publishes `epoch` in the peer's flag array, then polls its own slot of the local array.
+// ------------------------------------------------------------------------------------------------
+struct PeerFlags {
+    int *flags[MXG_MAX_DST];
+};
+__device__ int g_barrier_failed = 0;
+
+__global__ void __launch_bounds__(32) k_peer_barrier(int rank, int world, const PeerFlags pf, int epoch)
+{
+    const int g = threadIdx.x;
+    if (g >= world || g == rank) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(pf.flags[g] + rank) = epoch;
+    __threadfence_system();
+    const volatile int *mine = reinterpret_cast<volatile int *>(pf.flags[rank] + g);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*mine < epoch) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ULL) { // 10 s: a peer died; do not hang the device
+            g_barrier_failed = 1;
+            return;
+        }
+        __nanosleep(200);
+    }
+}
+
+int launch_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, cudaStream_t stream)
+{
+    if (world < 1 || world > MXG_MAX_DST || rank < 0 || rank >= world || !peer_flags)
+        return fail(MXG_ERR_ARG, "peer_barrier: bad arguments");
+    if (world == 1) return MXG_OK;
+    PeerFlags pf;
+    for (int g = 0; g < MXG_MAX_DST; g++) pf.flags[g] = g < world ? peer_flags[g] : nullptr;
+    MXG_LAUNCH(k_peer_barrier, 1, 32, 0, stream, rank, world, pf, epoch);
+    return MXG_OK;
+}
+
+int peer_barrier_failed(int *failed)
+{
+    MXG_CUDA_TRY(cudaMemcpyFromSymbol(failed, g_barrier_failed, sizeof(int)));
+    return MXG_OK;
+}
+
 int ensure_partial(mxg_csr_s *h, size_t bytes)
 {
     if (bytes <= h->partial_bytes) return MXG_OK;

@@ -117,6 +117,10 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
                   const void *y, void *out);
 int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream);
 
+// layout.cu: device-side completion barrier between the GPUs of a box (bcast products)
+int launch_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, cudaStream_t stream);
+int peer_barrier_failed(int *failed);
+
 // layout.cu
 int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream);
 int convert_f64_to_f32(const double *d_src, float *d_dst, size_t n, cudaStream_t stream);
@@ -126,8 +130,12 @@ int ensure_partial(mxg_csr_s *h, size_t bytes);
 // spmm.cu
 int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
                 void *d_Out, size_t ldc, cudaStream_t stream);
+// the same product written to n_dst result buffers (local and / or peer-mapped), all with leading dimension ldc
+int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream);
 // spmv.cu
 int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream);
+int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream);
 // transpose.cu
 int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src,
                            void *d_dst, size_t ld_dst, cudaStream_t stream);

@@ -191,8 +191,12 @@ struct SpmmArgs {
     const void *x;
     const void *B;
     size_t ldb;
-    void *Out;
+    void *Out;  // the local result
     size_t ldc;
+    // additional copies of every finished row (peer-mapped result buffers of the other GPUs of the box, same
+    // leading dimension): the all-gather of the row blocks happens store by store, inside the product
+    void *extra[MXG_MAX_DST - 1];
+    int n_extra;
     int rpw; // consecutive rows per warp (<= 31; column-major output uses SPMM_CM_RPW)
     int piece;
     int n_pieces;
@@ -387,6 +391,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? 8 : 4) k_spmm(const S
                                         for (int i = 0; i < V; i++) acc[c].v[i] = prev[c].v[i] + acc[c].v[i];
                                     }
                                     st_stream(dst + col[c], acc[c]);
+                                    for (int d = 0; d < g.n_extra; d++)
+                                        st_stream(static_cast<T *>(g.extra[d]) + (size_t)(row0 + r) * g.ldc + col[c], acc[c]);
                                 }
                         }
                     }
@@ -417,6 +423,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? 8 : 4) k_spmm(const S
                 T *q = dst + (size_t)(col0 + c) * g.ldc;
                 if (!first_panel) v = __ldcs(q) + v;
                 __stcs(q, v);
+                for (int d = 0; d < g.n_extra; d++) __stcs(static_cast<T *>(g.extra[d]) + (size_t)row + (size_t)(col0 + c) * g.ldc, v);
             }
         }
     }
@@ -445,21 +452,28 @@ __global__ void __launch_bounds__(256) k_panel_segments(int m, const int32_t *__
     }
 }
 
-// Adds the pieces of every long row in piece order and writes the row.
+// Adds the pieces of every long row in piece order and writes the row (to every destination).
+struct DstList {
+    void *dst[MXG_MAX_DST];
+    int n;
+};
+
 template <typename T, bool COLMAJOR>
 __global__ void __launch_bounds__(128) k_spmm_fixup(int n, const int32_t *__restrict__ long_rows,
                                                     const int32_t *__restrict__ long_first,
                                                     const int32_t *__restrict__ long_np,
-                                                    const T *__restrict__ partial, T *__restrict__ Out, size_t ldc)
+                                                    const T *__restrict__ partial, const DstList out, size_t ldc,
+                                                    const int *__restrict__ abort)
 {
+    if (abort != nullptr && *abort != 0) return;
     const int row = long_rows[blockIdx.x];
     const int first = long_first[blockIdx.x];
     const int np = long_np[blockIdx.x];
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
         T s = T(0);
         for (int k = 0; k < np; k++) s += partial[(size_t)(first + k) * n + c];
-        if (COLMAJOR) Out[(size_t)row + (size_t)c * ldc] = s;
-        else Out[(size_t)row * ldc + c] = s;
+        const size_t at = COLMAJOR ? (size_t)row + (size_t)c * ldc : (size_t)row * ldc + c;
+        for (int d = 0; d < out.n; d++) static_cast<T *>(out.dst[d])[at] = s;
     }
 }
 
@@ -558,22 +572,29 @@ static int plan_panels(mxg_csr_s *A, size_t b_bytes, cudaStream_t stream, SpmmAr
 
 template <typename T>
 static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, const T *d_B, size_t ldb,
-                      T *d_Out, size_t ldc, cudaStream_t stream)
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     const bool colmajor = out_layout == MXG_COLS_CONTIGUOUS;
     const size_t out_rows = (size_t)A->m;
+    T *d_Out = static_cast<T *>(d_outs[0]);
 
     if (A->nnz == 0) {
         // the reference returns its zero-filled matrix untouched (src/matmul.cpp:128-129, 160-161)
-        if (colmajor) MXG_LAUNCH(k_fill_zero_2d<T>, 148 * 4, 256, 0, stream, d_Out, (size_t)n, out_rows, ldc);
-        else MXG_LAUNCH(k_fill_zero_2d<T>, 148 * 4, 256, 0, stream, d_Out, out_rows, (size_t)n, ldc);
+        for (int d = 0; d < n_dst; d++) {
+            T *o = static_cast<T *>(d_outs[d]);
+            if (colmajor) MXG_LAUNCH(k_fill_zero_2d<T>, 148 * 4, 256, 0, stream, o, (size_t)n, out_rows, ldc);
+            else MXG_LAUNCH(k_fill_zero_2d<T>, 148 * 4, 256, 0, stream, o, out_rows, (size_t)n, ldc);
+        }
         return MXG_OK;
     }
 
-    // 128-bit path needs whole vectors and 16-byte aligned rows of B (and of Out when row-major)
+    // 128-bit path needs whole vectors and 16-byte aligned rows of B (and of every Out when row-major)
     bool vec = (n % VEC == 0) && (ldb % VEC == 0) && (((uintptr_t)d_B & 15) == 0);
-    if (!colmajor) vec = vec && (ldc % VEC == 0) && (((uintptr_t)d_Out & 15) == 0);
+    if (!colmajor) {
+        vec = vec && (ldc % VEC == 0);
+        for (int d = 0; d < n_dst; d++) vec = vec && (((uintptr_t)d_outs[d] & 15) == 0);
+    }
     const int V = vec ? VEC : 1;
     const int nvec = n / V;
 
@@ -597,6 +618,8 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.ldb = ldb;
     args.Out = d_Out;
     args.ldc = ldc;
+    args.n_extra = n_dst - 1;
+    for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.piece = A->piece;
     args.n_pieces = A->n_pieces;
     args.piece_row = A->d_piece_row;
@@ -607,7 +630,7 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.panel = 0;
     args.n_panels = 1;
     args.panel_width = A->K > 0 ? A->K : 1;
-    MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
+    if (n_dst == 1) MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
     if (A->n_pieces > 0) {
         MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * (size_t)n * sizeof(T)));
         args.partial = A->d_partial;
@@ -624,12 +647,15 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     MXG_TRY(rc);
 
     if (A->n_long > 0) {
+        DstList out;
+        out.n = n_dst;
+        for (int d = 0; d < MXG_MAX_DST; d++) out.dst[d] = d < n_dst ? d_outs[d] : nullptr;
         if (colmajor)
             MXG_LAUNCH((k_spmm_fixup<T, true>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), d_Out, ldc);
+                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort);
         else
             MXG_LAUNCH((k_spmm_fixup<T, false>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), d_Out, ldc);
+                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort);
     }
     return MXG_OK;
 }
@@ -637,6 +663,14 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
 int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
                 void *d_Out, size_t ldc, cudaStream_t stream)
 {
+    void *outs[1] = {d_Out};
+    return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, 1, outs, ldc, stream);
+}
+
+int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream)
+{
+    if (n_dst < 1 || n_dst > MXG_MAX_DST || !d_outs) return fail(MXG_ERR_ARG, "spmm: 1 .. %d destinations", MXG_MAX_DST);
     if (n < 0) return fail(MXG_ERR_ARG, "spmm: negative n");
     if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS)
         return fail(MXG_ERR_ARG, "spmm: bad out_layout %d", out_layout);
@@ -646,13 +680,11 @@ int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void
     if (out_layout == MXG_COLS_CONTIGUOUS && ldc < (size_t)A->m) return fail(MXG_ERR_ARG, "spmm: ldc < m");
     if (dtype == MXG_F64) {
         if (!A->d_x64 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "spmm: handle holds no float64 values");
-        return spmm_typed<double>(A, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb,
-                                  static_cast<double *>(d_Out), ldc, stream);
+        return spmm_typed<double>(A, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb, n_dst, d_outs, ldc, stream);
     }
     if (dtype == MXG_F32) {
         if (!A->d_x32 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "spmm: handle holds no float32 values");
-        return spmm_typed<float>(A, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb,
-                                 static_cast<float *>(d_Out), ldc, stream);
+        return spmm_typed<float>(A, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb, n_dst, d_outs, ldc, stream);
     }
     return fail(MXG_ERR_ARG, "spmm: bad dtype %d", dtype);
 }

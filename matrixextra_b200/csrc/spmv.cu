@@ -109,13 +109,21 @@ __device__ __forceinline__ bool team_any(bool f)
     return v != 0;
 }
 
+// result copies beyond the local one (peer-mapped vectors of the other GPUs of the box)
+struct SpmvExtra {
+    void *dst[MXG_MAX_DST - 1];
+    int n;
+};
+
 template <int YTYPE>
-__device__ __forceinline__ void store_result(typename YTraits<YTYPE>::out *out, int row, double v, bool na)
+__device__ __forceinline__ void store_result(typename YTraits<YTYPE>::out *out, const SpmvExtra &extra, int row, double v, bool na)
 {
     // a row that met an NA keeps R's NA payload: x86 propagates NA_real_ through the reference's sum as
     // the quieted NaN 0x7FF80000000007A2 (low word still 1954, so R's is.na() holds)
     if (na && v != v) v = __longlong_as_double(0x7FF80000000007A2LL);
-    out[row] = (typename YTraits<YTYPE>::out)v;
+    typedef typename YTraits<YTYPE>::out OE;
+    out[row] = (OE)v;
+    for (int d = 0; d < extra.n; d++) static_cast<OE *>(extra.dst[d])[row] = (OE)v;
 }
 
 struct SpmvArgs {
@@ -134,6 +142,7 @@ struct SpmvArgs {
     int *partial_na;   // [n_pieces]
     int rows_per_team; // rows each team walks inside its CTA
     const int *abort;  // optional device flag: non-zero => the column ids failed validation, do nothing
+    SpmvExtra extra;
 };
 
 template <int YTYPE, typename XT, int LPR>
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(256) k_spmv(const SpmvArgs g)
         double acc = team_dot<YTYPE, XT, LPR>(a, b, maxlen, l, j, x, y, na);
         acc = team_reduce<LPR>(acc);
         na = team_any<LPR>(na);
-        if (store && l == 0) store_result<YTYPE>(out, row, acc, na);
+        if (store && l == 0) store_result<YTYPE>(out, g.extra, row, acc, na);
     }
 }
 
@@ -202,8 +211,10 @@ __global__ void __launch_bounds__(128) k_spmv_fixup(int n_long, const int32_t *_
                                                     const int32_t *__restrict__ long_np,
                                                     const double *__restrict__ partial,
                                                     const int *__restrict__ partial_na,
-                                                    typename YTraits<YTYPE>::out *__restrict__ out)
+                                                    typename YTraits<YTYPE>::out *__restrict__ out, const SpmvExtra extra,
+                                                    const int *__restrict__ abort)
 {
+    if (abort != nullptr && *abort != 0) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_long) return;
     const int first = long_first[i], np = long_np[i];
@@ -213,13 +224,16 @@ __global__ void __launch_bounds__(128) k_spmv_fixup(int n_long, const int32_t *_
         s += partial[first + k];
         na = na || (partial_na[first + k] != 0);
     }
-    store_result<YTYPE>(out, long_rows[i], s, na);
+    store_result<YTYPE>(out, extra, long_rows[i], s, na);
 }
 
 template <int YTYPE, typename XT>
-static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, void *d_out, cudaStream_t stream)
+static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream)
 {
+    void *d_out = d_outs[0];
     SpmvArgs args;
+    args.extra.n = n_dst - 1;
+    for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra.dst[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.m = A->m;
     args.p = A->d_p;
     args.j = A->d_j;
@@ -266,28 +280,35 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, voi
     if (A->n_long > 0) {
         MXG_LAUNCH((k_spmv_fixup<YTYPE>), ceil_div_i(A->n_long, 128), 128, 0, stream, A->n_long, A->d_long_rows,
                    A->d_long_first, A->d_long_np, args.partial, args.partial_na,
-                   static_cast<typename YTraits<YTYPE>::out *>(d_out));
+                   static_cast<typename YTraits<YTYPE>::out *>(d_out), args.extra, A->d_abort);
     }
     return MXG_OK;
 }
 
 template <int YTYPE>
-static int spmv_values(const mxg_csr_s *A, const void *d_y, void *d_out, cudaStream_t stream)
+static int spmv_values(const mxg_csr_s *A, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream)
 {
-    if (A->d_x64) return spmv_dispatch<YTYPE, double>(A, A->d_x64, d_y, d_out, stream);
-    if (A->d_x32 && YTYPE == MXG_Y_FLOAT32) return spmv_dispatch<YTYPE, float>(A, A->d_x32, d_y, d_out, stream);
-    if (A->nnz == 0) return spmv_dispatch<YTYPE, double>(A, nullptr, d_y, d_out, stream);
+    if (A->d_x64) return spmv_dispatch<YTYPE, double>(A, A->d_x64, d_y, n_dst, d_outs, stream);
+    if (A->d_x32 && YTYPE == MXG_Y_FLOAT32) return spmv_dispatch<YTYPE, float>(A, A->d_x32, d_y, n_dst, d_outs, stream);
+    if (A->nnz == 0) return spmv_dispatch<YTYPE, double>(A, nullptr, d_y, n_dst, d_outs, stream);
     return fail(MXG_ERR_UNSUPPORTED, "spmv: handle holds no float64 values");
 }
 
 int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream)
 {
+    void *outs[1] = {d_out};
+    return launch_spmv_multi(A, ytype, d_y, 1, outs, stream);
+}
+
+int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream)
+{
+    if (n_dst < 1 || n_dst > MXG_MAX_DST || !d_outs) return fail(MXG_ERR_ARG, "spmv: 1 .. %d destinations", MXG_MAX_DST);
     if (A->m == 0) return MXG_OK;
     switch (ytype) {
-    case MXG_Y_NUMERIC: return spmv_values<MXG_Y_NUMERIC>(A, d_y, d_out, stream);
-    case MXG_Y_INTEGER: return spmv_values<MXG_Y_INTEGER>(A, d_y, d_out, stream);
-    case MXG_Y_LOGICAL: return spmv_values<MXG_Y_LOGICAL>(A, d_y, d_out, stream);
-    case MXG_Y_FLOAT32: return spmv_values<MXG_Y_FLOAT32>(A, d_y, d_out, stream);
+    case MXG_Y_NUMERIC: return spmv_values<MXG_Y_NUMERIC>(A, d_y, n_dst, d_outs, stream);
+    case MXG_Y_INTEGER: return spmv_values<MXG_Y_INTEGER>(A, d_y, n_dst, d_outs, stream);
+    case MXG_Y_LOGICAL: return spmv_values<MXG_Y_LOGICAL>(A, d_y, n_dst, d_outs, stream);
+    case MXG_Y_FLOAT32: return spmv_values<MXG_Y_FLOAT32>(A, d_y, n_dst, d_outs, stream);
     default: return fail(MXG_ERR_ARG, "spmv: bad ytype %d", ytype);
     }
 }

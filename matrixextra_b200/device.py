@@ -96,6 +96,21 @@ class DeviceCSR:
         _lib.call("mxg_dev_spmm", self._h, int(dtype), int(out_layout), int(b_layout), int(n), _dptr(B_t), int(ldb),
                   _dptr(out_t), int(ldc), _stream_ptr(stream))
 
+    def spmm_bcast(self, B_t, dst_ptrs, n, dtype, out_layout=MXG_ROWS_CONTIGUOUS, ldb=None, ldc=None, stream=None):
+        """The same product with every finished row stored into ALL ``dst_ptrs`` (raw device addresses: the local
+        result first, then the peer-mapped results of the other GPUs) — compute and all-gather in one kernel."""
+        if ldb is None:
+            ldb = n
+        if ldc is None:
+            ldc = n if out_layout == MXG_ROWS_CONTIGUOUS else self.m
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+        _lib.call("mxg_dev_spmm_bcast", self._h, int(dtype), int(out_layout), MXG_ROWS_CONTIGUOUS, int(n), _dptr(B_t),
+                  int(ldb), len(dst_ptrs), arr, int(ldc), _stream_ptr(stream))
+
+    def spmv_bcast(self, y_t, dst_ptrs, ytype=MXG_Y_NUMERIC, stream=None):
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+        _lib.call("mxg_dev_spmv_bcast", self._h, int(ytype), _dptr(y_t), len(dst_ptrs), arr, _stream_ptr(stream))
+
     def spmv(self, y_t, out_t, ytype=MXG_Y_NUMERIC, stream=None):
         _lib.call("mxg_dev_spmv", self._h, int(ytype), _dptr(y_t), _dptr(out_t), _stream_ptr(stream))
 

@@ -78,6 +78,100 @@ def sharded_spmm(p, j, x, B_rows, compute: Callable, dist, rank: int, world: int
     return allgather_row_blocks(local, bounds, local.shape[1], dist, rank, world)
 
 
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier so torch can view library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerResult:
+    """The full result of a row-sharded product, present on every GPU of the box, filled by all ranks at once.
+
+    Every rank allocates one buffer (``mxg_dev_alloc``: plain cudaMalloc, exportable), publishes its cudaIpc
+    handle through the process group (host-side plumbing only) and maps the other ranks' buffers.  A rank's
+    product kernel then stores each finished output row into all ``world`` buffers (local store + NVLink peer
+    stores, ``DeviceCSR.spmm_bcast``), and ``barrier()`` — a tiny device-side flag exchange on the same stream —
+    tells every rank when all blocks have landed.  No separate all-gather pass exists.
+
+    Buffer layout: 256 bytes of flags (``world`` ints used), then the payload."""
+
+    HEADER = 256
+
+    def __init__(self, payload_bytes: int, dist, rank: int, world: int):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        self._lib, self._C, self.rank, self.world = _lib, C, rank, world
+        self.payload_bytes = int(payload_bytes)
+        base = C.c_void_p()
+        _lib.call("mxg_dev_alloc", self.HEADER + self.payload_bytes, C.byref(base))
+        self.base = int(base.value)
+        self.ptrs: List[int] = [0] * world
+        self.ptrs[rank] = self.base
+        self._opened: List[int] = []
+        torch.as_tensor(_RawCuda(self.base, (self.HEADER // 4,), "<i4"), device="cuda").zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            handle = (C.c_ubyte * 64)()
+            _lib.call("mxg_ipc_export", C.c_void_p(self.base), handle)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle))
+            for g in range(world):
+                if g == rank:
+                    continue
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[g])
+                q = C.c_void_p()
+                _lib.call("mxg_ipc_open", buf, C.byref(q))
+                self.ptrs[g] = int(q.value)
+                self._opened.append(int(q.value))
+            dist.barrier()
+        self.epoch = 0
+
+    def payload_ptr(self, g: int) -> int:
+        return self.ptrs[g] + self.HEADER
+
+    def dst_ptrs(self, byte_offset: int) -> List[int]:
+        """Where this rank's block starts inside every rank's result, local buffer first."""
+        order = [self.rank] + [g for g in range(self.world) if g != self.rank]
+        return [self.payload_ptr(g) + int(byte_offset) for g in order]
+
+    def tensor(self, shape, dtype):
+        """torch view of the local payload."""
+        import torch
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4"}[dtype]
+        return torch.as_tensor(_RawCuda(self.payload_ptr(self.rank), shape, typestr), device="cuda")
+
+    def barrier(self, stream=None):
+        """Stream-ordered: returns immediately; work queued behind it sees every rank's rows."""
+        from .device import _stream_ptr
+        C = self._C
+        self.epoch += 1
+        arr = (C.c_void_p * self.world)(*self.ptrs)
+        self._lib.call("mxg_dev_peer_barrier", self.rank, self.world, arr, self.epoch, _stream_ptr(stream))
+
+    def failed(self) -> bool:
+        f = self._C.c_int(0)
+        self._lib.call("mxg_dev_barrier_failed", self._C.byref(f))
+        return bool(f.value)
+
+    def close(self, dist=None):
+        import torch
+        torch.cuda.synchronize()
+        if dist is not None and self.world > 1:
+            dist.barrier()
+        for q in self._opened:
+            self._lib.call("mxg_ipc_close", self._C.c_void_p(q))
+        self._opened = []
+        if dist is not None and self.world > 1:
+            dist.barrier()
+        if self.base:
+            self._lib.call("mxg_dev_free", self._C.c_void_p(self.base))
+            self.base = 0
+
+
 def cuda_compute(dtype, stream=None) -> Callable:
     """The production compute callable: upload the shard once, multiply on the current device."""
     import torch

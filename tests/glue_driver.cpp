@@ -1,0 +1,113 @@
+/* tests/glue_driver.cpp — TEST INFRASTRUCTURE: runs rglue/matmul_gpu_glue.cpp (the Rcpp glue a maintainer adds
+ * to MatrixExtra) without R.  The glue is compiled unmodified against the Rcpp stand-in oracle/shim/Rcpp.h
+ * (-DMXGPU_GLUE_SHIM) and linked with libmxgpu.so; the extern "C" functions below hand it caller buffers the
+ * way R hands it SEXPs (borrowed, column-major, float32 as int bits) and copy the returned object out.
+ * Return value: 0, or 1 with the R error message in gluedrv_last_error(). */
+#include "../rglue/matmul_gpu_glue.cpp"
+
+#include <cstring>
+#include <string>
+
+namespace {
+std::string g_err;
+typedef Rcpp::IntegerVector IV;
+typedef Rcpp::NumericVector NV;
+typedef Rcpp::LogicalVector LV;
+typedef Rcpp::NumericMatrix NM;
+typedef Rcpp::IntegerMatrix IM;
+
+template <class Obj, class T>
+void copy_out(const Obj &o, T *out)
+{
+    if (o.size() > 0) std::memcpy(out, o.data_ptr(), sizeof(T) * (size_t)o.size());
+}
+
+template <class Fn>
+int guarded(Fn fn)
+{
+    try {
+        fn();
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+} // namespace
+
+extern "C" {
+
+const char *gluedrv_last_error(void) { return g_err.c_str(); }
+
+/* dense(a x K) . t(sparse rows) : which = 0 matmul_dense_csc, 1 tcrossprod_dense_csr ; f32 = float bits in int */
+int gluedrv_dense_sparse(int which, int f32, const void *X, int a, int K, const int *p, int rows, const int *idx,
+                         const double *x, int nnz, void *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)rows + 1), J((int *)idx, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        if (f32) {
+            IM Xm((int *)X, a, K);
+            IM r = which == 0 ? matmul_dense_csc_float32(Xm, P, J, V, 1) : tcrossprod_dense_csr_float32(Xm, P, J, V, 1, K);
+            copy_out(r, (int *)out);
+        } else {
+            NM Xm((double *)X, a, K);
+            NM r = which == 0 ? matmul_dense_csc_numeric(Xm, P, J, V, 1) : tcrossprod_dense_csr_numeric(Xm, P, J, V, 1, K);
+            copy_out(r, (double *)out);
+        }
+    });
+}
+
+/* tcrossprod(CSR(m x K), dense(n x K)) */
+int gluedrv_sparse_tdense(int f32, const int *p, int m, const int *j, const double *x, int nnz, const void *Y, int n,
+                          int K, void *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        if (f32) copy_out(tcrossprod_csr_dense_float32(P, J, V, IM((int *)Y, n, K), 1), (int *)out);
+        else copy_out(tcrossprod_csr_dense_numeric(P, J, V, NM((double *)Y, n, K), 1), (double *)out);
+    });
+}
+
+/* CSR %*% dense vector; ytype as in mxgpu.h (0 numeric, 1 integer, 2 logical, 3 float32) */
+int gluedrv_csr_dvec(int ytype, const int *p, int m, const int *j, const double *x, int nnz, const void *y, int K,
+                     void *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        switch (ytype) {
+        case 0: copy_out(matmul_csr_dvec_numeric(P, J, V, NV((double *)y, (size_t)K), 1), (double *)out); break;
+        case 1: copy_out(matmul_csr_dvec_integer(P, J, V, IV((int *)y, (size_t)K), 1), (double *)out); break;
+        case 2: copy_out(matmul_csr_dvec_logical(P, J, V, LV((int *)y, (size_t)K), 1), (double *)out); break;
+        default: copy_out(matmul_csr_dvec_float32(P, J, V, IV((int *)y, (size_t)K), 1), (int *)out); break;
+        }
+    });
+}
+
+/* crossprod(CSR(m x K), dense(m x n)) -> K x n */
+int gluedrv_crossprod(int f32, const int *p, int m, const int *j, const double *x, int nnz, int K, const void *Y,
+                      int yrows, int n, void *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        if (f32) copy_out(crossprod_csr_dense_float32(P, J, V, K, IM((int *)Y, yrows, n), 1), (int *)out);
+        else copy_out(crossprod_csr_dense_numeric(P, J, V, K, NM((double *)Y, yrows, n), 1), (double *)out);
+    });
+}
+
+int gluedrv_csr_to_csc(const int *p, int m, const int *j, const double *x, int nnz, int K, int *p2, int *i2, double *x2)
+{
+    return guarded([&] {
+        Rcpp::List r = csr_to_csc_gpu(IV((int *)p, (size_t)m + 1), IV((int *)j, (size_t)nnz), NV((double *)x, (size_t)nnz), K);
+        std::memcpy(p2, r.entries[0].data, sizeof(int) * r.entries[0].size);
+        if (nnz > 0) {
+            std::memcpy(i2, r.entries[1].data, sizeof(int) * r.entries[1].size);
+            std::memcpy(x2, r.entries[2].data, sizeof(double) * r.entries[2].size);
+        }
+    });
+}
+
+} /* extern "C" */

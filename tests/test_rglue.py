@@ -1,0 +1,138 @@
+"""The Rcpp glue (rglue/matmul_gpu_glue.cpp) without R: compiled unmodified against the Rcpp stand-in of the
+test infrastructure (oracle/shim/Rcpp.h) together with tests/glue_driver.cpp, linked with libmxgpu.so, and
+driven through ctypes with the argument layouts R would pass (column-major, float32 as int bits).
+
+CPU: the glue builds, exports what the driver needs, and turns a failed C-ABI call into an R-style error.
+GPU: every exported entry point of the glue against the CPU oracle.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import FP32_TOL, FP64_TOL, NA_INT, powerlaw_csr, rel_err, rsparsematrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+LIB = os.path.join(BUILD, "libgluedrv.so")
+
+
+def _build():
+    from matrixextra_b200 import build_native
+    build_native.build()
+    srcs = [os.path.join(ROOT, "tests", "glue_driver.cpp"), os.path.join(ROOT, "rglue", "matmul_gpu_glue.cpp"),
+            os.path.join(ROOT, "include", "mxgpu.h"), os.path.join(ROOT, "oracle", "shim", "Rcpp.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DMXGPU_GLUE_SHIM",
+           "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), "-o", LIB, srcs[0],
+           "-L" + os.path.join(ROOT, "matrixextra_b200", "csrc"), "-lmxgpu",
+           "-Wl,-rpath," + os.path.join(ROOT, "matrixextra_b200", "csrc")]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(cmd, check=True, env=env)
+    return LIB
+
+
+@pytest.fixture(scope="module")
+def drv():
+    lib = C.CDLL(_build())
+    lib.gluedrv_last_error.restype = C.c_char_p
+    return lib
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def test_glue_builds_and_reports_errors_like_r(drv):
+    for name in ("gluedrv_dense_sparse", "gluedrv_sparse_tdense", "gluedrv_csr_dvec", "gluedrv_crossprod",
+                 "gluedrv_csr_to_csc"):
+        assert hasattr(drv, name)
+    # the ten export names of src/matmul.cpp:221-483 are all defined by the glue, with Rcpp::export tags
+    text = open(os.path.join(ROOT, "rglue", "matmul_gpu_glue.cpp")).read()
+    for name in ("matmul_dense_csc_numeric", "matmul_dense_csc_float32", "tcrossprod_dense_csr_numeric",
+                 "tcrossprod_dense_csr_float32", "tcrossprod_csr_dense_numeric", "tcrossprod_csr_dense_float32",
+                 "matmul_csr_dvec_numeric", "matmul_csr_dvec_integer", "matmul_csr_dvec_logical",
+                 "matmul_csr_dvec_float32"):
+        assert text.count(name + "(") >= 1
+    assert text.count("// [[Rcpp::export(rng = false)]]") >= 10
+    # an invalid matrix (decreasing indptr) or a missing device surfaces as an R error with the library's message
+    p = _i32([0, 2, 1])
+    j = _i32([0, 0])
+    x = np.array([1.0, 2.0])
+    y = np.array([3.0])
+    out = np.zeros(2)
+    rc = drv.gluedrv_csr_dvec(0, _p(p), 2, _p(j), _p(x), 2, _p(y), 1, _p(out))
+    assert rc == 1
+    msg = drv.gluedrv_last_error().decode()
+    assert ("indptr" in msg) or ("cuda" in msg.lower()), msg
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f32", [0, 1])
+def test_glue_products_match_oracle(drv, port, f32):
+    dt = np.float32 if f32 else np.float64
+    tol = FP32_TOL if f32 else FP64_TOL
+    sfx = "float32" if f32 else "numeric"
+    rng = np.random.default_rng(41)
+    a, K, b = 37, 120, 90
+    S = rsparsematrix(b, K, 0.2, 41)  # rows of S: CSR of S == CSC of t(S)
+    p, j, x = _i32(S.indptr), _i32(S.indices), S.data
+    X = np.asfortranarray(rng.standard_normal((a, K)).astype(dt))
+    for which, name in ((0, "matmul_dense_csc_"), (1, "tcrossprod_dense_csr_")):
+        out = np.empty((a, b), dtype=dt, order="F")
+        assert drv.gluedrv_dense_sparse(which, f32, _p(X), a, K, _p(p), b, _p(j), _p(x), j.size, _p(out)) == 0
+        want = getattr(port, name + sfx)(X, p, j, x, 1) if which == 0 else getattr(port, name + sfx)(X, p, j, x, 1, K)
+        assert rel_err(out, want) <= tol
+    Y = np.asfortranarray(rng.standard_normal((24, K)).astype(dt))
+    out = np.empty((b, 24), dtype=dt, order="F")
+    assert drv.gluedrv_sparse_tdense(f32, _p(p), b, _p(j), _p(x), j.size, _p(Y), 24, K, _p(out)) == 0
+    assert rel_err(out, getattr(port, "tcrossprod_csr_dense_" + sfx)(p, j, x, Y, 1)) <= tol
+    # crossprod(CSR(b x K), dense(b x n)) -> K x n  (new method on the device transpose)
+    Z = np.asfortranarray(rng.standard_normal((b, 12)).astype(dt))
+    out = np.empty((K, 12), dtype=dt, order="F")
+    assert drv.gluedrv_crossprod(f32, _p(p), b, _p(j), _p(x), j.size, K, _p(Z), b, 12, _p(out)) == 0
+    p2, i2, x2 = port.csr2csc(b, K, p, j, x)
+    want = getattr(port, "matmul_dense_csc_" + sfx)(np.asfortranarray(Z.T), p2, i2, x2).T
+    assert rel_err(out, want) <= tol
+    # dimension mismatch -> the reference's message
+    assert drv.gluedrv_crossprod(f32, _p(p), b, _p(j), _p(x), j.size, K, _p(Z), b - 1, 12, _p(out)) == 1
+    assert drv.gluedrv_last_error().decode() == "Matrix dimensions do not match."
+
+
+@pytest.mark.gpu
+def test_glue_vectors_and_transpose(drv, port):
+    p, j, x = powerlaw_csr(900, 300, 15, seed=42, cap=280)
+    rng = np.random.default_rng(42)
+    y = rng.standard_normal(300)
+    out = np.empty(900)
+    assert drv.gluedrv_csr_dvec(0, _p(p), 900, _p(j), _p(x), j.size, _p(y), 300, _p(out)) == 0
+    assert rel_err(out, port.matmul_csr_dvec_numeric(p, j, x, y, 1)) <= FP64_TOL
+    yi = rng.integers(-3, 4, 300).astype(np.int32)
+    yi[::11] = NA_INT
+    for ytype, fn in ((1, port.matmul_csr_dvec_integer), (2, port.matmul_csr_dvec_logical)):
+        assert drv.gluedrv_csr_dvec(ytype, _p(p), 900, _p(j), _p(x), j.size, _p(yi), 300, _p(out)) == 0
+        want = fn(p, j, x, yi, 1)
+        assert np.array_equal(np.isnan(out), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert rel_err(out[ok], want[ok]) <= FP64_TOL
+    yf = rng.standard_normal(300).astype(np.float32)
+    outf = np.empty(900, dtype=np.float32)
+    assert drv.gluedrv_csr_dvec(3, _p(p), 900, _p(j), _p(x), j.size, _p(yf), 300, _p(outf)) == 0
+    assert rel_err(outf, port.matmul_csr_dvec_float32(p, j, x, yf, 1)) <= FP32_TOL
+    p2, i2, x2 = np.empty(301, np.int32), np.empty(j.size, np.int32), np.empty(j.size)
+    assert drv.gluedrv_csr_to_csc(_p(p), 900, _p(j), _p(x), j.size, 300, _p(p2), _p(i2), _p(x2)) == 0
+    q2, k2, y2 = port.csr2csc(900, 300, p, j, x)
+    assert np.array_equal(p2, q2) and np.array_equal(i2, k2) and np.array_equal(x2, y2)
+    # out-of-range column id: an R error, not a fault
+    jb = j.copy()
+    jb[7] = 300
+    assert drv.gluedrv_csr_dvec(0, _p(p), 900, _p(jb), _p(x), j.size, _p(y), 300, _p(out)) == 1
+    assert "column index" in drv.gluedrv_last_error().decode()
