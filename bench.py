@@ -212,6 +212,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     _lib.call("mxg_set_device", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = dict(WORKLOADS[args.workload])
