@@ -71,7 +71,7 @@ int mxg_set_device(int device);
 
 /* Tuning knobs, all optional ("auto" when never set). Names: "piece" (nnz per long-row piece),
  * "spmm_lpr" (lanes per row of B), "spmm_rpw" (rows per warp), "spmm_panel_mb" (column-panel size of the
- * dense operand in MiB, 0 = off), "spmm_panel_cols" (forced panel width in columns), "spmv_lpr", "h2d_chunk_mb", "pipeline" (level-1 calls: 1 = streamed row chunks, 0 = whole-matrix
+ * dense operand in MiB, 0 = off), "spmm_panel_cols" (forced panel width in columns), "spmv_lpr", "spmv_tex" (numeric SpMV gathers y through the texture path, default 1), "h2d_chunk_mb", "pipeline" (level-1 calls: 1 = streamed row chunks, 0 = whole-matrix
  * upload first), "pipe_chunk_nnz" (stored entries per streamed chunk, 0 = auto).  Unknown names return MXG_ERR_ARG. */
 int mxg_set_option(const char *name, long value);
 int mxg_get_option(const char *name, long *value);

@@ -283,6 +283,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
+    if (!strcmp(name, "spmv_tex")) return &o.spmv_tex;
     if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;
     if (!strcmp(name, "pipeline")) return &o.pipeline;
     if (!strcmp(name, "pipe_chunk_nnz")) return &o.pipe_chunk_nnz;

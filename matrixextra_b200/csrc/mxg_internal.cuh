@@ -51,6 +51,7 @@ struct Options {
     long spmm_panel_cols = 0; // force a panel width in columns of A (tests / sweeps); 0 = by size
     long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
     long spmv_lpr = 0;        // 0 = auto
+    long spmv_tex = 1;        // gather a numeric y through the texture path (7 % faster than LDG on cfg2); 0 = plain loads
     long h2d_chunk_mb = 64;   // staging chunk of the value narrowing in mxg_csr_upload
     long pipe_chunk_nnz = 0;  // stored entries (and rows) per chunk of the streamed path; 0 = auto (nnz/16, >= 1 Mi)
     long pipeline = 1;        // level-1 products: 1 = streamed row chunks (pipeline.cu), 0 = upload-all-then-compute

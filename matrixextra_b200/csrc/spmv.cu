@@ -60,7 +60,8 @@ struct YTraits<MXG_Y_FLOAT32> {
 template <int YTYPE, typename XT, int LPR>
 __device__ __forceinline__ double team_dot(const int a, const int b, const int maxlen, const int l,
                                            const int32_t *__restrict__ j, const XT *__restrict__ x,
-                                           const typename YTraits<YTYPE>::elem *__restrict__ y, bool &na)
+                                           const typename YTraits<YTYPE>::elem *__restrict__ y, bool &na,
+                                           const cudaTextureObject_t tex = 0)
 {
     constexpr int U = 4;
     double acc = 0.0;
@@ -83,7 +84,14 @@ __device__ __forceinline__ double team_dot(const int a, const int b, const int m
 #pragma unroll
         for (int u = 0; u < U; u++) {
             yy[u] = 0.0;
-            if (ok[u]) yy[u] = YTraits<YTYPE>::value(__ldg(y + jj[u]), na);
+            if (ok[u]) {
+                if (YTYPE == MXG_Y_NUMERIC && tex != 0) {
+                    const int2 t = tex1Dfetch<int2>(tex, jj[u]);
+                    yy[u] = __hiloint2double(t.y, t.x);
+                } else {
+                    yy[u] = YTraits<YTYPE>::value(__ldg(y + jj[u]), na);
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
@@ -140,6 +148,7 @@ struct SpmvArgs {
     const int32_t *piece_k;
     double *partial;   // [n_pieces]
     int *partial_na;   // [n_pieces]
+    cudaTextureObject_t tex; // numeric y: gather through the texture path (fewer L1 wavefronts per warp gather); 0 = plain loads
     int rows_per_team; // rows each team walks inside its CTA
     const int *abort;  // optional device flag: non-zero => the column ids failed validation, do nothing
     SpmvExtra extra;
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(256) k_spmv(const SpmvArgs g)
         const int a = p[row] + g.piece_k[pc] * g.piece;
         const int b = min(a + g.piece, p[row + 1]);
         bool na = false;
-        double acc = team_dot<YTYPE, XT, 32>(a, b, b - a, lane, j, x, y, na);
+        double acc = team_dot<YTYPE, XT, 32>(a, b, b - a, lane, j, x, y, na, g.tex);
         acc = team_reduce<32>(acc);
         na = team_any<32>(na);
         if (lane == 0) {
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(256) k_spmv(const SpmvArgs g)
         }
         const int maxlen = __reduce_max_sync(0xffffffffu, b - a);
         bool na = false;
-        double acc = team_dot<YTYPE, XT, LPR>(a, b, maxlen, l, j, x, y, na);
+        double acc = team_dot<YTYPE, XT, LPR>(a, b, maxlen, l, j, x, y, na, g.tex);
         acc = team_reduce<LPR>(acc);
         na = team_any<LPR>(na);
         if (store && l == 0) store_result<YTYPE>(out, g.extra, row, acc, na);
@@ -266,6 +275,19 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int
         else lpr = 32;
     }
     args.rows_per_team = 4;
+    args.tex = 0;
+    cudaTextureObject_t tex = 0;
+    if (YTYPE == MXG_Y_NUMERIC && options().spmv_tex != 0 && A->K > 0 && A->K <= (1 << 27) && (((uintptr_t)d_y & 255) == 0)) {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = const_cast<void *>(d_y);
+        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindSigned);
+        rd.res.linear.sizeInBytes = (size_t)A->K * 8;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        MXG_CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        args.tex = tex;
+    }
 #define MXG_SPMV(L)                                                                              \
     if (lpr == L) {                                                                              \
         const int block_rows = (256 / L) * args.rows_per_team;                                   \
@@ -277,6 +299,7 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int
         return fail(MXG_ERR_ARG, "spmv: unsupported team size %d", lpr);
     }
 #undef MXG_SPMV
+    if (tex) cudaDestroyTextureObject(tex); // the launch holds its own copy of the descriptor handle
     if (A->n_long > 0) {
         MXG_LAUNCH((k_spmv_fixup<YTYPE>), ceil_div_i(A->n_long, 128), 128, 0, stream, A->n_long, A->d_long_rows,
                    A->d_long_first, A->d_long_np, args.partial, args.partial_na,

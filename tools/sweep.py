@@ -95,11 +95,14 @@ def main():
             A = DeviceCSR.synth(w2["m"], w2["K"], w2["nnz"], 1, 0, seed=1002, keep=MXG_KEEP_F64)
             y = torch.randn(A.K, device="cuda", dtype=torch.float64, generator=g)
             o = torch.empty(A.m, device="cuda", dtype=torch.float64)
-            for lpr in (4, 8, 16, 32):
-                _lib.set_option("spmv_lpr", lpr)
-                ms = _time_ms(lambda: A.spmv(y, o), args.steps, 3)
-                emit(case="cfg2_spmv", piece=piece, lpr=lpr, ms=ms, gflops=2.0 * A.nnz / ms / 1e6,
-                     eff_gbps=w_alg_bytes(A.m, A.K, A.nnz, 1, 8) / ms / 1e6)
+            for tex in (0, 1):
+                _lib.set_option("spmv_tex", tex)
+                for lpr in (8, 16, 32):
+                    _lib.set_option("spmv_lpr", lpr)
+                    ms = _time_ms(lambda: A.spmv(y, o), args.steps, 3)
+                    emit(case="cfg2_spmv", piece=piece, lpr=lpr, tex=tex, ms=ms, gflops=2.0 * A.nnz / ms / 1e6,
+                         eff_gbps=w_alg_bytes(A.m, A.K, A.nnz, 1, 8) / ms / 1e6)
+            _lib.set_option("spmv_tex", 0)
             _lib.set_option("spmv_lpr", 0)
             A.free()
         _lib.set_option("piece", 1024)
