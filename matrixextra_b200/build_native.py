@@ -39,7 +39,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("MXG_NVCC_EXTRA", "").split()  # development: e.g. -DSPMM_MINB=12
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper without OpenMP specs; nvcc's host compiler is the system g++
     env.pop("CC", None)

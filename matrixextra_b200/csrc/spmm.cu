@@ -123,6 +123,9 @@ __device__ __forceinline__ double fma_t(double a, double b, double c) { return f
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int SPMM_THREADS = 128;
 constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+#ifndef SPMM_MINB
+#define SPMM_MINB 8 // resident CTAs per SM the register allocation must allow (8 => 64 registers)
+#endif
 constexpr int SPMM_CM_RPW = 8; // rows per warp of a column-major CTA tile (tile = 32 rows)
 
 // Entries pos .. pos + cnt - 1 (cnt <= 32, one per lane in jj / xx) of the current row.
@@ -223,7 +226,7 @@ struct SpmmArgs {
 // panel are not touched).  Entries are consumed in stored order panel after panel, so for sorted rows the sum
 // order is unchanged; for unsorted rows the split points still partition the row (see k_panel_segments).
 template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS>
-__global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? 8 : 4) k_spmm(const SpmmArgs g)
+__global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? SPMM_MINB : 4) k_spmm(const SpmmArgs g)
 {
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
     constexpr int BR = SPMM_WARPS * SPMM_CM_RPW;

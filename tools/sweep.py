@@ -53,21 +53,18 @@ def main():
         A = DeviceCSR.synth(m, K, wl["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32 | MXG_KEEP_F64)
         emit(case="matrix", m=A.m, K=A.K, nnz=A.nnz, n_long=A.n_long, n_pieces=A.n_pieces, max_len=A.max_len)
         if "spmm32" in what:
-            for mb in (0, 32, 64, 128):
-                spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm", spmm_panel_mb=mb)
-            for rpw in (4, 16):
+            for rpw in (4, 8, 16):
                 spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm", spmm_rpw=rpw)
-            for mb in (0, 64):
-                spmm_case(A, MXG_F32, MXG_COLS_CONTIGUOUS, 64, "cfg3_f32_cm", spmm_panel_mb=mb)
+            spmm_case(A, MXG_F32, MXG_COLS_CONTIGUOUS, 64, "cfg3_f32_cm")
+            for mb in (64, 128):
+                spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm_panels", spmm_panel_mb=mb)
             for nn in (8, 16, 32, 128, 256):
                 spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, nn, "f32_rm_n")
         if "spmm64" in what:
-            for mb in (0, 64, 128):
-                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm", spmm_panel_mb=mb)
-            for mb in (0, 64):
-                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm_lpr16", spmm_panel_mb=mb, spmm_lpr=16)
-            for mb in (0, 64):
-                spmm_case(A, MXG_F64, MXG_COLS_CONTIGUOUS, 64, "k64_f64_cm", spmm_panel_mb=mb)
+            for rpw in (4, 8, 16):
+                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm", spmm_rpw=rpw)
+            spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm_lpr16", spmm_lpr=16)
+            spmm_case(A, MXG_F64, MXG_COLS_CONTIGUOUS, 64, "k64_f64_cm")
             for nn in (8, 16, 32, 128):
                 spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, nn, "f64_rm_n")
         A.free()
