@@ -35,6 +35,15 @@ int current_state(DeviceState **out)
     return MXG_OK;
 }
 
+// Level-2 entry points allocate from the device's default pool too: make sure it keeps freed blocks (otherwise
+// every stream synchronisation hands the memory back to the driver and the next multi-GB cudaMallocAsync
+// pays tens of milliseconds for fresh physical pages).
+static int ensure_device_ready()
+{
+    DeviceState *st;
+    return current_state(&st);
+}
+
 static int free_handle(mxg_csr_s *h)
 {
     if (!h) return MXG_OK;
@@ -336,6 +345,7 @@ int mxg_csr_upload(int m, int K, const int32_t *p, const int32_t *j, const doubl
 int mxg_csr_wrap_device(int m, int K, const int32_t *d_p, const int32_t *d_j, const double *d_x64,
                         const float *d_x32, int validate, void *stream, mxg_csr_t *handle)
 {
+    MXG_TRY(ensure_device_ready());
     if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
     *handle = nullptr;
     if (m < 0 || K < 0 || !d_p) return fail(MXG_ERR_ARG, "csr_wrap_device: bad arguments");
@@ -420,6 +430,7 @@ int mxg_csr_download(mxg_csr_t h, int32_t *p, int32_t *j, double *x)
 int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
                  void *d_Out, size_t ldc, void *stream)
 {
+    MXG_TRY(ensure_device_ready());
     if (!A) return fail(MXG_ERR_ARG, "dev_spmm: NULL handle");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (b_layout == MXG_ROWS_CONTIGUOUS) return launch_spmm(A, dtype, out_layout, n, d_B, ldb, d_Out, ldc, s);
@@ -440,6 +451,7 @@ int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, co
 int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
                        int n_dst, void *const *d_outs, size_t ldc, void *stream)
 {
+    MXG_TRY(ensure_device_ready());
     if (!A) return fail(MXG_ERR_ARG, "dev_spmm_bcast: NULL handle");
     if (b_layout != MXG_ROWS_CONTIGUOUS) return fail(MXG_ERR_UNSUPPORTED, "dev_spmm_bcast: the dense operand must be rows-contiguous");
     return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, static_cast<cudaStream_t>(stream));
@@ -447,6 +459,7 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
 
 int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream)
 {
+    MXG_TRY(ensure_device_ready());
     if (!A) return fail(MXG_ERR_ARG, "dev_spmv_bcast: NULL handle");
     return launch_spmv_multi(A, ytype, d_y, n_dst, d_outs, static_cast<cudaStream_t>(stream));
 }
@@ -504,12 +517,14 @@ int mxg_dev_barrier_failed(int *failed)
 
 int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream)
 {
+    MXG_TRY(ensure_device_ready());
     if (!A) return fail(MXG_ERR_ARG, "dev_spmv: NULL handle");
     return launch_spmv(A, ytype, d_y, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int mxg_dev_csr2csc(mxg_csr_t A, int keep, void *stream, mxg_csr_t *At)
 {
+    MXG_TRY(ensure_device_ready());
     if (!A || !At) return fail(MXG_ERR_ARG, "dev_csr2csc: NULL argument");
     *At = nullptr;
     mxg_csr_s *t = nullptr;
@@ -521,6 +536,7 @@ int mxg_dev_csr2csc(mxg_csr_t A, int keep, void *stream, mxg_csr_t *At)
 int mxg_dev_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src, void *d_dst,
                             size_t ld_dst, void *stream)
 {
+    MXG_TRY(ensure_device_ready());
     return launch_transpose_dense(elem_size, rows, cols, d_src, ld_src, d_dst, ld_dst, static_cast<cudaStream_t>(stream));
 }
 
@@ -546,6 +562,7 @@ int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts)
 int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed, int keep,
                   void *stream, mxg_csr_t *handle)
 {
+    MXG_TRY(ensure_device_ready());
     if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
     *handle = nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -5,8 +5,8 @@
 // column, so that inside every column the row ids ascend and duplicates keep their stored order —
 // exactly what the CPU counting sort produces.  Integer work, no floating point, bit-exact.
 //
-//   1. histogram  : count[c] += 1 for every entry (integer atomics commute => deterministic),
-//                   exclusive scan -> p2[K+1];
+//   1. histogram  : count[c] = entries in column c (integer atomics commute => deterministic; accumulated by the
+//                   last radix pass, one atomic per run of equal ids in a tile), exclusive scan -> p2[K+1];
 //   2. row expand : rowid[e] = r for e in [p[r], p[r+1]);
 //   3. stable LSD radix sort of the records (column key, row id, value) by 8-bit digits of the key,
 //      least significant first, ceil(log2(K)/8) passes.  Per pass:
@@ -72,12 +72,6 @@ int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *
 }
 
 // ================================ K4: CSR -> CSC ===================================================
-__global__ void __launch_bounds__(256) k_col_histogram(size_t nnz, const int32_t *__restrict__ j, int32_t *__restrict__ count)
-{
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) atomicAdd(&count[__ldg(j + e)], 1);
-}
-
 // one warp per row writes the row id over the row's entries
 __global__ void __launch_bounds__(256) k_expand_rows(int m, const int32_t *__restrict__ p, int32_t base, int32_t *__restrict__ rowid)
 {
@@ -89,25 +83,28 @@ __global__ void __launch_bounds__(256) k_expand_rows(int m, const int32_t *__res
     }
 }
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;                   // scatter CTA: 16 warps keep enough loads in flight at 2 CTAs / SM
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_STEPS = 16;                      // 32-entry steps per warp
+constexpr int RS_STEPS = 8;                       // 32-entry steps per warp
 constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;      // 512 consecutive entries per warp
 constexpr int RS_TILE = RS_WARPS * RS_WARP_ITEMS; // 4096 entries per CTA
 constexpr int RS_BINS = 256;
+constexpr int RS_HIST_THREADS = RS_BINS;          // histogram CTA: one thread per bin
 
 // a) digit histogram of every tile, written digit-major: hist[d * ntiles + tile]
-__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(size_t n, const int32_t *__restrict__ keys, int shift,
-                                                           int32_t *__restrict__ hist, int ntiles)
+__global__ void __launch_bounds__(RS_HIST_THREADS) k_radix_hist(size_t n, const int32_t *__restrict__ keys, int shift,
+                                                                int32_t *__restrict__ hist, int ntiles)
 {
     __shared__ int bins[RS_BINS];
     bins[threadIdx.x] = 0;
     __syncthreads();
     const size_t t0 = (size_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
-    for (int k = 0; k < RS_TILE / RS_THREADS; k++) {
-        const size_t e = t0 + (size_t)k * RS_THREADS + threadIdx.x;
-        if (e < n) atomicAdd(&bins[(__ldg(keys + e) >> shift) & (RS_BINS - 1)], 1);
+    for (int k = 0; k < RS_TILE / RS_HIST_THREADS; k++) {
+        const size_t e = t0 + (size_t)k * RS_HIST_THREADS + threadIdx.x;
+        if (e < n) {
+            atomicAdd(&bins[(__ldg(keys + e) >> shift) & (RS_BINS - 1)], 1);
+        }
     }
     __syncthreads();
     hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = bins[threadIdx.x];
@@ -122,6 +119,7 @@ struct RadixIO {
     int32_t *rows_out;
     double *x64_out;
     float *x32_out;
+    int32_t *col_count; // last pass only: entries per column (-> p2); nullptr otherwise
 };
 
 constexpr size_t radix_smem_bytes(bool h64, bool h32)
@@ -169,29 +167,32 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
         __syncwarp();
     }
     __syncthreads();
-    {
-        // per-warp counts -> per-warp starts inside the digit; digit totals -> tile-local digit starts
-        const int d = threadIdx.x; // RS_THREADS == RS_BINS
-        int run = 0;
+    // per-warp counts -> per-warp starts inside the digit; digit totals -> tile-local digit starts.
+    // One thread per digit (the first RS_BINS threads = the first RS_BINS / 32 warps); everybody meets at the barriers.
+    __shared__ int warp_tot[RS_BINS / 32];
+    int run = 0, incl = 0;
+    if (threadIdx.x < RS_BINS) {
+        const int d = threadIdx.x;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             const int c = wcnt[w * RS_BINS + d];
             wcnt[w * RS_BINS + d] = run;
             run += c;
         }
-        // block-wide exclusive scan of `run` over the 256 digits
-        __shared__ int warp_tot[RS_WARPS];
-        int incl = run;
+        incl = run; // warp-wide inclusive scan of the digit totals
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, dd);
             if (lane >= dd) incl += t;
         }
         if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_BINS) {
+        const int d = threadIdx.x;
         int wbase = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++)
+        for (int w = 0; w < RS_BINS / 32; w++)
             if (w < warp) wbase += warp_tot[w];
         const int excl = wbase + incl - run;
         dig_off[d] = excl;
@@ -220,6 +221,18 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
         io.rows_out[dst] = s_row[i];
         if (H64) io.x64_out[dst] = s_x64[i];
         if (H32) io.x32_out[dst] = s_x32[i];
+        // Last pass: the input was sorted by the lower digits and the re-order above is stable, so the tile is now
+        // sorted by the whole column id.  The first entry of every run of equal ids adds the run length to the
+        // column's count: one global atomic per (tile, column) instead of one per stored entry.
+        if (io.col_count != nullptr && (i == 0 || s_key[i - 1] != k)) {
+            int a = i + 1, b = tile_n; // first position after i whose key differs
+            while (a < b) {
+                const int mid = (a + b) >> 1;
+                if (s_key[mid] == k) a = mid + 1;
+                else b = mid;
+            }
+            atomicAdd(&io.col_count[k], a - i);
+        }
     }
 }
 
@@ -253,15 +266,11 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     const double *x64 = h64 ? d_x64 + base : nullptr;
     const float *x32 = h32 ? d_x32 + base : nullptr;
 
-    // p2: histogram + scan (count has K+1 slots so the scan output is the full pointer array)
+    // p2 = exclusive scan of the per-column counts (K+1 slots so the scan output is the full pointer array); the
+    // counts are accumulated by the LAST radix pass, where equal column ids sit next to each other in a tile
     int32_t *d_count = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_count, sizeof(int32_t) * ((size_t)K + 1), stream));
     MXG_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * ((size_t)K + 1), stream));
-    int g = ceil_div_i(nnz, 256 * 4);
-    if (g > 148 * 32) g = 148 * 32;
-    MXG_LAUNCH(k_col_histogram, g, 256, 0, stream, n, j, d_count);
-    MXG_TRY(exclusive_scan_i32(d_count, d_p2, (size_t)K + 1, stream));
-    MXG_CUDA_TRY(cudaFreeAsync(d_count, stream));
 
     // row ids per entry
     int32_t *d_rowid = nullptr;
@@ -302,7 +311,8 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
         io.rows_out = last ? d_i2 : o.row;
         io.x64_out = last ? d_x64o : o.x64;
         io.x32_out = last ? d_x32o : o.x32;
-        MXG_LAUNCH(k_radix_hist, ntiles, RS_THREADS, 0, stream, n, io.keys_in, shift, d_hist, ntiles);
+        io.col_count = last ? d_count : nullptr;
+        MXG_LAUNCH(k_radix_hist, ntiles, RS_HIST_THREADS, 0, stream, n, io.keys_in, shift, d_hist, ntiles);
         MXG_TRY(exclusive_scan_i32(d_hist, d_hist, hist_n, stream));
         int rc;
         if (h64 && h32) rc = launch_radix_scatter<true, true>(n, io, shift, d_hist, ntiles, stream);
@@ -316,6 +326,8 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
         io.x32_in = io.x32_out;
     }
 
+    MXG_TRY(exclusive_scan_i32(d_count, d_p2, (size_t)K + 1, stream));
+    MXG_CUDA_TRY(cudaFreeAsync(d_count, stream));
     MXG_CUDA_TRY(cudaFreeAsync(d_hist, stream));
     for (int b = 0; b < nbuf; b++) {
         MXG_CUDA_TRY(cudaFreeAsync(buf[b].key, stream));
