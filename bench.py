@@ -599,10 +599,17 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) is sent to
+    # stderr by pointing fd 1 at fd 2 for the duration of the run; print() below writes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
