@@ -53,6 +53,15 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
+# `ncu --set full` captures of exactly these workloads (profiles/README.md); None where no capture exists.
+NCU_TRAFFIC = {
+    "cfg3": (15.631161e9 + 0.518237e9, "profiles/r01_v3_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": (39.178352e9 + 1.051749e9, "profiles/r01_v3_spmm_f64_k64.ncu.txt"),
+    "cfg2": (1.220731e9 + 0.018394e9, "profiles/r01_v3_spmv_f64_cfg2.ncu.txt"),
+}
+
+
 def w_alg_bytes(m, K, nnz, n, s):
     """compulsory traffic, every operand byte once; values stored in the compute type."""
     return nnz * (4 + s) + 4 * (m + 1) + s * K * n + s * m * n
@@ -370,7 +379,9 @@ def run_ours(args):
         "effective_GBps": achieved,
         "compute_only": {"value": flops_step / (ms_kernel * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_kernel},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": w_alg,
+                     "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
+                     "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1] if world == 1 else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": w_alg,
                      "note": "W_alg = nnz*(4+s)+4(m+1)+s*K*n+s*m*n per GPU; gather-model bytes (B row per entry) = %.2f GB"
                              % ((nnz * (4 + s) + 4 * (m + 1) + s * nnz * n + s * m * n) / 1e9)},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -48,6 +48,7 @@ extern "C" {
 #define MXG_Y_INTEGER 1 /* int y, NA_INTEGER    : matmul_csr_dvec_integer  src/matmul.cpp:437 */
 #define MXG_Y_LOGICAL 2 /* int y, NA_LOGICAL    : matmul_csr_dvec_logical  src/matmul.cpp:453 */
 #define MXG_Y_FLOAT32 3 /* float y, float result: matmul_csr_dvec_float32  src/matmul.cpp:469 */
+#define MXG_Y_BINARY 4  /* sparse vectors only: pattern vector, every stored entry is 1: matmul_csr_svec_binary src/matmul.cpp:608 */
 
 /* most result buffers one product can write (the local one + the peer-mapped ones of the other GPUs of a box) */
 #define MXG_MAX_DST 8
@@ -71,7 +72,8 @@ int mxg_set_device(int device);
 
 /* Tuning knobs, all optional ("auto" when never set). Names: "piece" (nnz per long-row piece),
  * "spmm_lpr" (lanes per row of B), "spmm_rpw" (rows per warp), "spmm_panel_mb" (column-panel size of the
- * dense operand in MiB, 0 = off), "spmm_panel_cols" (forced panel width in columns), "spmv_lpr", "spmv_tex" (numeric SpMV gathers y through the texture path, default 1), "h2d_chunk_mb", "pipeline" (level-1 calls: 1 = streamed row chunks, 0 = whole-matrix
+ * dense operand in MiB, 0 = off), "spmm_panel_cols" (forced panel width in columns), "spmv_lpr", "spmv_tex" (numeric SpMV gathers y through the texture path, default 1), "svec_smem" (sparse-vector
+ * product keeps the presence bitmap in shared memory when it fits, default 1), "h2d_chunk_mb", "pipeline" (level-1 calls: 1 = streamed row chunks, 0 = whole-matrix
  * upload first), "pipe_chunk_nnz" (stored entries per streamed chunk, 0 = auto).  Unknown names return MXG_ERR_ARG. */
 int mxg_set_option(const char *name, long value);
 int mxg_get_option(const char *name, long *value);
@@ -107,6 +109,18 @@ int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout,
 int mxg_spmv_csr(int ytype, int m, int K,
                  const int32_t *p, const int32_t *j, const double *x,
                  const void *y, void *out);
+
+/* out[m] (always double) = A_csr(m x K) . y for a SPARSE vector y given as n_y (index, value) pairs with 1-based
+ * indices, as R's sparseVector@i / @x.  Replaces matmul_csr_svec<> (src/matmul.cpp:486-551) and its exports
+ * matmul_csr_svec_{numeric,integer,logical,binary,float32} (553-641), called from gemv_csr_vec (R/matmul.R:595-646).
+ * ytype: MXG_Y_NUMERIC (double values), MXG_Y_INTEGER / MXG_Y_LOGICAL (int values, INT_MIN = NA -> NA_real_,
+ * src/matmul.cpp:523-528), MXG_Y_FLOAT32 (float values), MXG_Y_BINARY (y_vals ignored, may be NULL).
+ * K: number of columns of A, or <= 0 when unknown (the reference's export does not receive it): column ids are
+ * then only required to be non-negative.  Indices of y outside [1, K] never match and are ignored, a repeated
+ * index keeps its first entry (what the reference's merge does); y and the rows of A need not be sorted. */
+int mxg_spmv_csr_svec(int ytype, int m, int K,
+                      const int32_t *p, const int32_t *j, const double *x,
+                      int n_y, const int32_t *y_idx_base1, const void *y_vals, double *out);
 
 /* Deep CSR(m x K) -> CSC conversion, bit-exact stable counting order (rows ascending inside each
  * column, duplicates in stored order).  Replaces the `as(x, "CsparseMatrix")` that
@@ -156,6 +170,10 @@ int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,
                  const void *d_B, size_t ldb, void *d_Out, size_t ldc, void *stream);
 
 int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *stream);
+
+/* Sparse-vector product on a device-resident handle; d_yidx_base1 / d_yvals / d_out are device pointers. */
+int mxg_dev_spmv_svec(mxg_csr_t A, int ytype, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
+                      double *d_out, void *stream);
 
 /* Multi-GPU form of the two products (north_star subsystem 4; no counterpart in the reference, which is one
  * process on shared memory: the OpenMP row loop of src/matmul.cpp:132-136 is the decomposition kept here).

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmxgpu.so")
 MXG_OK, MXG_ERR_CUDA, MXG_ERR_ARG, MXG_ERR_INDEX, MXG_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 MXG_F64, MXG_F32 = 0, 1
 MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS = 0, 1
-MXG_Y_NUMERIC, MXG_Y_INTEGER, MXG_Y_LOGICAL, MXG_Y_FLOAT32 = 0, 1, 2, 3
+MXG_Y_NUMERIC, MXG_Y_INTEGER, MXG_Y_LOGICAL, MXG_Y_FLOAT32, MXG_Y_BINARY = 0, 1, 2, 3, 4
 MXG_KEEP_F64, MXG_KEEP_F32 = 1, 2
 
 
@@ -36,6 +36,8 @@ _SIGNATURES = {
     "mxg_trim": [],
     "mxg_spmm_csr_dense": [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz],
     "mxg_spmv_csr": [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mxg_spmv_csr_svec": [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
+    "mxg_dev_spmv_svec": [_vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "mxg_csr2csc": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mxg_spmm_csrT_dense": [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz],
     "mxg_csr_upload": [_i32, _i32, _vp, _vp, _vp, _i32, C.POINTER(_vp)],

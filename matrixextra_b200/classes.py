@@ -93,6 +93,29 @@ class float32:
         return self.Data.ndim == 1
 
 
+@dataclass
+class sparseVector:
+    """Matrix::sparseVector family: ``i`` 1-based positions (R stores them as integer or double), ``x`` the stored
+    values (absent for the pattern class), ``length``.  ``kind`` is the class letter: "d" dsparseVector (double),
+    "i" isparseVector (int32, NA = INT_MIN), "l" lsparseVector (int32 0/1, NA = INT_MIN), "n" nsparseVector."""
+    i: np.ndarray
+    x: Optional[np.ndarray]
+    length: int
+    kind: str = "d"
+
+    def __post_init__(self):
+        self.i = _i32(self.i)  # as.integer(y@i), R/matmul.R:611
+        if self.kind == "d":
+            self.x = _f64(self.x)
+        elif self.kind in ("i", "l"):
+            self.x = _i32(self.x)
+        elif self.kind == "n":
+            self.x = None
+        else:
+            raise ValueError("sparseVector kind must be one of d, i, l, n")
+        self.length = int(self.length)
+
+
 def t_shallow(x):
     """CSR of X relabelled as the CSC of t(X) and vice versa: no data movement (R/trans.R:1-29, 135-149)."""
     if isinstance(x, dgRMatrix):

@@ -293,6 +293,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
     if (!strcmp(name, "spmv_tex")) return &o.spmv_tex;
+    if (!strcmp(name, "svec_smem")) return &o.svec_smem;
     if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;
     if (!strcmp(name, "pipeline")) return &o.pipeline;
     if (!strcmp(name, "pipe_chunk_nnz")) return &o.pipe_chunk_nnz;
@@ -665,6 +666,65 @@ int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, co
         rc = body();
     }
     cudaStreamSynchronize(st->stream);
+    free_handle(A);
+    return rc;
+}
+
+int mxg_dev_spmv_svec(mxg_csr_t A, int ytype, int n_y, const int32_t *d_yidx_base1, const void *d_yvals, double *d_out,
+                      void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmv_svec: NULL handle");
+    if (A->m > 0 && !d_out) return fail(MXG_ERR_ARG, "dev_spmv_svec: output is NULL");
+    return launch_spmv_svec(A, ytype, A->K, n_y, d_yidx_base1, d_yvals, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_spmv_csr_svec(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, int n_y,
+                      const int32_t *y_idx_base1, const void *y_vals, double *out)
+{
+    if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_BINARY) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
+    if (m < 0 || n_y < 0) return fail(MXG_ERR_ARG, "svec: negative size");
+    if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
+    if (m > 0 && !out) return fail(MXG_ERR_ARG, "output is NULL");
+    if (n_y > 0 && (!y_idx_base1 || (!y_vals && ytype != MXG_Y_BINARY))) return fail(MXG_ERR_ARG, "sparse vector is NULL");
+    if (m == 0) return MXG_OK;
+    // columns the presence bitmap has to cover: all of A's when K is known, else up to the largest index of y
+    int kmask = K;
+    if (K <= 0) {
+        kmask = 0;
+        for (int k = 0; k < n_y; k++) kmask = std::max(kmask, y_idx_base1[k]);
+    }
+    if (n_y == 0 || kmask <= 0 || p[m] - p[0] <= 0) { // src/matmul.cpp:495-496
+        std::memset(out, 0, sizeof(double) * (size_t)m);
+        return MXG_OK;
+    }
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *A = nullptr;
+    MXG_TRY(upload_csr(m, K > 0 ? K : INT32_MAX, p, j, x, MXG_KEEP_F64, st->stream, &A));
+    cudaStream_t s = st->stream;
+    int32_t *d_yi = nullptr;
+    void *d_yv = nullptr;
+    double *d_out = nullptr;
+    const size_t vs = ytype == MXG_Y_NUMERIC ? 8 : 4;
+    auto body = [&]() -> int {
+        MXG_CUDA_TRY(cudaMallocAsync(&d_yi, sizeof(int32_t) * (size_t)n_y, s));
+        MXG_CUDA_TRY(cudaMemcpyAsync(d_yi, y_idx_base1, sizeof(int32_t) * (size_t)n_y, cudaMemcpyHostToDevice, s));
+        if (ytype != MXG_Y_BINARY) {
+            MXG_CUDA_TRY(cudaMallocAsync(&d_yv, vs * (size_t)n_y, s));
+            MXG_CUDA_TRY(cudaMemcpyAsync(d_yv, y_vals, vs * (size_t)n_y, cudaMemcpyHostToDevice, s));
+        }
+        MXG_CUDA_TRY(cudaMallocAsync(&d_out, sizeof(double) * (size_t)m, s));
+        MXG_TRY(launch_spmv_svec(A, ytype, kmask, n_y, d_yi, d_yv, d_out, s));
+        MXG_CUDA_TRY(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, s));
+        MXG_CUDA_TRY(cudaStreamSynchronize(s));
+        return MXG_OK;
+    };
+    const int rc = body();
+    if (d_yi) cudaFreeAsync(d_yi, s);
+    if (d_yv) cudaFreeAsync(d_yv, s);
+    if (d_out) cudaFreeAsync(d_out, s);
+    cudaStreamSynchronize(s);
     free_handle(A);
     return rc;
 }

@@ -51,6 +51,7 @@ struct Options {
     long spmm_panel_cols = 0; // force a panel width in columns of A (tests / sweeps); 0 = by size
     long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
     long spmv_lpr = 0;        // 0 = auto
+    long svec_smem = 1;       // sparse-vector product: keep the presence bitmap in shared memory when it fits (<= 200 KB)
     long spmv_tex = 1;        // gather a numeric y through the texture path (7 % faster than LDG on cfg2); 0 = plain loads
     long h2d_chunk_mb = 64;   // staging chunk of the value narrowing in mxg_csr_upload
     long pipe_chunk_nnz = 0;  // stored entries (and rows) per chunk of the streamed path; 0 = auto (nnz/16, >= 1 Mi)
@@ -137,6 +138,9 @@ int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, cons
 // spmv.cu
 int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream);
 int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream);
+// CSR x sparse vector (indices base 1, K = columns covered by the presence bitmap), double result
+int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
+                     double *d_out, cudaStream_t stream);
 // transpose.cu
 int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src,
                            void *d_dst, size_t ld_dst, cudaStream_t stream);

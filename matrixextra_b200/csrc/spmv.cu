@@ -13,6 +13,7 @@
 #include "mxg_internal.cuh"
 
 #include <limits.h>
+#include <algorithm>
 
 namespace mxg {
 
@@ -334,6 +335,266 @@ int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst,
     case MXG_Y_FLOAT32: return spmv_values<MXG_Y_FLOAT32>(A, d_y, n_dst, d_outs, stream);
     default: return fail(MXG_ERR_ARG, "spmv: bad ytype %d", ytype);
     }
+}
+
+
+// ================================================================================================
+// CSR x SPARSE vector.  Replaces matmul_csr_svec<> (src/matmul.cpp:486-551) and its
+// exports _numeric/_integer/_logical/_binary/_float32 (553-641): out[r] = sum over the columns that
+// row r and the sparse vector share.  The reference walks both sorted index lists per row (merge with
+// std::lower_bound skips); here the sparse vector is scattered once into a dense double image plus a
+// presence bitmap (K/8 bytes: 125 KB for 1 M columns, kept in SHARED memory when it fits), and a
+// row-split kernel tests each stored column against the bitmap, touching x[] and the dense image
+// only on a hit.  The sums visit a row's matches in the same set as the reference (tree order instead
+// of left-to-right, 1e-12); rows of A need not be sorted here.  NA rules of src/matmul.cpp:523-531:
+// integer / logical NA contributes NA_real_ (also a stored NA_real_ of a numeric vector keeps R's payload).
+// Bound: HBM on the 4-byte column ids (x is read only where the vector has an entry).
+// ================================================================================================
+
+template <int YTYPE>
+struct SvecValue;
+template <>
+struct SvecValue<MXG_Y_NUMERIC> {
+    typedef double elem;
+    static __device__ __forceinline__ double get(const double *v, int k) { return v[k]; }
+};
+template <>
+struct SvecValue<MXG_Y_INTEGER> {
+    typedef int elem;
+    static __device__ __forceinline__ double get(const int *v, int k) { return v[k] == INT_MIN ? na_real() : (double)v[k]; }
+};
+template <>
+struct SvecValue<MXG_Y_LOGICAL> {
+    typedef int elem;
+    static __device__ __forceinline__ double get(const int *v, int k) { return v[k] == INT_MIN ? na_real() : (v[k] != 0 ? 1.0 : 0.0); }
+};
+template <>
+struct SvecValue<MXG_Y_FLOAT32> {
+    typedef float elem;
+    static __device__ __forceinline__ double get(const float *v, int k) { return (double)v[k]; }
+};
+template <>
+struct SvecValue<MXG_Y_BINARY> {
+    typedef int elem;
+    static __device__ __forceinline__ double get(const int *, int) { return 1.0; }
+};
+
+// dense image + bitmap of the sparse vector.  A repeated index keeps its FIRST occurrence, as the
+// reference's merge does for a sorted list (src/matmul.cpp:520-535: both cursors advance on a match).
+template <int YTYPE>
+__global__ void __launch_bounds__(256) k_svec_scatter(int n_y, const int32_t *__restrict__ yidx_base1,
+                                                      const typename SvecValue<YTYPE>::elem *__restrict__ yvals, int K,
+                                                      double *__restrict__ yd, unsigned *__restrict__ mask)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_y) return;
+    const int c = yidx_base1[k] - 1;
+    if (c < 0 || c >= K) return; // can never equal a column id of A
+    if (k > 0 && yidx_base1[k - 1] == yidx_base1[k]) return;
+    atomicOr(mask + (c >> 5), 1u << (c & 31));
+    yd[c] = SvecValue<YTYPE>::get(yvals, k);
+}
+
+struct SvecArgs {
+    int m;
+    const int32_t *p;
+    const int32_t *j;
+    const double *x;
+    const double *yd;
+    const unsigned *mask;
+    int K;          // columns covered by the bitmap
+    int mask_words; // ceil(K / 32)
+    double *out;
+    int piece, n_pieces;
+    const int32_t *piece_row;
+    const int32_t *piece_k;
+    double *partial;
+    int *partial_na;
+    const int *abort;
+};
+
+template <int LPR, bool SMASK>
+__device__ __forceinline__ double team_dot_masked(const int a, const int b, const int maxlen, const int l,
+                                                  const int32_t *__restrict__ j, const double *__restrict__ x,
+                                                  const double *__restrict__ yd, const unsigned *mask, const int K, bool &na)
+{
+    constexpr int U = 8; // column ids in flight per lane: the ids are the only streamed operand
+    double acc = 0.0;
+    for (int e0 = 0; e0 < maxlen; e0 += LPR * U) {
+        int jj[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int e = a + e0 + u * LPR + l;
+            jj[u] = e < b ? __ldcs(j + e) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned c = (unsigned)jj[u];
+            if (c < (unsigned)K) {
+                const unsigned w = SMASK ? mask[c >> 5] : __ldg(mask + (c >> 5));
+                if ((w >> (c & 31)) & 1u) {
+                    const double yy = __ldg(yd + c);
+                    const double xx = __ldg(x + (a + e0 + u * LPR + l));
+                    if (__double_as_longlong(yy) == 0x7FF00000000007A2LL) na = true;
+                    acc = fma(xx, yy, acc);
+                }
+            }
+        }
+    }
+    return acc;
+}
+
+template <int LPR, bool SMASK>
+__global__ void __launch_bounds__(SMASK ? 1024 : 256) k_spmv_svec(const SvecArgs g)
+{
+    extern __shared__ unsigned s_mask[];
+    const unsigned *mask = g.mask;
+    if (g.abort != nullptr && *g.abort != 0) return;
+    if (SMASK) {
+        for (int i = threadIdx.x; i < g.mask_words; i += blockDim.x) s_mask[i] = g.mask[i];
+        __syncthreads();
+        mask = s_mask;
+    }
+    const int32_t *__restrict__ p = g.p;
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    // long-row pieces first: one warp each, partial sums combined by k_spmv_fixup in piece order
+    for (int pc = blockIdx.x * warps + (threadIdx.x >> 5); pc < g.n_pieces; pc += gridDim.x * warps) {
+        const int row = g.piece_row[pc];
+        const int a = p[row] + g.piece_k[pc] * g.piece;
+        const int b = min(a + g.piece, p[row + 1]);
+        bool na = false;
+        double acc = team_dot_masked<32, SMASK>(a, b, b - a, lane, g.j, g.x, g.yd, mask, g.K, na);
+        acc = team_reduce<32>(acc);
+        na = team_any<32>(na);
+        if (lane == 0) {
+            g.partial[pc] = acc;
+            g.partial_na[pc] = na ? 1 : 0;
+        }
+    }
+    const int teams = blockDim.x / LPR;
+    const int team = threadIdx.x / LPR;
+    const int l = threadIdx.x % LPR;
+    const int n_blocks = (g.m + teams - 1) / teams;
+    const SpmvExtra none = {{nullptr}, 0};
+    for (int rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+        const int row = rb * teams + team;
+        int a = 0, b = 0;
+        bool store = false;
+        if (row < g.m) {
+            a = p[row];
+            b = p[row + 1];
+            store = true;
+            if (b - a > g.piece) {
+                b = a;
+                store = false;
+            }
+        }
+        const int maxlen = __reduce_max_sync(0xffffffffu, b - a);
+        bool na = false;
+        double acc = team_dot_masked<LPR, SMASK>(a, b, maxlen, l, g.j, g.x, g.yd, mask, g.K, na);
+        acc = team_reduce<LPR>(acc);
+        na = team_any<LPR>(na);
+        if (store && l == 0) store_result<MXG_Y_NUMERIC>(g.out, none, row, acc, na);
+    }
+}
+
+template <int YTYPE>
+static int svec_scatter(int n_y, const int32_t *d_yidx, const void *d_yvals, int K, double *yd, unsigned *mask, cudaStream_t stream)
+{
+    MXG_LAUNCH((k_svec_scatter<YTYPE>), ceil_div_i(n_y, 256), 256, 0, stream, n_y, d_yidx,
+               static_cast<const typename SvecValue<YTYPE>::elem *>(d_yvals), K, yd, mask);
+    return MXG_OK;
+}
+
+int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
+                     double *d_out, cudaStream_t stream)
+{
+    if (A->m == 0) return MXG_OK;
+    if (n_y < 0 || K < 0) return fail(MXG_ERR_ARG, "svec: negative size");
+    if (n_y == 0 || K == 0 || A->nnz == 0) { // src/matmul.cpp:495-496: an empty vector gives the zero-filled result
+        MXG_CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)A->m, stream));
+        return MXG_OK;
+    }
+    if (!A->d_x64) return fail(MXG_ERR_UNSUPPORTED, "svec: handle holds no float64 values");
+    if (!d_yidx_base1 || (!d_yvals && ytype != MXG_Y_BINARY)) return fail(MXG_ERR_ARG, "svec: NULL vector");
+    const int words = ceil_div_i(K, 32);
+    double *yd = nullptr;
+    unsigned *mask = nullptr;
+    MXG_CUDA_TRY(cudaMallocAsync(&yd, sizeof(double) * (size_t)K, stream));
+    MXG_CUDA_TRY(cudaMallocAsync(&mask, sizeof(unsigned) * (size_t)words, stream));
+    MXG_CUDA_TRY(cudaMemsetAsync(mask, 0, sizeof(unsigned) * (size_t)words, stream));
+    int rc = MXG_OK;
+    switch (ytype) {
+    case MXG_Y_NUMERIC: rc = svec_scatter<MXG_Y_NUMERIC>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    case MXG_Y_INTEGER: rc = svec_scatter<MXG_Y_INTEGER>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    case MXG_Y_LOGICAL: rc = svec_scatter<MXG_Y_LOGICAL>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    case MXG_Y_FLOAT32: rc = svec_scatter<MXG_Y_FLOAT32>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    case MXG_Y_BINARY: rc = svec_scatter<MXG_Y_BINARY>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    default: rc = fail(MXG_ERR_ARG, "svec: bad ytype %d", ytype);
+    }
+    if (rc == MXG_OK) {
+        SvecArgs args;
+        args.m = A->m;
+        args.p = A->d_p;
+        args.j = A->d_j;
+        args.x = A->d_x64;
+        args.yd = yd;
+        args.mask = mask;
+        args.K = K;
+        args.mask_words = words;
+        args.out = d_out;
+        args.piece = A->piece;
+        args.n_pieces = A->n_pieces;
+        args.piece_row = A->d_piece_row;
+        args.piece_k = A->d_piece_k;
+        args.partial = nullptr;
+        args.partial_na = nullptr;
+        args.abort = A->d_abort;
+        if (A->n_pieces > 0) {
+            rc = ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * 16);
+            args.partial = static_cast<double *>(A->d_partial);
+            args.partial_na = reinterpret_cast<int *>(static_cast<double *>(A->d_partial) + A->n_pieces);
+        }
+        int lpr = (int)options().spmv_lpr;
+        if (lpr != 4 && lpr != 8 && lpr != 16 && lpr != 32) {
+            const double mean = (double)A->nnz / (double)A->m;
+            lpr = mean <= 12 ? 4 : mean <= 96 ? 8 : mean <= 384 ? 16 : 32; // 8 ids per lane per step
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t smem = sizeof(unsigned) * (size_t)words;
+        const bool smask = options().svec_smem != 0 && smem <= 200 * 1024;
+#define MXG_SVEC(L)                                                                                                    \
+    if (rc == MXG_OK && lpr == L) {                                                                                    \
+        auto body = [&]() -> int {                                                                                     \
+            if (smask) {                                                                                               \
+                MXG_CUDA_TRY(cudaFuncSetAttribute(k_spmv_svec<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                MXG_LAUNCH((k_spmv_svec<L, true>), sms, 1024, smem, stream, args);                                     \
+            } else {                                                                                                   \
+                const int want = std::max(ceil_div_i(A->m, 256 / L), ceil_div_i(A->n_pieces, 8));                      \
+                MXG_LAUNCH((k_spmv_svec<L, false>), std::min(want, sms * 64), 256, 0, stream, args);                   \
+            }                                                                                                          \
+            return MXG_OK;                                                                                             \
+        };                                                                                                             \
+        rc = body();                                                                                                   \
+    }
+        MXG_SVEC(4) MXG_SVEC(8) MXG_SVEC(16) MXG_SVEC(32)
+#undef MXG_SVEC
+        if (rc == MXG_OK && A->n_long > 0) {
+            auto body = [&]() -> int {
+                const SpmvExtra none = {{nullptr}, 0};
+                MXG_LAUNCH((k_spmv_fixup<MXG_Y_NUMERIC>), ceil_div_i(A->n_long, 128), 128, 0, stream, A->n_long, A->d_long_rows,
+                           A->d_long_first, A->d_long_np, args.partial, args.partial_na, d_out, none, A->d_abort);
+                return MXG_OK;
+            };
+            rc = body();
+        }
+    }
+    cudaFreeAsync(yd, stream);
+    cudaFreeAsync(mask, stream);
+    return rc;
 }
 
 } // namespace mxg

@@ -114,6 +114,11 @@ class DeviceCSR:
     def spmv(self, y_t, out_t, ytype=MXG_Y_NUMERIC, stream=None):
         _lib.call("mxg_dev_spmv", self._h, int(ytype), _dptr(y_t), _dptr(out_t), _stream_ptr(stream))
 
+    def spmv_svec(self, yidx_base1_t, yvals_t, out_t, ytype=MXG_Y_NUMERIC, stream=None):
+        """out (float64) = A . sparse vector given by int32 1-based positions and values (device tensors)."""
+        _lib.call("mxg_dev_spmv_svec", self._h, int(ytype), int(yidx_base1_t.numel()), _dptr(yidx_base1_t), _dptr(yvals_t),
+                  _dptr(out_t), _stream_ptr(stream))
+
     def transpose(self, keep=MXG_KEEP_F64 | MXG_KEEP_F32, stream=None) -> "DeviceCSR":
         """Deep CSR -> CSC on device, returned as the CSR handle of t(A)."""
         h = C.c_void_p()

@@ -8,8 +8,9 @@ and which class comes back.  The three signatures MatrixExtra leaves to the Matr
 (``crossprod(Rsparse, matrix)``, ``Csparse %*% matrix``, ``matrix %*% Rsparse``)
 are added on top of the device CSR->CSC transpose.
 
-Sparse-vector right-hand sides and the single-column outer products (R/matmul.R:595-646, 659-744)
-are outside the scoped path and raise ``NotImplementedError``.
+Sparse-vector right-hand sides (R/matmul.R:595-646) run on the device too; the
+single-column outer products (R/matmul.R:659-744) are outside the scoped path and raise
+``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ import numpy as np
 
 from . import rcpp_exports as rx
 from ._lib import MXG_F32, MXG_F64
-from .classes import check_valid_matrix, dgCMatrix, dgRMatrix, float32, t_shallow
+from .classes import check_valid_matrix, dgCMatrix, dgRMatrix, float32, sparseVector, t_shallow
 
 #: options("MatrixExtra.*") read by the hot path (R/zzz.R:116-171).  ``nthreads`` is advisory on the GPU.
 options = {"MatrixExtra.nthreads": 1, "MatrixExtra.inplace_sort": False}
@@ -125,11 +126,23 @@ def gemm_csr_f32(x: dgRMatrix, y: float32):
 
 # ---- R/matmul.R:545-657 (dense-vector branches) -----------------------------------------------------
 def gemv_csr_vec(x: dgRMatrix, y):
-    ylen = y.Data.size if isinstance(y, float32) else np.asarray(y).size
+    if isinstance(y, sparseVector):
+        ylen = y.length
+    else:
+        ylen = y.Data.size if isinstance(y, float32) else np.asarray(y).size
     if x.Dim[1] != ylen:
         raise ValueError("Matrix-vector dimensions do not match.")
     check_valid_matrix(x)
     nt = int(options.get("MatrixExtra.nthreads", 1))
+    if isinstance(y, sparseVector):
+        # R/matmul.R:595-646.  The reference sorts x and y first (602-603) because its kernel merges two sorted
+        # lists; the device kernel tests membership in a bitmap and needs neither, so no sort is done here.
+        fn = {"d": rx.matmul_csr_svec_numeric, "i": rx.matmul_csr_svec_integer, "l": rx.matmul_csr_svec_logical}.get(y.kind)
+        if fn is not None:
+            res = fn(x.p, x.j, x.x, y.i, y.x, nt, ncols=x.Dim[1])
+        else:
+            res = rx.matmul_csr_svec_binary(x.p, x.j, x.x, y.i, nt, ncols=x.Dim[1])
+        return res.reshape(-1, 1)
     if isinstance(y, float32):
         res = rx.matmul_csr_dvec_float32(x.p, x.j, x.x, y.Data, nt)
         return float32(res.reshape(-1, 1))
@@ -197,7 +210,7 @@ def matmul(x, y):
         return gemm_csr_dense(x, y)
     if isinstance(x, dgRMatrix) and isinstance(y, float32):
         return gemm_csr_f32(x, y)
-    if isinstance(x, dgRMatrix) and isinstance(y, np.ndarray) and y.ndim == 1:
+    if isinstance(x, dgRMatrix) and ((isinstance(y, np.ndarray) and y.ndim == 1) or isinstance(y, sparseVector)):
         return matmul_csr_vec(x, y)
     if isinstance(x, dgCMatrix) and (_is_dense(y) or isinstance(y, float32)):
         return gemm_csc_dense(x, y)

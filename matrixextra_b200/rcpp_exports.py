@@ -15,8 +15,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_ROWS_CONTIGUOUS, MXG_Y_FLOAT32, MXG_Y_INTEGER,
-                   MXG_Y_LOGICAL, MXG_Y_NUMERIC)
+from ._lib import (MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_ROWS_CONTIGUOUS, MXG_Y_BINARY, MXG_Y_FLOAT32,
+                   MXG_Y_INTEGER, MXG_Y_LOGICAL, MXG_Y_NUMERIC)
 
 
 def _vp(a: np.ndarray):
@@ -122,6 +122,43 @@ def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, 
 
 def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32, out)
+
+
+# ---- CSR %*% sparseVector (src/matmul.cpp:553-641) ---------------------------------
+
+def _csr_svec(indptr, indices, values, y_indices_base1, y_values, ytype, y_np, ncols=0, out=None):
+    p, j, x = _csr(indptr, indices, values)
+    yi = np.ascontiguousarray(y_indices_base1, dtype=np.int32)
+    yv = None if y_values is None else np.ascontiguousarray(y_values, dtype=y_np)
+    if yv is not None and yv.size != yi.size:
+        raise ValueError("sparse vector: indices and values differ in length")
+    m = p.size - 1
+    out = _result((m,), np.float64, out)
+    # the reference's exports do not receive ncol(X); ncols=0 lets the library bound the columns by max(y@i)
+    _lib.call("mxg_spmv_csr_svec", ytype, m, int(ncols), _vp(p), _vp(j), _vp(x), int(yi.size), _vp(yi),
+              _vp(yv) if yv is not None else None, _vp(out))
+    return out
+
+
+def matmul_csr_svec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+    return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_NUMERIC, np.float64, ncols, out)
+
+
+def matmul_csr_svec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+    return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_INTEGER, np.int32, ncols, out)
+
+
+def matmul_csr_svec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+    return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_LOGICAL, np.int32, ncols, out)
+
+
+def matmul_csr_svec_binary(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, nthreads=1, ncols=0, out=None):
+    return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, None, MXG_Y_BINARY, np.int32, ncols, out)
+
+
+def matmul_csr_svec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+    """Exported by the reference but never called from R (src/matmul.cpp:626-641); double result."""
+    return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_FLOAT32, np.float32, ncols, out)
 
 
 # ---- additions beyond the reference's exports (SURVEY.md §3.4, §8 a6) -----------------------------

@@ -96,6 +96,8 @@ class Port:
         self.lib.mxo_spmv_float32.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f32p, _f32p, C.c_int]
         self.lib.mxo_csr2csc.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _i32p, _i32p, _f64p]
         self.lib.mxo_csr2csc.restype = C.c_int
+        self.lib.mxo_spmv_svec.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, C.c_int, _i32p, C.c_void_p, _f64p, C.c_int]
+        self.lib.mxo_spmv_svec.restype = None
 
     # -- kernels ------------------------------------------------------------------------------
     def _gather_rm(self, p, j, x, B_rows, nt):
@@ -173,6 +175,90 @@ class Port:
     def matmul_csr_dvec_float32(self, p, j, x, y_dense, nthreads=None):
         return self._spmv(self.lib.mxo_spmv_float32, p, j, x, y_dense, np.float32, np.float32,
                           nthreads or self.nthreads)
+
+    # -- CSR %*% sparse vector (src/matmul.cpp:486-641) ------------------------------
+    def _svec(self, ytype, p, j, x, yi, yv, np_t, nt):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        yi = _as_i32(yi)
+        yv = np.zeros(1, dtype=np.int32) if yv is None else np.ascontiguousarray(yv, dtype=np_t)
+        out = np.zeros(p.size - 1, dtype=np.float64)
+        self.lib.mxo_spmv_svec(ytype, p.size - 1, _ptr(p, _i32p), _ptr(j, _i32p), _ptr(x, _f64p), yi.size,
+                               _ptr(yi, _i32p), C.c_void_p(yv.ctypes.data), _ptr(out, _f64p), nt)
+        return out
+
+    def matmul_csr_svec_numeric(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(0, p, j, x, y_indices_base1, y_values, np.float64, nthreads or self.nthreads)
+
+    def matmul_csr_svec_integer(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(1, p, j, x, y_indices_base1, y_values, np.int32, nthreads or self.nthreads)
+
+    def matmul_csr_svec_logical(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(2, p, j, x, y_indices_base1, y_values, np.int32, nthreads or self.nthreads)
+
+    def matmul_csr_svec_float32(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(3, p, j, x, y_indices_base1, y_values, np.float32, nthreads or self.nthreads)
+
+    def matmul_csr_svec_binary(self, p, j, x, y_indices_base1, nthreads=None):
+        return self._svec(4, p, j, x, y_indices_base1, None, np.int32, nthreads or self.nthreads)
+
+    # -- index sorting and validity (src/misc.cpp:117-228, 970-1016) -----------------
+    def sort_sparse_indices_numeric(self, p, j, x):
+        """Returns sorted COPIES (the reference sorts in place)."""
+        p = _as_i32(p)
+        j, x = _as_i32(j).copy(), _as_f64(x).copy()
+        self.lib.mxo_sort_sparse_indices.argtypes = [C.c_int, _i32p, _i32p, _f64p]
+        if self.lib.mxo_sort_sparse_indices(p.size - 1, _ptr(p, _i32p), _ptr(j, _i32p), _ptr(x, _f64p)) != 0:
+            raise MemoryError
+        return j, x
+
+    def check_indices_are_unsorted(self, p, j):
+        """True when every row is sorted (the reference's name is misleading, src/misc.cpp:161-175)."""
+        p, j = _as_i32(p), _as_i32(j)
+        self.lib.mxo_rows_sorted.argtypes = [C.c_int, _i32p, _i32p]
+        return bool(self.lib.mxo_rows_sorted(p.size - 1, _ptr(p, _i32p), _ptr(j, _i32p)))
+
+    CSR_ERRORS = (None, "Matrix has negative indices.", "Matrix has invalid column indices.",
+                  "Matrix has indices with missing values.", "Matrix has missing values in the index pointer.",
+                  "Matrix index pointer is not monotonicaly increasing.")
+
+    def check_valid_csr_matrix(self, p, j, nrows, ncols):
+        """None when valid, else the reference's error string (src/misc.cpp:970-1016)."""
+        p, j = _as_i32(p), _as_i32(j)
+        self.lib.mxo_check_valid_csr.argtypes = [C.c_int, C.c_int, _i32p, _i32p, C.c_size_t]
+        return self.CSR_ERRORS[self.lib.mxo_check_valid_csr(int(nrows), int(ncols), _ptr(p, _i32p), _ptr(j, _i32p), j.size)]
+
+    # -- SURVEY.md §8 f4: elementwise CSR * dense (src/operators.cpp:239-330, 1501-2178) ---------------
+    def _mult_dense(self, dtype, p, j, x, dense, np_t):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        d = np.asfortranarray(dense, dtype=np_t)
+        out = np.zeros(j.size, dtype=np.float64)
+        self.lib.mxo_multiply_csr_by_dense.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, C.c_void_p, _f64p]
+        self.lib.mxo_multiply_csr_by_dense.restype = None
+        self.lib.mxo_multiply_csr_by_dense(dtype, p.size - 1, _ptr(p, _i32p), _ptr(j, _i32p), _ptr(x, _f64p),
+                                           C.c_void_p(d.ctypes.data), _ptr(out, _f64p))
+        return out
+
+    def multiply_csr_by_dense_elemwise_double(self, p, j, x, dense_mat):
+        return self._mult_dense(0, p, j, x, dense_mat, np.float64)
+
+    def multiply_csr_by_dense_elemwise_float32(self, p, j, x, dense_mat):
+        return self._mult_dense(1, p, j, x, dense_mat, np.float32)
+
+    def multiply_csr_by_dense_elemwise_int(self, p, j, x, dense_mat):
+        return self._mult_dense(2, p, j, x, dense_mat, np.int32)
+
+    def multiply_csr_by_dense_elemwise_bool(self, p, j, x, dense_mat):
+        return self._mult_dense(3, p, j, x, dense_mat, np.int32)
+
+    def multiply_csr_by_dvec_no_NAs_numeric(self, p, j, x, dvec, ncols):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        d = _as_f64(dvec)
+        out = np.zeros(j.size, dtype=np.float64)
+        self.lib.mxo_multiply_csr_by_dvec.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, C.c_size_t, _f64p]
+        self.lib.mxo_multiply_csr_by_dvec.restype = None
+        self.lib.mxo_multiply_csr_by_dvec(p.size - 1, int(ncols), _ptr(p, _i32p), _ptr(j, _i32p), _ptr(x, _f64p),
+                                          _ptr(d, _f64p), d.size, _ptr(out, _f64p))
+        return out
 
     # -- CSR -> CSC (Matrix package; restated) ---------------------------------------------------
     def csr2csc(self, m, K, p, j, x):
@@ -290,6 +376,96 @@ class Ref:
     def matmul_csr_dvec_float32(self, p, j, x, y, nthreads=None):
         return self._spmv(self.lib.mxref_matmul_csr_dvec_float32, p, j, x, y, np.float32, np.float32,
                           nthreads or self.nthreads)
+
+    # -- CSR %*% sparse vector, the reference's own exports (src/matmul.cpp:553-641) ---
+    def _svec(self, fn, p, j, x, yi, yv, np_t, nt):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        yi = _as_i32(yi)
+        yv = np.zeros(1, dtype=np.int32) if yv is None else np.ascontiguousarray(yv, dtype=np_t)
+        rc = fn(_ptr(p, _i32p), p.size - 1, _ptr(j, _i32p), _ptr(x, _f64p), j.size, _ptr(yi, _i32p),
+                C.c_void_p(yv.ctypes.data), yi.size, nt, None)
+        if rc != 0:
+            raise RuntimeError(f"reference driver returned {rc}")
+        return self._result(np.float64).reshape(-1)
+
+    def matmul_csr_svec_numeric(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(self.lib.mxref_matmul_csr_svec_numeric, p, j, x, y_indices_base1, y_values, np.float64,
+                          nthreads or self.nthreads)
+
+    def matmul_csr_svec_integer(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(self.lib.mxref_matmul_csr_svec_integer, p, j, x, y_indices_base1, y_values, np.int32,
+                          nthreads or self.nthreads)
+
+    def matmul_csr_svec_logical(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(self.lib.mxref_matmul_csr_svec_logical, p, j, x, y_indices_base1, y_values, np.int32,
+                          nthreads or self.nthreads)
+
+    def matmul_csr_svec_float32(self, p, j, x, y_indices_base1, y_values, nthreads=None):
+        return self._svec(self.lib.mxref_matmul_csr_svec_float32, p, j, x, y_indices_base1, y_values, np.float32,
+                          nthreads or self.nthreads)
+
+    def matmul_csr_svec_binary(self, p, j, x, y_indices_base1, nthreads=None):
+        return self._svec(self.lib.mxref_matmul_csr_svec_binary, p, j, x, y_indices_base1, None, np.int32,
+                          nthreads or self.nthreads)
+
+    # -- src/misc.cpp and src/operators.cpp compiled in place (libmxref_ops.so) ---
+    @staticmethod
+    def ops_available() -> bool:
+        return os.path.exists(os.path.join(_HERE, "_ref", "libmxref_ops.so"))
+
+    @property
+    def ops(self):
+        if getattr(self, "_ops", None) is None:
+            self._ops = C.CDLL(os.path.join(_HERE, "_ref", "libmxref_ops.so"))
+        return self._ops
+
+    def sort_sparse_indices_numeric(self, p, j, x):
+        """Returns sorted COPIES (the reference sorts in place, src/misc.cpp:300-313)."""
+        p = _as_i32(p)
+        j, x = _as_i32(j).copy(), _as_f64(x).copy()
+        self.ops.mxref_sort_sparse_indices_numeric(_ptr(p, _i32p), C.c_int(p.size - 1), _ptr(j, _i32p), _ptr(x, _f64p),
+                                                   C.c_int(j.size))
+        return j, x
+
+    def check_indices_are_unsorted(self, p, j):
+        p, j = _as_i32(p), _as_i32(j)
+        return bool(self.ops.mxref_check_indices_are_unsorted(_ptr(p, _i32p), C.c_int(p.size - 1), _ptr(j, _i32p)))
+
+    def check_valid_csr_matrix(self, p, j, nrows, ncols):
+        p, j = _as_i32(p), _as_i32(j)
+        buf = C.create_string_buffer(256)
+        rc = self.ops.mxref_check_valid_csr_matrix(_ptr(p, _i32p), C.c_int(int(nrows)), _ptr(j, _i32p), C.c_int(j.size),
+                                                   C.c_int(int(ncols)), buf, C.c_int(256))
+        return buf.value.decode() if rc else None
+
+    def _mult_dense(self, fn, p, j, x, dense, np_t):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        d = np.asfortranarray(dense, dtype=np_t)
+        out = np.zeros(j.size, dtype=np.float64)
+        fn(_ptr(p, _i32p), C.c_int(p.size - 1), _ptr(j, _i32p), _ptr(x, _f64p), C.c_int(j.size),
+           C.c_void_p(d.ctypes.data), C.c_size_t(d.size), _ptr(out, _f64p))
+        return out
+
+    def multiply_csr_by_dense_elemwise_double(self, p, j, x, dense_mat):
+        return self._mult_dense(self.ops.mxref_multiply_csr_by_dense_elemwise_double, p, j, x, dense_mat, np.float64)
+
+    def multiply_csr_by_dense_elemwise_float32(self, p, j, x, dense_mat):
+        return self._mult_dense(self.ops.mxref_multiply_csr_by_dense_elemwise_float32, p, j, x, dense_mat, np.float32)
+
+    def multiply_csr_by_dense_elemwise_int(self, p, j, x, dense_mat):
+        return self._mult_dense(self.ops.mxref_multiply_csr_by_dense_elemwise_int, p, j, x, dense_mat, np.int32)
+
+    def multiply_csr_by_dense_elemwise_bool(self, p, j, x, dense_mat):
+        return self._mult_dense(self.ops.mxref_multiply_csr_by_dense_elemwise_bool, p, j, x, dense_mat, np.int32)
+
+    def multiply_csr_by_dvec_no_NAs_numeric(self, p, j, x, dvec, ncols):
+        p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
+        d = _as_f64(dvec)
+        out = np.zeros(j.size, dtype=np.float64)
+        self.ops.mxref_multiply_csr_by_dvec_numeric(_ptr(p, _i32p), C.c_int(p.size - 1), _ptr(j, _i32p), _ptr(x, _f64p),
+                                                    C.c_int(j.size), _ptr(d, _f64p), C.c_size_t(d.size), C.c_int(int(ncols)),
+                                                    _ptr(out, _f64p))
+        return out
 
 
 def best_cpu_baseline(nthreads: int | None = None):

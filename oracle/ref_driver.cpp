@@ -229,3 +229,58 @@ int mxref_matmul_csr_dvec_float32(const int *p, int nrowsX, const int *j, const 
 }
 
 } /* extern "C" */
+
+/* ---- src/matmul.cpp:553-641 : CSR %*% sparse vector.  y indices are 1-based. ---- */
+extern "C" {
+
+int mxref_matmul_csr_svec_numeric(const int *p, int nrowsX, const int *j, const double *x, int nnz,
+                                  const int *yi, const double *yv, int ny, int nthreads, double *out)
+{
+    hold_vector(matmul_csr_svec_numeric(IV((int *)p, (size_t)nrowsX + 1), IV((int *)j, (size_t)nnz),
+                                        NV((double *)x, (size_t)nnz), IV((int *)yi, (size_t)ny),
+                                        NV((double *)yv, (size_t)ny), nthreads));
+    maybe_copy<double>(out);
+    return 0;
+}
+
+int mxref_matmul_csr_svec_integer(const int *p, int nrowsX, const int *j, const double *x, int nnz,
+                                  const int *yi, const int *yv, int ny, int nthreads, double *out)
+{
+    hold_vector(matmul_csr_svec_integer(IV((int *)p, (size_t)nrowsX + 1), IV((int *)j, (size_t)nnz),
+                                        NV((double *)x, (size_t)nnz), IV((int *)yi, (size_t)ny),
+                                        IV((int *)yv, (size_t)ny), nthreads));
+    maybe_copy<double>(out);
+    return 0;
+}
+
+int mxref_matmul_csr_svec_logical(const int *p, int nrowsX, const int *j, const double *x, int nnz,
+                                  const int *yi, const int *yv, int ny, int nthreads, double *out)
+{
+    hold_vector(matmul_csr_svec_logical(IV((int *)p, (size_t)nrowsX + 1), IV((int *)j, (size_t)nnz),
+                                        NV((double *)x, (size_t)nnz), IV((int *)yi, (size_t)ny),
+                                        LV((int *)yv, (size_t)ny), nthreads));
+    maybe_copy<double>(out);
+    return 0;
+}
+
+int mxref_matmul_csr_svec_binary(const int *p, int nrowsX, const int *j, const double *x, int nnz,
+                                 const int *yi, const void *unused, int ny, int nthreads, double *out)
+{
+    (void)unused;
+    hold_vector(matmul_csr_svec_binary(IV((int *)p, (size_t)nrowsX + 1), IV((int *)j, (size_t)nnz),
+                                       NV((double *)x, (size_t)nnz), IV((int *)yi, (size_t)ny), nthreads));
+    maybe_copy<double>(out);
+    return 0;
+}
+
+int mxref_matmul_csr_svec_float32(const int *p, int nrowsX, const int *j, const double *x, int nnz,
+                                  const int *yi, const int *yv_float_bits, int ny, int nthreads, double *out)
+{
+    hold_vector(matmul_csr_svec_float32(IV((int *)p, (size_t)nrowsX + 1), IV((int *)j, (size_t)nnz),
+                                        NV((double *)x, (size_t)nnz), IV((int *)yi, (size_t)ny),
+                                        IV((int *)yv_float_bits, (size_t)ny), nthreads));
+    maybe_copy<double>(out);
+    return 0;
+}
+
+} /* extern "C" */

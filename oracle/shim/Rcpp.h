@@ -12,6 +12,10 @@
  *   - IntegerVector and LogicalVector are DISTINCT types (std::is_same dispatch at
  *     src/matmul.cpp:406-411 depends on it);
  *   - matrices are column-major.
+ * For src/misc.cpp and src/operators.cpp (sort / validity checks / elementwise products) the
+ * subset is a little wider: iterator-range constructors, Rcpp::String, Rcpp::stop, LogicalMatrix, List["name"]
+ * assignment and lookup, ISNAN/ISNA/R_FINITE/R_NaN/R_pow (R_pow is std::pow here: only there so that the whole file
+ * links; no checked function of the oracle goes through it).
  * Added for the ctypes driver: non-owning (pointer, size) constructors that borrow caller memory,
  * exactly like Rcpp borrows the SEXP payload.
  */
@@ -23,6 +27,10 @@
 #include <cstring>
 #include <climits>
 #include <cmath>
+#include <cfloat>
+#include <limits>
+#include <stdexcept>
+#include <iterator>
 #include <memory>
 #include <vector>
 #include <string>
@@ -54,6 +62,29 @@ static inline double mx_shim_na_real()
 #ifndef NA_REAL
 #define NA_REAL (mx_shim_na_real())
 #endif
+static inline bool mx_shim_isna(double x)
+{
+    uint64_t bits;
+    std::memcpy(&bits, &x, sizeof(bits));
+    return std::isnan(x) && (uint32_t)bits == 1954u; /* arithmetic.c: R_IsNA */
+}
+#ifndef ISNAN
+#define ISNAN(x) (std::isnan((double)(x)))
+#endif
+#ifndef ISNA
+#define ISNA(x) (mx_shim_isna((double)(x)))
+#endif
+#ifndef R_FINITE
+#define R_FINITE(x) (std::isfinite((double)(x)))
+#endif
+#ifndef R_NaN
+#define R_NaN (std::numeric_limits<double>::quiet_NaN())
+#endif
+#ifndef R_PosInf
+#define R_PosInf (std::numeric_limits<double>::infinity())
+#define R_NegInf (-std::numeric_limits<double>::infinity())
+#endif
+static inline double R_pow(double x, double y) { return std::pow(x, y); }
 
 namespace Rcpp {
 
@@ -74,6 +105,24 @@ public:
     }
     /* non-owning view over caller memory (what Rcpp does with a SEXP) */
     ShimVector(T *borrowed, size_t n) : ptr_(borrowed), n_(n) {}
+    /* Rcpp's copying iterator-range constructor */
+    template <class It, class = typename std::enable_if<!std::is_integral<It>::value>::type,
+              class = typename std::iterator_traits<It>::value_type>
+    ShimVector(It first, It last) : n_((size_t)std::distance(first, last))
+    {
+        own_ = std::shared_ptr<T>(new T[n_ ? n_ : 1](), std::default_delete<T[]>());
+        ptr_ = own_.get();
+        size_t k = 0;
+        for (It it = first; it != last; ++it) ptr_[k++] = (T)*it;
+    }
+    /* Rcpp vectors convert to SEXP implicitly */
+    operator SEXP() const
+    {
+        SEXP s = new mx_shim_sexprec();
+        if (std::is_same<T, double>::value) s->dbls.assign(ptr_, ptr_ + n_);
+        else { s->is_int = true; s->ints.assign(ptr_, ptr_ + n_); }
+        return s;
+    }
     /* from the fake SEXP returned by SafeRcppVector / unwindProtect */
     ShimVector(SEXP s)
     {
@@ -123,6 +172,18 @@ private:
 
 typedef ShimMatrix<double, mx_tag_num> NumericMatrix;
 typedef ShimMatrix<int, mx_tag_int> IntegerMatrix;
+typedef ShimMatrix<int, mx_tag_lgl> LogicalMatrix;
+
+struct String {
+    std::string s;
+    String() {}
+    String(const char *c) : s(c) {}
+    String(const std::string &c) : s(c) {}
+};
+
+template <class... Args>
+[[noreturn]] static inline void stop(const char *msg, Args...) { throw std::runtime_error(msg); }
+static inline void checkUserInterrupt() {}
 
 /* ---- List::create(_["name"] = value, ...) ---- */
 struct ListEntry {
@@ -131,6 +192,7 @@ struct ListEntry {
     void *data = nullptr;
     size_t size = 0;
     bool is_int = false;
+    std::string str; /* for Rcpp::String values */
 };
 
 template <class V>
@@ -150,9 +212,34 @@ struct NamedPlaceholder {
 };
 static const NamedPlaceholder _ = NamedPlaceholder();
 
+class List;
+struct ListProxy {
+    List *list;
+    std::string name;
+    template <class T, class Tag> ListProxy &operator=(const ShimVector<T, Tag> &v);
+    ListProxy &operator=(SEXP s);
+    void *data_ptr() const;
+};
+
 class List {
 public:
     std::vector<ListEntry> entries;
+    ListProxy operator[](const char *name) { return ListProxy{this, name}; }
+    ListEntry *find(const std::string &name)
+    {
+        for (auto &e : entries) if (e.name == name) return &e;
+        return nullptr;
+    }
+    template <class T, class Tag>
+    void set(const std::string &name, const ShimVector<T, Tag> &v)
+    {
+        ListEntry *e = find(name);
+        if (!e) { entries.push_back(ListEntry()); e = &entries.back(); e->name = name; }
+        e->keep = v.keepalive();
+        e->data = (void *)v.data_ptr();
+        e->size = (size_t)v.size();
+        e->is_int = std::is_same<T, int>::value;
+    }
     template <class... Args>
     static List create(const Args &...args)
     {
@@ -162,18 +249,39 @@ public:
         return out;
     }
 private:
+    template <class V>
+    void push(const NamedValue<V> &nv) { store(nv.name, nv.value); }
     template <class T, class Tag>
-    void push(const NamedValue<ShimVector<T, Tag>> &nv)
+    void store(const char *name, const ShimVector<T, Tag> &v) { set(name, v); }
+    void store(const char *name, const String &v)
     {
         ListEntry e;
-        e.name = nv.name;
-        e.keep = nv.value.keepalive();
-        e.data = (void *)nv.value.data_ptr();
-        e.size = (size_t)nv.value.size();
-        e.is_int = std::is_same<T, int>::value;
+        e.name = name;
+        e.str = v.s;
+        entries.push_back(e);
+    }
+    template <class V, class = typename std::enable_if<std::is_arithmetic<V>::value>::type>
+    void store(const char *name, V)
+    {
+        ListEntry e;
+        e.name = name;
         entries.push_back(e);
     }
 };
+
+template <class T, class Tag>
+inline ListProxy &ListProxy::operator=(const ShimVector<T, Tag> &v) { list->set(name, v); return *this; }
+inline ListProxy &ListProxy::operator=(SEXP s)
+{
+    if (s->is_int) list->set(name, IntegerVector(s));
+    else list->set(name, NumericVector(s));
+    return *this;
+}
+inline void *ListProxy::data_ptr() const
+{
+    ListEntry *e = list->find(name);
+    return e ? e->data : nullptr;
+}
 
 template <class Fn>
 SEXP unwindProtect(Fn fn, void *arg) { return fn(arg); }
