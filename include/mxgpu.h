@@ -122,6 +122,37 @@ int mxg_spmv_csr_svec(int ytype, int m, int K,
                       const int32_t *p, const int32_t *j, const double *x,
                       int n_y, const int32_t *y_idx_base1, const void *y_vals, double *out);
 
+/* ---- the steps either side of a product ---- */
+
+/* Validity of hand-built CSR arrays.  Replaces check_valid_csr_matrix (src/misc.cpp:970-1016, called from
+ * R/utils.R:439-489): *code = 0 when valid, else the ordinal of the FIRST failing check in the reference's order;
+ * mxg_csr_error_string(code) is the reference's message ("Matrix has negative indices." ...).  nnz = length of j. */
+int mxg_check_valid_csr(int m, int ncols, const int32_t *p, const int32_t *j, int64_t nnz, int *code);
+const char *mxg_csr_error_string(int code);
+
+/* *sorted = 1 when the column ids of EVERY row are non-decreasing.  Replaces check_indices_are_unsorted
+ * (src/misc.cpp:161-175; the reference's name is misleading, it returns true for sorted input). */
+int mxg_rows_sorted(int m, const int32_t *p, const int32_t *j, int *sorted);
+
+/* Sort the column ids of every row (and the values with them; x may be NULL) IN PLACE in the caller's arrays.
+ * Replaces sort_sparse_indices<T> (src/misc.cpp:192-252, exports 300-330): rows already non-decreasing are left
+ * alone; repeated ids keep their stored order (the reference's std::sort leaves that unspecified).  A sparse
+ * vector is the one-row case (m = 1, p = {0, n}). */
+int mxg_sort_csr_indices(int m, const int32_t *p, int32_t *j, double *x);
+
+/* values_out[nnz] = x[e] * dense[row(e), j[e]] for a column-major m x K dense matrix of element type `dtype`
+ * (MXG_Y_NUMERIC double, MXG_Y_FLOAT32 float, MXG_Y_INTEGER / MXG_Y_LOGICAL int with INT_MIN = NA -> NA_real_).
+ * Replaces multiply_csr_by_dense_elemwise_{double,float32,int,bool} (src/operators.cpp:239-314): the result keeps
+ * the sparsity pattern of the CSR operand, only the values change.  Bit-exact (one multiply per entry). */
+int mxg_mul_csr_dense(int dtype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
+                      const void *dense, double *values_out);
+
+/* values_out[nnz] = x[e] * dvec[pos(e)] with R's recycling of a dense vector along the column-major position:
+ * pos = row + col * m, taken modulo len when len < m * K.  Replaces the Multiply case of
+ * multiply_csr_by_dvec_no_NAs_numeric (src/operators.cpp:1478, 1501-2178; R/operators.R:236-397). */
+int mxg_mul_csr_dvec(int m, int K, const int32_t *p, const int32_t *j, const double *x,
+                     const double *dvec, size_t len, double *values_out);
+
 /* Deep CSR(m x K) -> CSC conversion, bit-exact stable counting order (rows ascending inside each
  * column, duplicates in stored order).  Replaces the `as(x, "CsparseMatrix")` that
  * R/conversions.R:390-392 delegates to the Matrix package.  p2[K+1], i2[nnz], x2[nnz] are caller
@@ -174,6 +205,16 @@ int mxg_dev_spmv(mxg_csr_t A, int ytype, const void *d_y, void *d_out, void *str
 /* Sparse-vector product on a device-resident handle; d_yidx_base1 / d_yvals / d_out are device pointers. */
 int mxg_dev_spmv_svec(mxg_csr_t A, int ytype, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
                       double *d_out, void *stream);
+
+/* Device-array forms of the f3 / f4 entry points (raw device pointers or a handle; they synchronise `stream` where
+ * a result is returned to the host).  The device sort is OUT of place: d_j_out / d_x_out must not alias the inputs;
+ * *rows_sorted (may be NULL) receives how many rows needed sorting. */
+int mxg_dev_check_valid_csr(int m, int ncols, const int32_t *d_p, const int32_t *d_j, int64_t nnz, int *code, void *stream);
+int mxg_dev_rows_sorted(int m, const int32_t *d_p, const int32_t *d_j, int *sorted, void *stream);
+int mxg_dev_sort_csr_indices(int m, const int32_t *d_p, const int32_t *d_j, const double *d_x,
+                             int32_t *d_j_out, double *d_x_out, int *rows_sorted, void *stream);
+int mxg_dev_mul_csr_dense(mxg_csr_t A, int dtype, const void *d_dense, double *d_values_out, void *stream);
+int mxg_dev_mul_csr_dvec(mxg_csr_t A, const double *d_dvec, size_t len, double *d_values_out, void *stream);
 
 /* Multi-GPU form of the two products (north_star subsystem 4; no counterpart in the reference, which is one
  * process on shared memory: the OpenMP row loop of src/matmul.cpp:132-136 is the decomposition kept here).

@@ -38,6 +38,16 @@ _SIGNATURES = {
     "mxg_spmv_csr": [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "mxg_spmv_csr_svec": [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "mxg_dev_spmv_svec": [_vp, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mxg_check_valid_csr": [_i32, _i32, _vp, _vp, _i64, C.POINTER(C.c_int)],
+    "mxg_rows_sorted": [_i32, _vp, _vp, C.POINTER(C.c_int)],
+    "mxg_sort_csr_indices": [_i32, _vp, _vp, _vp],
+    "mxg_mul_csr_dense": [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mxg_mul_csr_dvec": [_i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp],
+    "mxg_dev_check_valid_csr": [_i32, _i32, _vp, _vp, _i64, C.POINTER(C.c_int), _vp],
+    "mxg_dev_rows_sorted": [_i32, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mxg_dev_sort_csr_indices": [_i32, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), _vp],
+    "mxg_dev_mul_csr_dense": [_vp, _i32, _vp, _vp, _vp],
+    "mxg_dev_mul_csr_dvec": [_vp, _vp, _sz, _vp, _vp],
     "mxg_csr2csc": [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "mxg_spmm_csrT_dense": [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp, _sz],
     "mxg_csr_upload": [_i32, _i32, _vp, _vp, _vp, _i32, C.POINTER(_vp)],
@@ -62,7 +72,7 @@ _SIGNATURES = {
     "mxg_row_partition": [_i32, _vp, _i32, _vp],
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],
 }
-_RESTYPES = {"mxg_last_error": C.c_char_p, "mxg_launch_count": C.c_ulonglong}
+_RESTYPES = {"mxg_last_error": C.c_char_p, "mxg_launch_count": C.c_ulonglong, "mxg_csr_error_string": C.c_char_p}
 
 _lib = None
 
@@ -85,6 +95,8 @@ def load() -> C.CDLL:
     lib.mxg_last_error.restype = C.c_char_p
     lib.mxg_launch_count.argtypes = []
     lib.mxg_launch_count.restype = C.c_ulonglong
+    lib.mxg_csr_error_string.argtypes = [C.c_int]
+    lib.mxg_csr_error_string.restype = C.c_char_p
     _lib = lib
     return lib
 

@@ -729,6 +729,204 @@ int mxg_spmv_csr_svec(int ytype, int m, int K, const int32_t *p, const int32_t *
     return rc;
 }
 
+// ---- validity, sorting, elementwise products -------------------------------------------
+
+const char *mxg_csr_error_string(int code)
+{
+    switch (code) { // src/misc.cpp:977-1013, verbatim messages of the reference
+    case 0: return "";
+    case 1: return "Matrix has negative indices.";
+    case 2: return "Matrix has invalid column indices.";
+    case 3: return "Matrix has indices with missing values.";
+    case 4: return "Matrix has missing values in the index pointer.";
+    case 5: return "Matrix index pointer is not monotonicaly increasing.";
+    default: return "unknown";
+    }
+}
+
+int mxg_dev_check_valid_csr(int m, int ncols, const int32_t *d_p, const int32_t *d_j, int64_t nnz, int *code, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!code || m < 0 || nnz < 0 || !d_p || (nnz > 0 && !d_j)) return fail(MXG_ERR_ARG, "check_valid_csr: bad argument");
+    return dev_check_valid_csr(m, ncols, d_p, d_j, nnz, code, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_rows_sorted(int m, const int32_t *d_p, const int32_t *d_j, int *sorted, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!sorted || m < 0 || !d_p) return fail(MXG_ERR_ARG, "rows_sorted: bad argument");
+    return dev_rows_sorted(m, d_p, d_j, sorted, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_sort_csr_indices(int m, const int32_t *d_p, const int32_t *d_j, const double *d_x, int32_t *d_j_out,
+                             double *d_x_out, int *rows_sorted, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (m < 0) return fail(MXG_ERR_ARG, "sort_csr_indices: negative dimension");
+    return dev_sort_csr_indices(m, d_p, d_j, d_x, d_j_out, d_x_out, rows_sorted, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_mul_csr_dense(mxg_csr_t A, int dtype, const void *d_dense, double *d_values_out, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A) return fail(MXG_ERR_ARG, "dev_mul_csr_dense: NULL handle");
+    return launch_mul_csr_dense(A, dtype, d_dense, d_values_out, static_cast<cudaStream_t>(stream));
+}
+
+int mxg_dev_mul_csr_dvec(mxg_csr_t A, const double *d_dvec, size_t len, double *d_values_out, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A) return fail(MXG_ERR_ARG, "dev_mul_csr_dvec: NULL handle");
+    return launch_mul_csr_dvec(A, d_dvec, len, d_values_out, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+// small RAII holder for the stream-ordered temporaries of the host-buffer entry points below
+struct DevTemps {
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit DevTemps(cudaStream_t stream) : s(stream) {}
+    int alloc(void **out, size_t bytes)
+    {
+        *out = nullptr;
+        MXG_CUDA_TRY(cudaMallocAsync(out, std::max<size_t>(bytes, 16), s));
+        ptrs.push_back(*out);
+        return MXG_OK;
+    }
+    int upload(void **out, const void *src, size_t bytes)
+    {
+        MXG_TRY(alloc(out, bytes));
+        if (bytes) MXG_CUDA_TRY(cudaMemcpyAsync(*out, src, bytes, cudaMemcpyHostToDevice, s));
+        return MXG_OK;
+    }
+    ~DevTemps()
+    {
+        for (void *q : ptrs) cudaFreeAsync(q, s);
+        cudaStreamSynchronize(s);
+    }
+};
+} // namespace
+
+int mxg_check_valid_csr(int m, int ncols, const int32_t *p, const int32_t *j, int64_t nnz, int *code)
+{
+    if (!code || m < 0 || nnz < 0 || !p || (nnz > 0 && !j)) return fail(MXG_ERR_ARG, "check_valid_csr: bad argument");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    DevTemps t(st->stream);
+    void *d_p, *d_j;
+    MXG_TRY(t.upload(&d_p, p, sizeof(int32_t) * ((size_t)m + 1)));
+    MXG_TRY(t.upload(&d_j, j, sizeof(int32_t) * (size_t)nnz));
+    return dev_check_valid_csr(m, ncols, static_cast<int32_t *>(d_p), static_cast<int32_t *>(d_j), nnz, code, st->stream);
+}
+
+int mxg_rows_sorted(int m, const int32_t *p, const int32_t *j, int *sorted)
+{
+    if (!sorted || m < 0 || !p) return fail(MXG_ERR_ARG, "rows_sorted: bad argument");
+    *sorted = 1;
+    const int64_t nnz = (int64_t)p[m] - p[0];
+    if (m == 0 || nnz <= 0) return MXG_OK;
+    if (!j) return fail(MXG_ERR_ARG, "rows_sorted: indices is NULL");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    DevTemps t(st->stream);
+    void *d_p, *d_j;
+    MXG_TRY(t.upload(&d_p, p, sizeof(int32_t) * ((size_t)m + 1)));
+    MXG_TRY(t.upload(&d_j, j, sizeof(int32_t) * (size_t)p[m])); // offsets are absolute: keep j's origin
+    return dev_rows_sorted(m, static_cast<int32_t *>(d_p), static_cast<int32_t *>(d_j), sorted, st->stream);
+}
+
+int mxg_sort_csr_indices(int m, const int32_t *p, int32_t *j, double *x)
+{
+    if (m < 0 || !p) return fail(MXG_ERR_ARG, "sort_csr_indices: bad argument");
+    if (m == 0 || p[m] <= 0) return MXG_OK;
+    if (!j) return fail(MXG_ERR_ARG, "sort_csr_indices: indices is NULL");
+    for (int r = 0; r < m; r++)
+        if (p[r] < 0 || p[r] > p[r + 1]) return fail(MXG_ERR_INDEX, "sort_csr_indices: indptr is negative or decreasing");
+    const size_t n = (size_t)p[m];
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    cudaStream_t s = st->stream;
+    DevTemps t(s);
+    void *d_p, *d_j, *d_x = nullptr, *d_j2, *d_x2 = nullptr;
+    MXG_TRY(t.upload(&d_p, p, sizeof(int32_t) * ((size_t)m + 1)));
+    MXG_TRY(t.upload(&d_j, j, sizeof(int32_t) * n));
+    MXG_TRY(t.alloc(&d_j2, sizeof(int32_t) * n));
+    if (x) {
+        MXG_TRY(t.upload(&d_x, x, sizeof(double) * n));
+        MXG_TRY(t.alloc(&d_x2, sizeof(double) * n));
+    }
+    int changed = 0;
+    MXG_TRY(dev_sort_csr_indices(m, static_cast<int32_t *>(d_p), static_cast<int32_t *>(d_j), static_cast<double *>(d_x),
+                                 static_cast<int32_t *>(d_j2), static_cast<double *>(d_x2), &changed, s));
+    if (changed > 0) { // rows before p[0] (none for an R matrix) are not touched
+        const size_t off = (size_t)p[0];
+        MXG_CUDA_TRY(cudaMemcpyAsync(j + off, static_cast<int32_t *>(d_j2) + off, sizeof(int32_t) * (n - off), cudaMemcpyDeviceToHost, s));
+        if (x) MXG_CUDA_TRY(cudaMemcpyAsync(x + off, static_cast<double *>(d_x2) + off, sizeof(double) * (n - off), cudaMemcpyDeviceToHost, s));
+        MXG_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return MXG_OK;
+}
+
+int mxg_mul_csr_dense(int dtype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *dense,
+                      double *values_out)
+{
+    if (dtype < MXG_Y_NUMERIC || dtype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "mul_csr_dense: bad element type %d", dtype);
+    if (m < 0 || K < 0 || !p) return fail(MXG_ERR_ARG, "mul_csr_dense: bad argument");
+    const int64_t nnz = (int64_t)p[m] - p[0];
+    if (m == 0 || nnz <= 0) return MXG_OK;
+    if (!dense || !values_out) return fail(MXG_ERR_ARG, "mul_csr_dense: NULL operand");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *A = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, MXG_KEEP_F64, st->stream, &A));
+    int rc;
+    {
+        DevTemps t(st->stream);
+        void *d_dense, *d_out;
+        const size_t es = dtype == MXG_Y_NUMERIC ? 8 : 4;
+        auto body = [&]() -> int {
+            MXG_TRY(t.upload(&d_dense, dense, es * (size_t)m * (size_t)K));
+            MXG_TRY(t.alloc(&d_out, sizeof(double) * (size_t)nnz));
+            MXG_TRY(launch_mul_csr_dense(A, dtype, d_dense, static_cast<double *>(d_out), st->stream));
+            MXG_CUDA_TRY(cudaMemcpyAsync(values_out, d_out, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st->stream));
+            MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
+            return MXG_OK;
+        };
+        rc = body();
+    }
+    free_handle(A);
+    return rc;
+}
+
+int mxg_mul_csr_dvec(int m, int K, const int32_t *p, const int32_t *j, const double *x, const double *dvec, size_t len,
+                     double *values_out)
+{
+    if (m < 0 || K < 0 || !p) return fail(MXG_ERR_ARG, "mul_csr_dvec: bad argument");
+    const int64_t nnz = (int64_t)p[m] - p[0];
+    if (m == 0 || nnz <= 0) return MXG_OK;
+    if (!dvec || !values_out || len == 0) return fail(MXG_ERR_ARG, "mul_csr_dvec: NULL or empty operand");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    mxg_csr_s *A = nullptr;
+    MXG_TRY(upload_csr(m, K, p, j, x, MXG_KEEP_F64, st->stream, &A));
+    int rc;
+    {
+        DevTemps t(st->stream);
+        void *d_vec, *d_out;
+        auto body = [&]() -> int {
+            MXG_TRY(t.upload(&d_vec, dvec, sizeof(double) * len));
+            MXG_TRY(t.alloc(&d_out, sizeof(double) * (size_t)nnz));
+            MXG_TRY(launch_mul_csr_dvec(A, static_cast<double *>(d_vec), len, static_cast<double *>(d_out), st->stream));
+            MXG_CUDA_TRY(cudaMemcpyAsync(values_out, d_out, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st->stream));
+            MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
+            return MXG_OK;
+        };
+        rc = body();
+    }
+    free_handle(A);
+    return rc;
+}
+
 int mxg_csr2csc(int m, int K, const int32_t *p, const int32_t *j, const double *x, int32_t *p2, int32_t *i2, double *x2)
 {
     if (!p2) return fail(MXG_ERR_ARG, "p2 is NULL");

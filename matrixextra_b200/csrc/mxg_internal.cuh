@@ -141,6 +141,13 @@ int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst,
 // CSR x sparse vector (indices base 1, K = columns covered by the presence bitmap), double result
 int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
                      double *d_out, cudaStream_t stream);
+// rowops.cu
+int launch_mul_csr_dense(const mxg_csr_s *A, int dtype, const void *d_dense, double *d_out, cudaStream_t stream);
+int launch_mul_csr_dvec(const mxg_csr_s *A, const double *d_dvec, size_t len, double *d_out, cudaStream_t stream);
+int dev_check_valid_csr(int m, int ncols, const int32_t *d_p, const int32_t *d_j, int64_t nnz, int *code, cudaStream_t stream);
+int dev_rows_sorted(int m, const int32_t *d_p, const int32_t *d_j, int *sorted, cudaStream_t stream);
+int dev_sort_csr_indices(int m, const int32_t *d_p, const int32_t *d_j, const double *d_x, int32_t *d_j_out, double *d_x_out,
+                         int *rows_sorted, cudaStream_t stream);
 // transpose.cu
 int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *d_src, size_t ld_src,
                            void *d_dst, size_t ld_dst, cudaStream_t stream);

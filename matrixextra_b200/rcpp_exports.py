@@ -161,6 +161,98 @@ def matmul_csr_svec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_indices
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_FLOAT32, np.float32, ncols, out)
 
 
+# ---- index sorting and validity checks (src/misc.cpp:161-330, 970-1016) -----------
+
+def sort_sparse_indices_numeric(indptr, indices, values):
+    """Sorts ``indices`` / ``values`` IN PLACE row by row, like the reference (src/misc.cpp:300-313): the arrays
+    must be writeable contiguous int32 / float64 (as R's are)."""
+    p = np.ascontiguousarray(indptr, dtype=np.int32)
+    for a, dt in ((indices, np.int32), (values, np.float64)):
+        if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.flags.writeable):
+            raise ValueError("sort_sparse_indices_numeric sorts in place: pass writeable contiguous int32 / float64 arrays")
+    _lib.call("mxg_sort_csr_indices", p.size - 1, _vp(p), _vp(indices), _vp(values))
+
+
+def sort_sparse_indices_binary(indptr, indices):
+    """Pattern overload (src/misc.cpp:230-252, export 332-343)."""
+    p = np.ascontiguousarray(indptr, dtype=np.int32)
+    if not (isinstance(indices, np.ndarray) and indices.dtype == np.int32 and indices.flags.c_contiguous and indices.flags.writeable):
+        raise ValueError("sort_sparse_indices_binary sorts in place: pass a writeable contiguous int32 array")
+    _lib.call("mxg_sort_csr_indices", p.size - 1, _vp(p), _vp(indices), None)
+
+
+def check_indices_are_unsorted(indptr, indices) -> bool:
+    """True when every row is sorted — the reference's (misleading) name and meaning, src/misc.cpp:161-175."""
+    p = np.ascontiguousarray(indptr, dtype=np.int32)
+    j = np.ascontiguousarray(indices, dtype=np.int32)
+    flag = C.c_int(1)
+    _lib.call("mxg_rows_sorted", p.size - 1, _vp(p), _vp(j), C.byref(flag))
+    return bool(flag.value)
+
+
+def check_valid_csr_matrix(indptr, indices, nrows, ncols) -> dict:
+    """``{}`` for a valid matrix, else ``{"err": <the reference's message>}`` (src/misc.cpp:970-1016)."""
+    p = np.ascontiguousarray(indptr, dtype=np.int32)
+    j = np.ascontiguousarray(indices, dtype=np.int32)
+    if p.size != int(nrows) + 1:
+        raise ValueError("indptr must have nrows + 1 entries")
+    code = C.c_int(0)
+    _lib.call("mxg_check_valid_csr", int(nrows), int(ncols), _vp(p), _vp(j), int(j.size), C.byref(code))
+    if code.value == 0:
+        return {}
+    return {"err": _lib.load().mxg_csr_error_string(code.value).decode()}
+
+
+# ---- elementwise CSR * dense (src/operators.cpp:239-314, 2147-2178; SURVEY.md §8 f4) ------------------
+
+def _mul_dense(indptr, indices, values, dense_mat, dtype, np_t):
+    p, j, x = _csr(indptr, indices, values)
+    m = p.size - 1
+    d = np.asarray(dense_mat, dtype=np_t)
+    if d.ndim == 2:
+        if d.shape[0] != m:
+            raise ValueError("dense matrix must have as many rows as the CSR matrix")
+        K = d.shape[1]
+        d = np.asfortranarray(d)
+    else:  # the reference receives the matrix as a flat column-major vector
+        if m == 0 or d.size % m:
+            raise ValueError("dense_mat length is not a multiple of the number of rows")
+        K = d.size // m
+        d = np.ascontiguousarray(d)
+    out = np.empty(j.size, dtype=np.float64)
+    _lib.call("mxg_mul_csr_dense", dtype, m, int(K), _vp(p), _vp(j), _vp(x), _vp(d), _vp(out))
+    return out
+
+
+def multiply_csr_by_dense_elemwise_double(indptr, indices, values, dense_mat):
+    return _mul_dense(indptr, indices, values, dense_mat, MXG_Y_NUMERIC, np.float64)
+
+
+def multiply_csr_by_dense_elemwise_float32(indptr, indices, values, dense_mat):
+    return _mul_dense(indptr, indices, values, dense_mat, MXG_Y_FLOAT32, np.float32)
+
+
+def multiply_csr_by_dense_elemwise_int(indptr, indices, values, dense_mat):
+    return _mul_dense(indptr, indices, values, dense_mat, MXG_Y_INTEGER, np.int32)
+
+
+def multiply_csr_by_dense_elemwise_bool(indptr, indices, values, dense_mat):
+    return _mul_dense(indptr, indices, values, dense_mat, MXG_Y_LOGICAL, np.int32)
+
+
+def multiply_csr_by_dvec_no_NAs_numeric(indptr, indices, values, dvec, ncols, multiply=True, powerto=False, divide=False,
+                                        divrest=False, intdiv=False, X_is_LHS=True):
+    """Only the Multiply operation is on the scoped path; the other operators of the reference's template
+    (src/operators.cpp:1501-2143) stay on its C++."""
+    if not multiply or powerto or divide or divrest or intdiv:
+        raise NotImplementedError("only multiply=TRUE is implemented on the device (SURVEY.md §8 f4)")
+    p, j, x = _csr(indptr, indices, values)
+    d = np.ascontiguousarray(dvec, dtype=np.float64)
+    out = np.empty(j.size, dtype=np.float64)
+    _lib.call("mxg_mul_csr_dvec", p.size - 1, int(ncols), _vp(p), _vp(j), _vp(x), _vp(d), int(d.size), _vp(out))
+    return out
+
+
 # ---- additions beyond the reference's exports (SURVEY.md §3.4, §8 a6) -----------------------------
 
 def csr_to_csc(m, K, indptr, indices, values):
