@@ -406,7 +406,7 @@ def run_ours(args):
         if op == "spmv":
             d_h = pin(dense.cpu().numpy())
             o_h = pinned_out((m,), torch.float64)
-            call = lambda out=o_h: rx.matmul_csr_dvec_numeric(p_h, j_h, x_h, d_h, 1, out=out)  # noqa: E731
+            call = lambda out=o_h: rx.matmul_csr_dvec_numeric(p_h, j_h, x_h, d_h, 0, out=out)  # noqa: E731
             h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
             d2h = 8 * m
         elif op == "crossprod":
@@ -421,10 +421,10 @@ def run_ours(args):
                   ("csr_dense", True): rx.tcrossprod_csr_dense_float32, ("csr_dense", False): rx.tcrossprod_csr_dense_numeric}[(op, f32)]
             if op == "dense_tcsr":
                 o_h = pinned_out((n, m), tdt)
-                call = lambda out=o_h: fn(d_h, p_h, j_h, x_h, 1, K, out=out)  # noqa: E731
+                call = lambda out=o_h: fn(d_h, p_h, j_h, x_h, 0, K, out=out)  # noqa: E731
             else:
                 o_h = pinned_out((m, n), tdt)
-                call = lambda out=o_h: fn(p_h, j_h, x_h, d_h, 1, out=out)  # noqa: E731
+                call = lambda out=o_h: fn(p_h, j_h, x_h, d_h, 0, out=out)  # noqa: E731
             h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
             d2h = s * m * n
         call()  # warm-up (allocator pools)
@@ -446,12 +446,35 @@ def run_ours(args):
         t_e2e, res = time_calls(call, k_e2e)
         # same call the way R makes it: the result is a freshly allocated (pageable, untouched) matrix
         t_fresh, res = time_calls(lambda: call(out=None), 2)
+        # bytes that cross PCIe: a float32 product narrows the float64 values on the host (hoststage.cu)
+        host_narrow = f32 and op != "crossprod" and _lib.get_option("host_narrow") != 0 and _lib.get_option("pipeline") != 0
+        if host_narrow:
+            h2d -= x_h.nbytes // 2
         e2e = {"value": 2.0 * nnz_all * n / t_e2e / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "ms_per_step": t_e2e * 1e3,
                "entry_point": "level-1 C ABI (streamed row chunks) via the Rcpp-export mirror; pinned host inputs, "
-                              "result into a page-locked host buffer",
+                              "result into a page-locked host buffer"
+                              + ("; float64 values narrowed to float32 by the library's host threads before the copy "
+                                 "(h2d bytes counted after narrowing)" if host_narrow else ""),
+               "host_threads": min(os.cpu_count() or 4, 16),
                "fresh_pageable_result": {"value": 2.0 * nnz_all * n / t_fresh / 1e9, "ms_per_step": t_fresh * 1e3,
                                          "note": "same call returning a newly allocated pageable matrix, as the Rcpp glue does"}}
+        if op not in ("crossprod",) and world == 1:
+            # everything pageable, as in an R session: operands are ordinary (non page-locked) arrays, the result is new
+            pg = lambda a: np.array(a, copy=True, order="K")  # noqa: E731
+            p_g, j_g, x_g, d_g = pg(p_h), pg(j_h), pg(x_h), pg(d_h)
+            if op == "spmv":
+                call_pg = lambda: rx.matmul_csr_dvec_numeric(p_g, j_g, x_g, d_g, 0)  # noqa: E731
+            elif op == "dense_tcsr":
+                call_pg = lambda: fn(d_g, p_g, j_g, x_g, 0, K)  # noqa: E731
+            else:
+                call_pg = lambda: fn(p_g, j_g, x_g, d_g, 0)  # noqa: E731
+            call_pg()
+            t_pg, res = time_calls(call_pg, 3)
+            e2e["all_pageable"] = {"value": 2.0 * nnz_all * n / t_pg / 1e9, "ms_per_step": t_pg * 1e3,
+                                   "note": "operands AND result in pageable memory (an R session): bounced through the "
+                                           "library's page-locked ring by its host threads"}
+            del p_g, j_g, x_g, d_g
         del res
         if rank == 0 and world == 1 and not args.skip_cpu:
             cpu = cpu_baseline(wl, p_h, j_h, x_h)

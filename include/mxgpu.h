@@ -252,6 +252,15 @@ int mxg_dev_transpose_dense(int elem_size, size_t rows, size_t cols,
  * row_starts[parts+1] is filled with 0 = r_0 <= r_1 <= ... <= r_parts = m.  Host indptr. */
 int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
 
+/* ============ host-side staging helpers (no GPU involved) ============
+ * The streamed level-1 calls run these on the library's pool of host threads (option "host_threads", what the
+ * reference's `nthreads` argument of src/matmul.cpp:221-483 now controls; 0 = all logical CPUs up to 16).
+ * mxg_host_narrow: dst[i] = (float)src[i], round-to-nearest-even — the reference's per-entry cast
+ * (src/matmul.cpp:53-57) done once, before the values cross PCIe.  mxg_host_copy_2d: `height` lines of `width`
+ * bytes between pitched host buffers (how pageable R memory enters and leaves the page-locked staging arena). */
+int mxg_host_narrow(const double *src, float *dst, size_t n);
+int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height);
+
 /* ============ synthetic inputs for bench.py / tests (device-side, counter-based RNG) ============
  * Power-law row lengths, stratified sorted unique columns; see DESIGN.md "Synthetic inputs". */
 int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed,

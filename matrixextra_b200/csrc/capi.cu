@@ -291,6 +291,10 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_panel_mb")) return &o.spmm_panel_mb;
     if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
+    if (!strcmp(name, "host_threads")) return &o.host_threads;
+    if (!strcmp(name, "host_narrow")) return &o.host_narrow;
+    if (!strcmp(name, "host_stage")) return &o.host_stage;
+    if (!strcmp(name, "pipe_slots")) return &o.pipe_slots;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
     if (!strcmp(name, "spmv_tex")) return &o.spmv_tex;
     if (!strcmp(name, "svec_smem")) return &o.svec_smem;
@@ -318,6 +322,21 @@ int mxg_get_option(const char *name, long *value)
 
 unsigned long long mxg_launch_count(void) { return g_launches.load(); }
 
+int mxg_host_narrow(const double *src, float *dst, size_t n)
+{
+    if (n > 0 && (!src || !dst)) return fail(MXG_ERR_ARG, "host_narrow: NULL buffer");
+    host_narrow_f64_to_f32(src, dst, n);
+    return MXG_OK;
+}
+
+int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height)
+{
+    if (width > 0 && height > 0 && (!src || !dst)) return fail(MXG_ERR_ARG, "host_copy_2d: NULL buffer");
+    if (height > 1 && (dpitch < width || spitch < width)) return fail(MXG_ERR_ARG, "host_copy_2d: pitch < width");
+    host_copy_2d(dst, dpitch, src, spitch, width, height);
+    return MXG_OK;
+}
+
 int mxg_trim(void)
 {
     int dev = 0;
@@ -326,6 +345,7 @@ int mxg_trim(void)
     cudaMemPool_t pool;
     MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
     MXG_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    if (dev >= 0 && dev < 64 && g_dev[dev].ready) MXG_TRY(pinned_arena_release(&g_dev[dev]));
     return MXG_OK;
 }
 

@@ -1,0 +1,228 @@
+// hoststage.cu — host side of the streamed (level-1) products: worker threads + a page-locked staging arena.
+//
+// An Rcpp export (src/matmul.cpp:221-483) is handed R vectors: PAGEABLE memory, float64 values even when the
+// product is float32 (src/matmul.cpp:213-214 narrows per entry), and it returns a freshly allocated R matrix
+// whose pages have never been touched.  cudaMemcpyAsync on such memory is a single-threaded bounce through the
+// driver's own staging buffer (~10 GB/s, and ~4 GB/s into untouched pages), five times slower than the link.
+// So the library brings its own bounce: a grow-only page-locked arena per device, cut into ring slots, and a
+// small pool of host threads (what the reference's `nthreads` argument now controls) that
+//     * narrows float64 values to float32 straight into a slot (bit-identical to the device narrowing and to
+//       the reference's per-entry `(float)values[ix]`: round-to-nearest-even) — a float32 product then moves
+//       8 instead of 12 bytes per stored entry over PCIe,
+//     * copies pageable indices / dense operands into slots,
+//     * copies finished output rows from slots into the caller's matrix, first-touching its pages in parallel.
+// Page-locked caller memory (cudaHostAlloc / cudaHostRegister) is detected and DMA'd directly.
+#include "mxg_internal.cuh"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <emmintrin.h>
+
+namespace mxg {
+
+// ------------------------------------------------------------------------------------------------
+// worker pool: run(ntasks, fn) executes fn(0..ntasks-1) on the calling thread plus the workers
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+class HostPool {
+public:
+    static HostPool &get()
+    {
+        static HostPool *pool = new HostPool; // leaked on purpose: workers may still be parked at process exit
+        return *pool;
+    }
+
+    void run(size_t ntasks, int threads, const std::function<void(size_t)> &fn)
+    {
+        if (ntasks == 0) return;
+        threads = (int)std::min<size_t>((size_t)std::max(threads, 1), ntasks);
+        if (threads <= 1) {
+            for (size_t i = 0; i < ntasks; i++) fn(i);
+            return;
+        }
+        std::lock_guard<std::mutex> serial(run_mu_); // one parallel region at a time
+        ensure(threads - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = &fn;
+            ntasks_ = ntasks;
+            next_.store(0, std::memory_order_relaxed);
+            invited_ = threads - 1;
+            pending_ = threads - 1;
+            generation_++;
+        }
+        cv_work_.notify_all();
+        for (size_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < ntasks;) fn(i);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void ensure(int workers)
+    {
+        while ((int)workers_.size() < workers) {
+            const int id = (int)workers_.size();
+            workers_.emplace_back([this, id] { loop(id); });
+            workers_.back().detach();
+        }
+    }
+
+    void loop(int id)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(size_t)> *job = nullptr;
+            size_t n = 0;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= invited_) continue; // this region runs on fewer threads
+                job = job_;
+                n = ntasks_;
+            }
+            for (size_t i; (i = next_.fetch_add(1, std::memory_order_relaxed)) < n;) (*job)(i);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                pending_--;
+            }
+            cv_done_.notify_one();
+        }
+    }
+
+    std::mutex run_mu_, mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(size_t)> *job_ = nullptr;
+    size_t ntasks_ = 0;
+    std::atomic<size_t> next_{0};
+    int invited_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+void narrow_block(const double *s, float *d, size_t n)
+{
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(d + i) & 15)) {
+        d[i] = (float)s[i];
+        i++;
+    }
+    for (; i + 4 <= n; i += 4) { // cvtpd2ps rounds by MXCSR: nearest-even, like the cast
+        const __m128 lo = _mm_cvtpd_ps(_mm_loadu_pd(s + i));
+        const __m128 hi = _mm_cvtpd_ps(_mm_loadu_pd(s + i + 2));
+        _mm_stream_ps(d + i, _mm_movelh_ps(lo, hi));
+    }
+    for (; i < n; i++) d[i] = (float)s[i];
+    _mm_sfence();
+}
+
+} // namespace
+
+int host_threads()
+{
+    long t = options().host_threads;
+    if (t <= 0) {
+        t = (long)std::thread::hardware_concurrency();
+        if (t <= 0) t = 4;
+        t = std::min<long>(t, 16);
+    }
+    return (int)std::min<long>(t, 64);
+}
+
+void host_narrow_f64_to_f32(const double *src, float *dst, size_t n)
+{
+    const size_t grain = (size_t)1 << 17;
+    HostPool::get().run((n + grain - 1) / grain, host_threads(), [&](size_t t) {
+        const size_t a = t * grain, b = std::min(n, a + grain);
+        narrow_block(src + a, dst + a, b - a);
+    });
+}
+
+void host_copy(void *dst, const void *src, size_t bytes)
+{
+    const size_t grain = (size_t)1 << 20;
+    HostPool::get().run((bytes + grain - 1) / grain, host_threads(), [&](size_t t) {
+        const size_t a = t * grain, b = std::min(bytes, a + grain);
+        memcpy(static_cast<char *>(dst) + a, static_cast<const char *>(src) + a, b - a);
+    });
+}
+
+void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height)
+{
+    if (width == 0 || height == 0) return;
+    if (dpitch == width && spitch == width) {
+        host_copy(dst, src, width * height);
+        return;
+    }
+    // tasks of about 1 MiB: several short lines, or a slice of a long one
+    const size_t target = (size_t)1 << 20;
+    if (width >= target) {
+        const size_t per_line = (width + target - 1) / target;
+        HostPool::get().run(height * per_line, host_threads(), [&](size_t t) {
+            const size_t line = t / per_line, a = (t % per_line) * target, b = std::min(width, a + target);
+            memcpy(static_cast<char *>(dst) + line * dpitch + a, static_cast<const char *>(src) + line * spitch + a, b - a);
+        });
+    } else {
+        const size_t lines = std::max<size_t>(1, target / width);
+        HostPool::get().run((height + lines - 1) / lines, host_threads(), [&](size_t t) {
+            const size_t l0 = t * lines, l1 = std::min(height, l0 + lines);
+            for (size_t l = l0; l < l1; l++)
+                memcpy(static_cast<char *>(dst) + l * dpitch, static_cast<const char *>(src) + l * spitch, width);
+        });
+    }
+}
+
+// true when the range can be DMA'd directly: page-locked by CUDA (cudaHostAlloc / cudaHostRegister) or managed
+bool host_is_pinned(const void *ptr)
+{
+    if (!ptr) return true;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+int pinned_arena(DeviceState *st, size_t bytes, char **base)
+{
+    if (bytes > st->pin_bytes) {
+        if (st->pin_base) {
+            MXG_CUDA_TRY(cudaFreeHost(st->pin_base));
+            st->pin_base = nullptr;
+            st->pin_bytes = 0;
+        }
+        const size_t want = (bytes + ((size_t)1 << 22) - 1) & ~(((size_t)1 << 22) - 1);
+        MXG_CUDA_TRY(cudaHostAlloc(&st->pin_base, want, cudaHostAllocDefault));
+        st->pin_bytes = want;
+        // touch every page now, in parallel: the first DMA must not pay for it
+        char *b = static_cast<char *>(st->pin_base);
+        const size_t grain = (size_t)1 << 21;
+        HostPool::get().run((want + grain - 1) / grain, host_threads(), [&](size_t t) {
+            const size_t a = t * grain, e = std::min(want, a + grain);
+            memset(b + a, 0, e - a);
+        });
+    }
+    *base = static_cast<char *>(st->pin_base);
+    return MXG_OK;
+}
+
+int pinned_arena_release(DeviceState *st)
+{
+    if (st->pin_base) {
+        MXG_CUDA_TRY(cudaFreeHost(st->pin_base));
+        st->pin_base = nullptr;
+        st->pin_bytes = 0;
+    }
+    return MXG_OK;
+}
+
+} // namespace mxg

@@ -56,6 +56,10 @@ struct Options {
     long h2d_chunk_mb = 64;   // staging chunk of the value narrowing in mxg_csr_upload
     long pipe_chunk_nnz = 0;  // stored entries (and rows) per chunk of the streamed path; 0 = auto (nnz/16, >= 1 Mi)
     long pipeline = 1;        // level-1 products: 1 = streamed row chunks (pipeline.cu), 0 = upload-all-then-compute
+    long host_threads = 0;    // host threads of the staging engine (hoststage.cu); 0 = auto (all logical CPUs, <= 16)
+    long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry)
+    long host_stage = 1;      // bounce pageable caller memory through the page-locked arena with the host threads
+    long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
 };
 Options &options();
 
@@ -109,6 +113,9 @@ struct DeviceState {
     cudaStream_t stream = nullptr; // kernels (and everything of the non-pipelined calls)
     cudaStream_t h2d = nullptr;
     cudaStream_t d2h = nullptr;
+    // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
+    void *pin_base = nullptr;
+    size_t pin_bytes = 0;
 };
 int current_state(DeviceState **out);
 
@@ -118,6 +125,15 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
 int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
                   const void *y, void *out);
 int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream);
+
+// hoststage.cu: worker threads + page-locked arena for pageable caller memory and host-side narrowing
+int host_threads();
+void host_narrow_f64_to_f32(const double *src, float *dst, size_t n);
+void host_copy(void *dst, const void *src, size_t bytes);
+void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height);
+bool host_is_pinned(const void *ptr);
+int pinned_arena(DeviceState *st, size_t bytes, char **base);
+int pinned_arena_release(DeviceState *st);
 
 // layout.cu: device-side completion barrier between the GPUs of a box (bcast products)
 int launch_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, cudaStream_t stream);

@@ -15,14 +15,44 @@
 // copies are in flight, which removes every mid-pipeline device->host synchronisation; column ids are
 // validated on the device per chunk and a device flag makes the product kernels of that and all later
 // chunks return immediately (no out-of-range gather ever executes); the flag is read back once at the end.
+//
+// Host side (hoststage.cu): R hands the glue PAGEABLE vectors and float64 values.  Pageable operands are
+// bounced through ring slots of a page-locked arena by a pool of host threads (parallel memcpy in, parallel
+// first-touch copy out) instead of the driver's single-threaded bounce, and for float32 products the values
+// are narrowed by those threads straight into the slot, so 8 instead of 12 bytes per entry cross PCIe.
+// Caller memory that is already page-locked is DMA'd in place.
 #include "mxg_internal.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace mxg {
 namespace {
+
+// MXG_TRACE=1: host-side timeline of a streamed call on stderr (development aid, off by default)
+struct Trace {
+    bool on = false;
+    std::chrono::steady_clock::time_point t0;
+    double wait_ms = 0, fill_ms = 0, drain_wait_ms = 0, drain_ms = 0, plan_ms = 0, finish_ms = 0;
+    Trace()
+    {
+        const char *e = getenv("MXG_TRACE");
+        on = e && *e && *e != '0';
+        t0 = std::chrono::steady_clock::now();
+    }
+    double now() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    void report(const char *what, int chunks) const
+    {
+        if (on)
+            fprintf(stderr, "[mxg trace] %s: %d chunks, total %.2f ms | plan %.2f | slot waits %.2f | host fill %.2f | "
+                            "out waits %.2f | out copies %.2f | finish %.2f\n",
+                    what, chunks, now(), plan_ms, wait_ms, fill_ms, drain_wait_ms, drain_ms, finish_ms);
+    }
+};
 
 struct HostPlan {
     int piece = 1024;
@@ -34,6 +64,7 @@ struct HostPlan {
     std::vector<int32_t> long_rows, long_first, long_np, piece_row, piece_k;
     int max_chunk_pieces = 0;
     size_t max_chunk_nnz = 0;
+    size_t max_chunk_rows = 0;
 };
 
 // One pass over the host indptr: chunk boundaries, monotonicity check, long-row tables (the host twin of
@@ -60,6 +91,7 @@ int build_plan(int m, const int32_t *p, HostPlan &plan)
         plan.chunk_piece_off.push_back((int)plan.piece_row.size());
         plan.max_chunk_pieces = std::max(plan.max_chunk_pieces, pieces_in_chunk);
         plan.max_chunk_nnz = std::max(plan.max_chunk_nnz, (size_t)((int64_t)p[row_end] - chunk_first));
+        plan.max_chunk_rows = std::max(plan.max_chunk_rows, (size_t)(row_end - chunk_start));
         chunk_start = row_end;
         chunk_first = p[row_end];
         pieces_in_chunk = 0;
@@ -135,6 +167,64 @@ int copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t w
     return MXG_OK;
 }
 
+// Ring of page-locked slots for host -> device traffic.  acquire() hands out the next slot once the copy that
+// last read it has finished; release(stream) marks it busy until everything enqueued on `stream` so far is done.
+thread_local Trace *g_trace = nullptr;
+
+struct InRing {
+    char *base = nullptr;
+    size_t slot_bytes = 0;
+    int slots = 0, cur = -1, next = 0;
+    std::vector<cudaEvent_t> busy;
+    std::vector<char> used;
+    bool enabled() const { return slots > 0 && slot_bytes > 0; }
+    int init(Scratch &sc, char *mem, size_t bytes_per_slot, int n)
+    {
+        base = mem;
+        slot_bytes = bytes_per_slot;
+        slots = n;
+        busy.resize((size_t)n);
+        used.assign((size_t)n, 0);
+        for (int i = 0; i < n; i++) MXG_TRY(sc.event(&busy[(size_t)i]));
+        return MXG_OK;
+    }
+    int acquire(char **slot)
+    {
+        cur = next;
+        next = (next + 1) % slots;
+        const double t = g_trace ? g_trace->now() : 0;
+        if (used[(size_t)cur]) MXG_CUDA_TRY(cudaEventSynchronize(busy[(size_t)cur]));
+        if (g_trace) g_trace->wait_ms += g_trace->now() - t;
+        *slot = base + (size_t)cur * slot_bytes;
+        return MXG_OK;
+    }
+    int release(cudaStream_t stream)
+    {
+        MXG_CUDA_TRY(cudaEventRecord(busy[(size_t)cur], stream));
+        used[(size_t)cur] = 1;
+        return MXG_OK;
+    }
+};
+
+// host -> device copy of `height` lines of `width` bytes; a pageable source goes through the ring block by block
+int upload_lines(InRing *ring, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                 cudaStream_t stream)
+{
+    if (width == 0 || height == 0) return MXG_OK;
+    if (!ring || !ring->enabled() || width > ring->slot_bytes)
+        return copy_rows(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, stream);
+    const size_t lines = ring->slot_bytes / width;
+    for (size_t l0 = 0; l0 < height; l0 += lines) {
+        const size_t nl = std::min(lines, height - l0);
+        char *slot = nullptr;
+        MXG_TRY(ring->acquire(&slot));
+        host_copy_2d(slot, width, static_cast<const char *>(src) + l0 * spitch, spitch, width, nl);
+        MXG_TRY(copy_rows(static_cast<char *>(dst) + l0 * dpitch, dpitch, slot, width, width, nl, cudaMemcpyHostToDevice, stream));
+        MXG_TRY(ring->release(stream));
+    }
+    return MXG_OK;
+}
+
 // state shared by the SpMM and SpMV pipelines: device CSR arrays, chunk plan, long-row tables
 struct CsrStream {
     Scratch &sc;
@@ -143,7 +233,15 @@ struct CsrStream {
     int64_t nnz;
     const int32_t *p, *j;
     const double *x;
-    bool narrow; // values are narrowed to float32 on the device
+    bool narrow; // the product runs on float32 values
+    // host staging (hoststage.cu)
+    bool narrow_on_host = false; // float32 values are produced by the host threads, no device narrowing
+    bool stage_x = false, stage_j = false;
+    size_t x_part = 0; // bytes of a slot reserved for the values (indices follow)
+    InRing ring;       // slots for chunk uploads (also used for the dense operand before the first chunk)
+    char *out_base = nullptr; // ring of output slots (one per chunk, c % out_slots)
+    size_t out_slot_bytes = 0;
+    int out_slots = 0;
     int32_t *d_p = nullptr, *d_j = nullptr;
     double *d_x64 = nullptr;
     float *d_x32 = nullptr;
@@ -161,7 +259,34 @@ struct CsrStream {
     }
     int chunks() const { return (int)plan.chunk_row.size() - 1; }
 
-    // allocations + indptr upload + host plan + table upload.  partial_per_piece = workspace bytes per piece.
+    // Plan + page-locked arena.  dense_pageable: the dense operand wants ring slots too; out_row_bytes > 0:
+    // the result is pageable and every chunk's rows (out_row_bytes each) are bounced through an output slot.
+    int plan_host(bool dense_pageable, size_t out_row_bytes)
+    {
+        MXG_TRY(build_plan(m, p, plan));
+        const bool stage = options().host_stage != 0;
+        narrow_on_host = narrow && options().host_narrow != 0 && nnz > 0;
+        stage_x = nnz > 0 && (narrow_on_host || (stage && !host_is_pinned(x)));
+        stage_j = nnz > 0 && stage && !host_is_pinned(j);
+        auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
+        x_part = stage_x ? up(plan.max_chunk_nnz * (narrow_on_host ? sizeof(float) : sizeof(double))) : 0;
+        size_t in_slot = x_part + (stage_j ? up(plan.max_chunk_nnz * sizeof(int32_t)) : 0);
+        if (dense_pageable && stage) in_slot = std::max(in_slot, (size_t)16 << 20);
+        const int S = (int)std::min<long>(std::max<long>(options().pipe_slots, 3), 8);
+        out_slots = out_row_bytes > 0 && stage ? S : 0;
+        out_slot_bytes = out_slots ? up(plan.max_chunk_rows * out_row_bytes) : 0;
+        const size_t total = (size_t)S * in_slot + (size_t)out_slots * out_slot_bytes;
+        if (total > 0) {
+            char *base = nullptr;
+            MXG_TRY(pinned_arena(sc.st, total, &base));
+            if (in_slot > 0) MXG_TRY(ring.init(sc, base, in_slot, S));
+            out_base = base + (size_t)S * in_slot;
+        }
+        return MXG_OK;
+    }
+    char *out_slot(int c) const { return out_base + (size_t)(c % out_slots) * out_slot_bytes; }
+
+    // device allocations + indptr upload + table upload.  partial_per_piece = workspace bytes per piece.
     int begin(size_t partial_per_piece)
     {
         DeviceState *st = sc.st;
@@ -174,7 +299,6 @@ struct CsrStream {
         MXG_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st->stream));
         MXG_TRY(chain(sc, st->stream, st->h2d));
         MXG_CUDA_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, st->h2d));
-        MXG_TRY(build_plan(m, p, plan)); // host work, overlaps the copies already in flight
         const size_t nl = plan.long_rows.size(), np = plan.piece_row.size();
         if (nl > 0) {
             MXG_TRY(sc.alloc((void **)&d_tables, sizeof(int32_t) * (3 * nl + 2 * np)));
@@ -189,7 +313,7 @@ struct CsrStream {
                 off += src[t]->size();
             }
         }
-        if (narrow) {
+        if (narrow && !narrow_on_host) {
             const size_t stage_n = plan.max_chunk_nnz + (plan.max_chunk_nnz & 1);
             for (int b = 0; b < NSTAGE && b < chunks(); b++) MXG_TRY(sc.alloc((void **)&d_stage[b], sizeof(double) * stage_n));
             MXG_TRY(chain(sc, st->stream, st->h2d));
@@ -198,26 +322,50 @@ struct CsrStream {
         ev_conv.resize((size_t)chunks());
         for (int c = 0; c < chunks(); c++) {
             MXG_TRY(sc.event(&ev_h2d[(size_t)c]));
-            if (narrow) MXG_TRY(sc.event(&ev_conv[(size_t)c]));
+            if (narrow && !narrow_on_host) MXG_TRY(sc.event(&ev_conv[(size_t)c]));
         }
         return MXG_OK;
     }
 
-    // h2d stream: indices and values of chunk c
+    // h2d stream: indices and values of chunk c (through a ring slot where the host threads are involved)
     int upload_chunk(int c)
     {
         DeviceState *st = sc.st;
         const int64_t e0 = p[plan.chunk_row[(size_t)c]], e1 = p[plan.chunk_row[(size_t)c + 1]];
         const size_t len = (size_t)(e1 - e0);
         if (len > 0) {
-            MXG_CUDA_TRY(cudaMemcpyAsync(d_j + e0, j + e0, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
-            if (narrow) {
-                // the staging buffer is free again once the narrowing of chunk c - NSTAGE has run
-                if (c >= NSTAGE) MXG_CUDA_TRY(cudaStreamWaitEvent(st->h2d, ev_conv[(size_t)(c - NSTAGE)], 0));
-                MXG_CUDA_TRY(cudaMemcpyAsync(d_stage[c % NSTAGE], x + e0, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+            char *slot = nullptr;
+            if (stage_x || stage_j) MXG_TRY(ring.acquire(&slot));
+            // values: float32 made on the host -> d_x32; float64 -> d_x64, or -> device staging + narrowing kernel
+            const void *xsrc = x + e0;
+            const double tf = g_trace ? g_trace->now() : 0;
+            if (narrow_on_host) {
+                host_narrow_f64_to_f32(x + e0, reinterpret_cast<float *>(slot), len);
+                if (g_trace) g_trace->fill_ms += g_trace->now() - tf;
+                MXG_CUDA_TRY(cudaMemcpyAsync(d_x32 + e0, slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
             } else {
-                MXG_CUDA_TRY(cudaMemcpyAsync(d_x64 + e0, x + e0, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                if (stage_x) {
+                    host_copy(slot, x + e0, sizeof(double) * len);
+                    xsrc = slot;
+                    if (g_trace) g_trace->fill_ms += g_trace->now() - tf;
+                }
+                if (narrow) {
+                    // the device staging buffer is free again once the narrowing of chunk c - NSTAGE has run
+                    if (c >= NSTAGE) MXG_CUDA_TRY(cudaStreamWaitEvent(st->h2d, ev_conv[(size_t)(c - NSTAGE)], 0));
+                    MXG_CUDA_TRY(cudaMemcpyAsync(d_stage[c % NSTAGE], xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                } else {
+                    MXG_CUDA_TRY(cudaMemcpyAsync(d_x64 + e0, xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                }
             }
+            const void *jsrc = j + e0;
+            if (stage_j) {
+                const double tj = g_trace ? g_trace->now() : 0;
+                host_copy(slot + x_part, j + e0, sizeof(int32_t) * len);
+                jsrc = slot + x_part;
+                if (g_trace) g_trace->fill_ms += g_trace->now() - tj;
+            }
+            MXG_CUDA_TRY(cudaMemcpyAsync(d_j + e0, jsrc, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
+            if (slot) MXG_TRY(ring.release(st->h2d));
         }
         MXG_CUDA_TRY(cudaEventRecord(ev_h2d[(size_t)c], st->h2d));
         return MXG_OK;
@@ -231,7 +379,7 @@ struct CsrStream {
         const int64_t e0 = p[r0], e1 = p[r1];
         const size_t len = (size_t)(e1 - e0);
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->stream, ev_h2d[(size_t)c], 0));
-        if (narrow) {
+        if (narrow && !narrow_on_host) {
             if (len > 0) {
                 // chunk starts are not always even: narrow element-wise from the staging buffer's start
                 MXG_TRY(convert_f64_to_f32(d_stage[c % NSTAGE], d_x32 + e0, len, st->stream));
@@ -305,57 +453,91 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     const int64_t nnz = p[m];
     if (nnz > 0 && (!j || !x)) return fail(MXG_ERR_ARG, "csr: indices / values is NULL");
 
+    Trace trace;
+    struct TraceScope {
+        explicit TraceScope(Trace *t) { g_trace = t->on ? t : nullptr; }
+        ~TraceScope() { g_trace = nullptr; }
+    } trace_scope(&trace);
     Scratch sc(st);
+    CsrStream cs(sc, m, K, p, j, x, /*narrow=*/dtype == MXG_F32);
+    const bool stage = options().host_stage != 0;
+    const bool stage_B = stage && K > 0 && !host_is_pinned(B);
+    const bool stage_out = stage && !host_is_pinned(Out);
     // dense operand first: every chunk needs all of it.  Device copy is rows-contiguous [K][ld_b].
     const size_t ld_b = round_up(nz, vec);
-    char *d_B = nullptr, *d_Out = nullptr;
+    char *d_B = nullptr, *d_Out = nullptr, *d_tmp = nullptr;
     MXG_TRY(sc.alloc((void **)&d_B, Kz * ld_b * s));
     const size_t ld_o = out_layout == MXG_ROWS_CONTIGUOUS ? round_up(nz, vec) : rows;
     MXG_TRY(sc.alloc((void **)&d_Out, out_layout == MXG_ROWS_CONTIGUOUS ? rows * ld_o * s : rows * nz * s));
-    if (K > 0) {
-        if (ld_b != nz) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, Kz * ld_b * s, st->stream));
-        if (b_layout == MXG_ROWS_CONTIGUOUS) {
-            MXG_TRY(chain(sc, st->stream, st->h2d));
-            MXG_TRY(copy_rows(d_B, ld_b * s, B, ldb * s, nz * s, Kz, cudaMemcpyHostToDevice, st->h2d));
-            MXG_TRY(chain(sc, st->h2d, st->stream));
-        } else {
-            char *d_tmp = nullptr;
-            MXG_TRY(sc.alloc((void **)&d_tmp, Kz * nz * s));
-            MXG_TRY(chain(sc, st->stream, st->h2d));
-            MXG_TRY(copy_rows(d_tmp, Kz * s, B, ldb * s, Kz * s, nz, cudaMemcpyHostToDevice, st->h2d));
-            MXG_TRY(chain(sc, st->h2d, st->stream));
-            MXG_TRY(launch_transpose_dense((int)s, nz, Kz, d_tmp, Kz, d_B, ld_b, st->stream)); // [n][K] -> [K][ld_b]
-        }
-    }
+    if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS) MXG_TRY(sc.alloc((void **)&d_tmp, Kz * nz * s));
+    if (K > 0 && ld_b != nz) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, Kz * ld_b * s, st->stream));
+    MXG_TRY(chain(sc, st->stream, st->h2d));
+    auto upload_dense = [&](InRing *ring) -> int {
+        if (K == 0) return MXG_OK;
+        if (b_layout == MXG_ROWS_CONTIGUOUS) return upload_lines(ring, d_B, ld_b * s, B, ldb * s, nz * s, Kz, st->h2d);
+        return upload_lines(ring, d_tmp, Kz * s, B, ldb * s, Kz * s, nz, st->h2d);
+    };
+    // a page-locked operand starts to fly before the host pass over the indptr, a pageable one needs the ring first
+    if (!stage_B) MXG_TRY(upload_dense(nullptr));
+    const double t_plan = trace.now();
+    MXG_TRY(cs.plan_host(stage_B, stage_out ? nz * s : 0));
+    trace.plan_ms = trace.now() - t_plan;
+    if (stage_B) MXG_TRY(upload_dense(&cs.ring));
+    MXG_TRY(chain(sc, st->h2d, st->stream));
+    if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS)
+        MXG_TRY(launch_transpose_dense((int)s, nz, Kz, d_tmp, Kz, d_B, ld_b, st->stream)); // [n][K] -> [K][ld_b]
 
-    CsrStream cs(sc, m, K, p, j, x, /*narrow=*/dtype == MXG_F32);
     MXG_TRY(cs.begin(nz * s));
     const int C = cs.chunks();
-    std::vector<cudaEvent_t> ev_done((size_t)C);
+    std::vector<cudaEvent_t> ev_done((size_t)C), ev_out((size_t)(stage_out ? C : 0));
     for (int c = 0; c < C; c++) MXG_TRY(sc.event(&ev_done[(size_t)c]));
+    for (size_t c = 0; c < ev_out.size(); c++) MXG_TRY(sc.event(&ev_out[c]));
 
+    // geometry of chunk c's block of the result: `height` lines of `width` bytes
+    const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
     auto process = [&](int c) -> int {
         mxg_csr_s h;
         MXG_TRY(cs.prepare_chunk(c, h));
         const size_t r0 = (size_t)cs.plan.chunk_row[(size_t)c], nr = (size_t)h.m;
-        char *d_o = d_Out + (out_layout == MXG_ROWS_CONTIGUOUS ? r0 * ld_o * s : r0 * s);
+        char *d_o = d_Out + (rm ? r0 * ld_o * s : r0 * s);
         MXG_TRY(launch_spmm(&h, dtype, out_layout, n, d_B, ld_b, d_o, ld_o, st->stream));
         if (h.d_seg) MXG_CUDA_TRY(cudaFreeAsync(h.d_seg, st->stream)); // the chunk's column-panel table
         MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)c], st->stream));
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
-        char *h_o = static_cast<char *>(Out) + (out_layout == MXG_ROWS_CONTIGUOUS ? r0 * ldc * s : r0 * s);
-        if (out_layout == MXG_ROWS_CONTIGUOUS)
-            MXG_TRY(copy_rows(h_o, ldc * s, d_o, ld_o * s, nz * s, nr, cudaMemcpyDeviceToHost, st->d2h));
-        else
-            MXG_TRY(copy_rows(h_o, ldc * s, d_o, ld_o * s, nr * s, nz, cudaMemcpyDeviceToHost, st->d2h));
+        const size_t width = rm ? nz * s : nr * s, height = rm ? nr : nz;
+        if (stage_out) { // packed into the chunk's output slot; drain() moves it into the caller's matrix
+            MXG_TRY(copy_rows(cs.out_slot(c), width, d_o, ld_o * s, width, height, cudaMemcpyDeviceToHost, st->d2h));
+            MXG_CUDA_TRY(cudaEventRecord(ev_out[(size_t)c], st->d2h));
+        } else {
+            char *h_o = static_cast<char *>(Out) + (rm ? r0 * ldc * s : r0 * s);
+            MXG_TRY(copy_rows(h_o, ldc * s, d_o, ld_o * s, width, height, cudaMemcpyDeviceToHost, st->d2h));
+        }
         return MXG_OK;
     };
-    for (int c = 0; c < C; c++) {
-        MXG_TRY(cs.upload_chunk(c));
-        if (c >= 1) MXG_TRY(process(c - 1));
+    auto drain = [&](int c) -> int {
+        if (!stage_out) return MXG_OK;
+        const size_t r0 = (size_t)cs.plan.chunk_row[(size_t)c], nr = (size_t)cs.plan.chunk_row[(size_t)c + 1] - r0;
+        const size_t width = rm ? nz * s : nr * s, height = rm ? nr : nz;
+        const double t0 = trace.now();
+        MXG_CUDA_TRY(cudaEventSynchronize(ev_out[(size_t)c]));
+        const double t1 = trace.now();
+        char *h_o = static_cast<char *>(Out) + (rm ? r0 * ldc * s : r0 * s);
+        host_copy_2d(h_o, ldc * s, cs.out_slot(c), width, width, height);
+        trace.drain_wait_ms += t1 - t0;
+        trace.drain_ms += trace.now() - t1;
+        return MXG_OK;
+    };
+    // chunk c is uploaded while c - 1 is computed and c - 2 leaves its output slot
+    for (int c = 0; c < C + 2; c++) {
+        if (c < C) MXG_TRY(cs.upload_chunk(c));
+        if (c >= 1 && c <= C) MXG_TRY(process(c - 1));
+        if (c >= 2) MXG_TRY(drain(c - 2));
     }
-    if (C >= 1) MXG_TRY(process(C - 1));
-    return cs.finish();
+    const double t_fin = trace.now();
+    const int rc = cs.finish();
+    trace.finish_ms = trace.now() - t_fin;
+    trace.report("spmm", C);
+    return rc;
 }
 
 int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
@@ -370,18 +552,30 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
     const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
 
     Scratch sc(st);
+    CsrStream cs(sc, m, K, p, j, x, /*narrow=*/false);
+    const bool stage = options().host_stage != 0;
+    const bool stage_y = stage && K > 0 && !host_is_pinned(y);
+    const bool stage_out = stage && !host_is_pinned(out);
     char *d_y = nullptr, *d_out = nullptr;
     MXG_TRY(sc.alloc((void **)&d_y, (size_t)K * ys));
     MXG_TRY(sc.alloc((void **)&d_out, (size_t)m * os));
     MXG_TRY(chain(sc, st->stream, st->h2d));
-    if (K > 0) MXG_CUDA_TRY(cudaMemcpyAsync(d_y, y, (size_t)K * ys, cudaMemcpyHostToDevice, st->h2d));
+    if (!stage_y) MXG_TRY(upload_lines(nullptr, d_y, (size_t)K * ys, y, (size_t)K * ys, (size_t)K * ys, 1, st->h2d));
+    MXG_TRY(cs.plan_host(stage_y, stage_out ? os : 0));
+    // the vector as lines of <= 4 MiB so that it fits the ring slots whatever K is
+    if (stage_y) {
+        const size_t line = (size_t)4 << 20, total = (size_t)K * ys;
+        MXG_TRY(upload_lines(&cs.ring, d_y, line, y, line, line, total / line, st->h2d));
+        const size_t done = total / line * line;
+        MXG_TRY(upload_lines(&cs.ring, d_y + done, total - done, static_cast<const char *>(y) + done, total - done, total - done, 1, st->h2d));
+    }
     MXG_TRY(chain(sc, st->h2d, st->stream));
 
-    CsrStream cs(sc, m, K, p, j, x, /*narrow=*/false);
     MXG_TRY(cs.begin(16)); // a double and a flag per piece
     const int C = cs.chunks();
-    std::vector<cudaEvent_t> ev_done((size_t)C);
+    std::vector<cudaEvent_t> ev_done((size_t)C), ev_out((size_t)(stage_out ? C : 0));
     for (int c = 0; c < C; c++) MXG_TRY(sc.event(&ev_done[(size_t)c]));
+    for (size_t c = 0; c < ev_out.size(); c++) MXG_TRY(sc.event(&ev_out[c]));
     auto process = [&](int c) -> int {
         mxg_csr_s h;
         MXG_TRY(cs.prepare_chunk(c, h));
@@ -389,14 +583,25 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
         MXG_TRY(launch_spmv(&h, ytype, d_y, d_out + r0 * os, st->stream));
         MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)c], st->stream));
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
-        MXG_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(out) + r0 * os, d_out + r0 * os, nr * os, cudaMemcpyDeviceToHost, st->d2h));
+        if (nr == 0) return MXG_OK;
+        char *dst = stage_out ? cs.out_slot(c) : static_cast<char *>(out) + r0 * os;
+        MXG_CUDA_TRY(cudaMemcpyAsync(dst, d_out + r0 * os, nr * os, cudaMemcpyDeviceToHost, st->d2h));
+        if (stage_out) MXG_CUDA_TRY(cudaEventRecord(ev_out[(size_t)c], st->d2h));
         return MXG_OK;
     };
-    for (int c = 0; c < C; c++) {
-        MXG_TRY(cs.upload_chunk(c));
-        if (c >= 1) MXG_TRY(process(c - 1));
+    auto drain = [&](int c) -> int {
+        if (!stage_out) return MXG_OK;
+        const size_t r0 = (size_t)cs.plan.chunk_row[(size_t)c], nr = (size_t)cs.plan.chunk_row[(size_t)c + 1] - r0;
+        if (nr == 0) return MXG_OK;
+        MXG_CUDA_TRY(cudaEventSynchronize(ev_out[(size_t)c]));
+        host_copy(static_cast<char *>(out) + r0 * os, cs.out_slot(c), nr * os);
+        return MXG_OK;
+    };
+    for (int c = 0; c < C + 2; c++) {
+        if (c < C) MXG_TRY(cs.upload_chunk(c));
+        if (c >= 1 && c <= C) MXG_TRY(process(c - 1));
+        if (c >= 2) MXG_TRY(drain(c - 2));
     }
-    if (C >= 1) MXG_TRY(process(C - 1));
     return cs.finish();
 }
 

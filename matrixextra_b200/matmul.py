@@ -20,12 +20,13 @@ from . import rcpp_exports as rx
 from ._lib import MXG_F32, MXG_F64
 from .classes import check_valid_matrix, dgCMatrix, dgRMatrix, float32, sparseVector, t_shallow
 
-#: options("MatrixExtra.*") read by the hot path (R/zzz.R:116-171).  ``nthreads`` is advisory on the GPU.
-options = {"MatrixExtra.nthreads": 1, "MatrixExtra.inplace_sort": False}
+#: options("MatrixExtra.*") read by the hot path (R/zzz.R:116-171).  ``nthreads`` defaults to all cores in the
+#: reference (parallel::detectCores(), R/zzz.R:140-171); here it sizes the library's host staging threads, 0 = all.
+options = {"MatrixExtra.nthreads": 0, "MatrixExtra.inplace_sort": False}
 
 
 def _nthreads() -> int:
-    return max(int(options.get("MatrixExtra.nthreads", 1)), 1)
+    return max(int(options.get("MatrixExtra.nthreads", 0)), 0)
 
 
 def _is_dense(x) -> bool:
@@ -133,7 +134,7 @@ def gemv_csr_vec(x: dgRMatrix, y):
     if x.Dim[1] != ylen:
         raise ValueError("Matrix-vector dimensions do not match.")
     check_valid_matrix(x)
-    nt = int(options.get("MatrixExtra.nthreads", 1))
+    nt = _nthreads()
     if isinstance(y, sparseVector):
         # R/matmul.R:595-646.  The reference sorts x and y first (602-603) because its kernel merges two sorted
         # lists; the device kernel tests membership in a bitmap and needs neither, so no sort is done here.

@@ -5,8 +5,9 @@ implemented on the CUDA library through the level-1 (host buffers) C ABI.
 This file plays the role of rglue/matmul_gpu_glue.cpp (the real Rcpp glue, which cannot be executed
 in an image without R): same dimension inference from the argument shapes, same zero-copy borrowing
 of inputs, a freshly allocated column-major output, errors raised from mxg_last_error().
-``nthreads`` and ``ncols_Y`` are accepted and ignored, as ``ncols_Y`` already is in the reference
-(src/matmul.cpp:259).
+``nthreads`` (the reference's OpenMP team size) sets the number of HOST threads of the library's staging engine
+(csrc/hoststage.cu: narrowing float64 values, bouncing pageable memory through page-locked slots); 0 = all
+logical CPUs.  ``ncols_Y`` is accepted and ignored, as it already is in the reference (src/matmul.cpp:259).
 """
 from __future__ import annotations
 
@@ -21,6 +22,10 @@ from ._lib import (MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_ROWS_CONTIGUOUS, M
 
 def _vp(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
+
+
+def _threads(nthreads) -> None:
+    _lib.set_option("host_threads", max(0, int(nthreads)))
 
 
 def _csr(p, j, x):
@@ -60,19 +65,23 @@ def _dense_times_tcsr(X_colmajor, indptr, indices, values, dtype, out=None):
     return out
 
 
-def matmul_dense_csc_numeric(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1, out=None):
+def matmul_dense_csc_numeric(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=0, out=None):
+    _threads(nthreads)
     return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F64, out)
 
 
-def matmul_dense_csc_float32(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=1, out=None):
+def matmul_dense_csc_float32(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, nthreads=0, out=None):
+    _threads(nthreads)
     return _dense_times_tcsr(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values, MXG_F32, out)
 
 
-def tcrossprod_dense_csr_numeric(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0, out=None):
+def tcrossprod_dense_csr_numeric(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=0, ncols_Y=0, out=None):
+    _threads(nthreads)
     return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F64, out)
 
 
-def tcrossprod_dense_csr_float32(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=1, ncols_Y=0, out=None):
+def tcrossprod_dense_csr_float32(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, nthreads=0, ncols_Y=0, out=None):
+    _threads(nthreads)
     return _dense_times_tcsr(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values, MXG_F32, out)
 
 
@@ -90,11 +99,13 @@ def _csr_times_tdense(indptr, indices, values, Y_colmajor, dtype, out=None):
     return out
 
 
-def tcrossprod_csr_dense_numeric(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1, out=None):
+def tcrossprod_csr_dense_numeric(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F64, out)
 
 
-def tcrossprod_csr_dense_float32(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=1, out=None):
+def tcrossprod_csr_dense_float32(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_times_tdense(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor, MXG_F32, out)
 
 
@@ -108,19 +119,23 @@ def _csr_dvec(indptr, indices, values, y, ytype, y_np, out_np, out=None):
     return out
 
 
-def matmul_csr_dvec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+def matmul_csr_dvec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_NUMERIC, np.float64, np.float64, out)
 
 
-def matmul_csr_dvec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+def matmul_csr_dvec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_INTEGER, np.int32, np.float64, out)
 
 
-def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+def matmul_csr_dvec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_LOGICAL, np.int32, np.float64, out)
 
 
-def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=1, out=None):
+def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, nthreads=0, out=None):
+    _threads(nthreads)
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32, out)
 
 
@@ -140,23 +155,28 @@ def _csr_svec(indptr, indices, values, y_indices_base1, y_values, ytype, y_np, n
     return out
 
 
-def matmul_csr_svec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+def matmul_csr_svec_numeric(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=0, ncols=0, out=None):
+    _threads(nthreads)
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_NUMERIC, np.float64, ncols, out)
 
 
-def matmul_csr_svec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+def matmul_csr_svec_integer(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=0, ncols=0, out=None):
+    _threads(nthreads)
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_INTEGER, np.int32, ncols, out)
 
 
-def matmul_csr_svec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+def matmul_csr_svec_logical(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=0, ncols=0, out=None):
+    _threads(nthreads)
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_LOGICAL, np.int32, ncols, out)
 
 
-def matmul_csr_svec_binary(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, nthreads=1, ncols=0, out=None):
+def matmul_csr_svec_binary(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, nthreads=0, ncols=0, out=None):
+    _threads(nthreads)
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, None, MXG_Y_BINARY, np.int32, ncols, out)
 
 
-def matmul_csr_svec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=1, ncols=0, out=None):
+def matmul_csr_svec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, nthreads=0, ncols=0, out=None):
+    _threads(nthreads)
     """Exported by the reference but never called from R (src/matmul.cpp:626-641); double result."""
     return _csr_svec(X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, y_values, MXG_Y_FLOAT32, np.float32, ncols, out)
 

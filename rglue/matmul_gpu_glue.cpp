@@ -10,7 +10,7 @@
  *
  * Contract kept from the reference:
  *   - inputs are borrowed (no copy, never written); the result is a freshly allocated R matrix / vector;
- *   - `nthreads` is accepted and ignored (advisory on a GPU); `ncols_Y` is accepted and ignored exactly as
+ *   - `nthreads` sets the library's HOST staging threads (narrowing, pageable bounce; 0 = auto); `ncols_Y` is accepted and ignored exactly as
  *     the reference ignores it (src/matmul.cpp:259);
  *   - float32 matrices arrive as IntegerMatrix holding IEEE-754 binary32 bits (src/matmul.cpp:213-214);
  *   - errors surface as R errors: a non-zero status becomes Rcpp::stop(mxg_last_error()) AFTER the C call has
@@ -101,7 +101,7 @@ Rcpp::NumericMatrix matmul_dense_csc_numeric(Rcpp::NumericMatrix X_colmajor, Rcp
                                              Rcpp::IntegerVector Y_csc_indices, Rcpp::NumericVector Y_csc_values,
                                              int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     return dense_times_tsparse<Rcpp::NumericMatrix>(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values);
 }
 
@@ -110,7 +110,7 @@ Rcpp::IntegerMatrix matmul_dense_csc_float32(Rcpp::IntegerMatrix X_colmajor, Rcp
                                              Rcpp::IntegerVector Y_csc_indices, Rcpp::NumericVector Y_csc_values,
                                              int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     return dense_times_tsparse<Rcpp::IntegerMatrix>(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values);
 }
 
@@ -120,7 +120,7 @@ Rcpp::NumericMatrix tcrossprod_dense_csr_numeric(Rcpp::NumericMatrix X_colmajor,
                                                  Rcpp::IntegerVector Y_csr_indices, Rcpp::NumericVector Y_csr_values,
                                                  int nthreads, int ncols_Y)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     (void)ncols_Y;
     return dense_times_tsparse<Rcpp::NumericMatrix>(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values);
 }
@@ -130,7 +130,7 @@ Rcpp::IntegerMatrix tcrossprod_dense_csr_float32(Rcpp::IntegerMatrix X_colmajor,
                                                  Rcpp::IntegerVector Y_csr_indices, Rcpp::NumericVector Y_csr_values,
                                                  int nthreads, int ncols_Y)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     (void)ncols_Y;
     return dense_times_tsparse<Rcpp::IntegerMatrix>(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values);
 }
@@ -141,7 +141,7 @@ Rcpp::NumericMatrix tcrossprod_csr_dense_numeric(Rcpp::IntegerVector X_csr_indpt
                                                  Rcpp::NumericVector X_csr_values, Rcpp::NumericMatrix Y_colmajor,
                                                  int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     return sparse_times_tdense<Rcpp::NumericMatrix>(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor);
 }
 
@@ -150,7 +150,7 @@ Rcpp::IntegerMatrix tcrossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indpt
                                                  Rcpp::NumericVector X_csr_values, Rcpp::IntegerMatrix Y_colmajor,
                                                  int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     return sparse_times_tdense<Rcpp::IntegerMatrix>(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor);
 }
 
@@ -159,7 +159,7 @@ Rcpp::IntegerMatrix tcrossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indpt
 Rcpp::NumericVector matmul_csr_dvec_numeric(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::NumericVector y_dense, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_NUMERIC, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -171,7 +171,7 @@ Rcpp::NumericVector matmul_csr_dvec_numeric(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::NumericVector matmul_csr_dvec_integer(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::IntegerVector y_dense, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_INTEGER, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -183,7 +183,7 @@ Rcpp::NumericVector matmul_csr_dvec_integer(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::NumericVector matmul_csr_dvec_logical(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::LogicalVector y_dense, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_LOGICAL, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -195,7 +195,7 @@ Rcpp::NumericVector matmul_csr_dvec_logical(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::IntegerVector matmul_csr_dvec_float32(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::IntegerVector y_dense, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::IntegerVector out = MXGPU_NEW_VECTOR(Rcpp::IntegerVector, m); /* binary32 bits, like y_dense */
     mxgpu_check(mxg_spmv_csr(MXG_Y_FLOAT32, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -212,7 +212,7 @@ Rcpp::NumericMatrix crossprod_csr_dense_numeric(Rcpp::IntegerVector X_csr_indptr
                                                 Rcpp::NumericVector X_csr_values, int ncols_X,
                                                 Rcpp::NumericMatrix Y_colmajor, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     const int n = Y_colmajor.ncol();
     if (Y_colmajor.nrow() != m) MXGPU_GLUE_STOP("Matrix dimensions do not match.");
@@ -229,7 +229,7 @@ Rcpp::IntegerMatrix crossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indptr
                                                 Rcpp::NumericVector X_csr_values, int ncols_X,
                                                 Rcpp::IntegerMatrix Y_colmajor, int nthreads)
 {
-    (void)nthreads;
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
     const int m = (int)X_csr_indptr.size() - 1;
     const int n = Y_colmajor.ncol();
     if (Y_colmajor.nrow() != m) MXGPU_GLUE_STOP("Matrix dimensions do not match.");

@@ -1,0 +1,169 @@
+"""GPU tests of the host staging engine of the streamed level-1 calls (csrc/hoststage.cu + csrc/pipeline.cu):
+pageable caller memory bounced through the page-locked ring by the host threads, float32 values narrowed on the
+host.  Whatever route the bytes take — pageable or page-locked operands, host or device narrowing, staging on or
+off, one thread or many, few ring slots and many chunks — the result must be the SAME BITS, and within the
+north_star tolerance of the CPU oracle (src/matmul.cpp:118-185, 381-483)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from helpers import FP32_TOL, FP64_TOL, powerlaw_csr, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rx():
+    from matrixextra_b200 import rcpp_exports
+    return rcpp_exports
+
+
+@pytest.fixture()
+def options():
+    from matrixextra_b200 import _lib
+    names = ("pipe_chunk_nnz", "piece", "host_narrow", "host_stage", "host_threads", "pipe_slots")
+    old = {k: _lib.get_option(k) for k in names}
+    yield _lib
+    for k, v in old.items():
+        _lib.set_option(k, v)
+
+
+def _pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t.numpy()
+
+
+def _pinned_f(shape, dtype):
+    """Page-locked Fortran-ordered matrix."""
+    import torch
+    flat = torch.empty(int(np.prod(shape)), dtype={np.float32: torch.float32, np.float64: torch.float64}[dtype]).pin_memory()
+    return flat.numpy().reshape(shape, order="F")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_every_staging_route_gives_the_same_bits(rx, port, options, dtype):
+    sfx = "float32" if dtype == np.float32 else "numeric"
+    tol = FP32_TOL if dtype == np.float32 else FP64_TOL
+    m, K, n = 4000, 1500, 24
+    p, j, x = powerlaw_csr(m, K, 15, seed=77, cap=1400)
+    options.set_option("piece", 64)
+    options.set_option("pipe_chunk_nnz", 1500)  # ~40 chunks: the ring wraps many times
+    rng = np.random.default_rng(3)
+    X = np.asfortranarray(rng.standard_normal((n, K)).astype(dtype))
+    want_rm = getattr(port, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, K)
+    want_cm = getattr(port, "tcrossprod_csr_dense_" + sfx)(p, j, x, X, 1)
+    pp, pj, px = _pinned(p), _pinned(j), _pinned(x)
+    pX = _pinned_f((n, K), dtype)
+    pX[...] = X
+    ref_rm = ref_cm = None
+    routes = itertools.product((0, 1), (0, 1), (1, 5), (False, True), (3, 8))
+    for narrow, stage, threads, pinned, slots in routes:
+        options.set_option("host_narrow", narrow)
+        options.set_option("host_stage", stage)
+        options.set_option("pipe_slots", slots)
+        a = (pp, pj, px, pX) if pinned else (p, j, x, X)
+        out_rm = _pinned_f((n, m), dtype) if pinned else None
+        out_cm = _pinned_f((m, n), dtype) if pinned else None
+        got_rm = getattr(rx, "tcrossprod_dense_csr_" + sfx)(a[3], a[0], a[1], a[2], threads, K, out=out_rm)
+        got_cm = getattr(rx, "tcrossprod_csr_dense_" + sfx)(a[0], a[1], a[2], a[3], threads, out=out_cm)
+        if ref_rm is None:
+            ref_rm, ref_cm = got_rm.copy(), got_cm.copy()
+            assert rel_err(ref_rm, want_rm) <= tol and rel_err(ref_cm, want_cm) <= tol
+        route = dict(narrow=narrow, stage=stage, threads=threads, pinned=pinned, slots=slots)
+        assert np.array_equal(got_rm, ref_rm), route
+        assert np.array_equal(got_cm, ref_cm), route
+
+
+def test_mixed_pinned_and_pageable_operands(rx, port, options):
+    """Each operand is classified on its own: pageable indices with page-locked values, pageable result, ..."""
+    m, K, n = 2500, 800, 16
+    p, j, x = powerlaw_csr(m, K, 10, seed=5, cap=700)
+    options.set_option("pipe_chunk_nnz", 2000)
+    rng = np.random.default_rng(8)
+    X = np.asfortranarray(rng.standard_normal((n, K)))
+    want = port.tcrossprod_dense_csr_numeric(X, p, j, x, 1, K)
+    ref = None
+    for pin_j, pin_x, pin_X, pin_out in itertools.product((False, True), repeat=4):
+        out = _pinned_f((n, m), np.float64) if pin_out else None
+        XX = X
+        if pin_X:
+            XX = _pinned_f((n, K), np.float64)
+            XX[...] = X
+        got = rx.tcrossprod_dense_csr_numeric(XX, p, _pinned(j) if pin_j else j, _pinned(x) if pin_x else x, 1, K, out=out)
+        if ref is None:
+            ref = got.copy()
+            assert rel_err(ref, want) <= FP64_TOL
+        assert np.array_equal(got, ref), (pin_j, pin_x, pin_X, pin_out)
+
+
+def test_staged_wide_operands_and_strided_result(rx, port, options):
+    """A dense operand larger than one ring slot (cut into blocks of lines), a column-major operand whose lines
+    are longer than the copy grain, and a caller result with ldc > n."""
+    import ctypes as C
+    from matrixextra_b200 import _lib
+    from matrixextra_b200._lib import MXG_F64, MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS
+    m, K, n = 3000, 300_000, 8  # B: 300000 x 8 doubles = 19.2 MB > the 16 MiB slot
+    rng = np.random.default_rng(11)
+    lens = rng.integers(0, 12, size=m)
+    p = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum(lens, out=p[1:])
+    j = np.concatenate([np.sort(rng.choice(K, size=l, replace=False)) for l in lens]).astype(np.int32)
+    x = rng.uniform(-1, 1, size=p[-1])
+    X = np.asfortranarray(rng.standard_normal((n, K)))  # n x K column-major == K rows of n contiguous
+    want = port.tcrossprod_dense_csr_numeric(X, p, j, x, 1, K)  # (n x m) column-major
+    vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    for b_layout in (MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS):
+        Bsrc = X if b_layout == MXG_ROWS_CONTIGUOUS else np.ascontiguousarray(X)  # lines of K doubles (2.4 MB)
+        ldb = n if b_layout == MXG_ROWS_CONTIGUOUS else K
+        ldc = n + 3
+        out = np.full((m, ldc), -7.0)
+        _lib.call("mxg_spmm_csr_dense", MXG_F64, MXG_ROWS_CONTIGUOUS, b_layout, m, K, n, vp(p), vp(j), vp(x), vp(Bsrc), ldb,
+                  vp(out), ldc)
+        assert np.all(out[:, n:] == -7.0)  # the padding of the caller's rows is not touched
+        assert rel_err(out[:, :n].T, want) <= FP64_TOL
+
+
+@pytest.mark.parametrize("ytype", ["numeric", "integer", "logical", "float32"])
+def test_spmv_staging_routes(rx, port, options, ytype):
+    m, K = 6000, 2000
+    p, j, x = powerlaw_csr(m, K, 12, seed=9, cap=1900)
+    options.set_option("pipe_chunk_nnz", 3000)
+    options.set_option("piece", 128)
+    rng = np.random.default_rng(2)
+    if ytype == "numeric":
+        y = rng.standard_normal(K)
+    elif ytype == "float32":
+        y = rng.standard_normal(K).astype(np.float32)
+    else:
+        y = rng.integers(-3, 4, size=K).astype(np.int32)
+        y[::97] = np.iinfo(np.int32).min  # NA
+    fn = getattr(rx, "matmul_csr_dvec_" + ytype)
+    want = getattr(port, "matmul_csr_dvec_" + ytype)(p, j, x, y, 1)
+    ref = None
+    for stage, threads, pinned in itertools.product((0, 1), (1, 4), (False, True)):
+        options.set_option("host_stage", stage)
+        a = (_pinned(p), _pinned(j), _pinned(x), _pinned(y)) if pinned else (p, j, x, y)
+        got = np.asarray(fn(*a, threads))
+        if ref is None:
+            ref = got.copy()
+            g64, w64 = np.asarray(ref, dtype=np.float64), np.asarray(want, dtype=np.float64)
+            assert np.array_equal(np.isnan(g64), np.isnan(w64))
+            ok = ~np.isnan(w64)
+            assert rel_err(g64[ok], w64[ok]) <= (FP32_TOL if ytype == "float32" else FP64_TOL)
+        assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), (stage, threads, pinned)
+
+
+def test_bad_column_index_is_still_reported_through_the_staged_route(rx, options):
+    from matrixextra_b200 import _lib
+    p, j, x = powerlaw_csr(500, 200, 8, seed=1)
+    j = j.copy()
+    j[len(j) // 2] = 200  # == K: out of range
+    options.set_option("pipe_chunk_nnz", 500)
+    X = np.asfortranarray(np.ones((4, 200), dtype=np.float32))
+    with pytest.raises(_lib.MxgError, match="outside"):
+        rx.tcrossprod_dense_csr_float32(X, p, j, x, 1, 200)
+    # and the library is usable afterwards
+    j[len(j) // 2] = 0
+    rx.tcrossprod_dense_csr_float32(X, p, j, x, 1, 200)
