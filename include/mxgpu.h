@@ -266,6 +266,12 @@ int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, s
 int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed,
                   int keep, void *stream, mxg_csr_t *handle);
 
+/* Measurement probe: fetches `gathers` (rounded up; the exact count comes back in *gathers_done) random rows of
+ * row_bytes (128 / 256 / 512) from a device table of `rows` rows and does nothing else — the random-row-gather
+ * roof (DRAM when the table is far larger than L2, L2->SM when it fits) that bounds K1/K2.  d_sink: 1 float. */
+int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
+                         float *d_sink, long long *gathers_done, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

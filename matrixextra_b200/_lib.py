@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mxg_dev_csr2csc": [_vp, _i32, _vp, C.POINTER(_vp)],
     "mxg_dev_transpose_dense": [_i32, _sz, _sz, _vp, _sz, _vp, _sz, _vp],
     "mxg_row_partition": [_i32, _vp, _i32, _vp],
+    "mxg_dev_gather_probe": [_i32, _vp, _sz, C.c_longlong, C.c_uint64, _vp, C.POINTER(C.c_longlong), _vp],
     "mxg_host_narrow": [_vp, _vp, _sz],
     "mxg_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz],
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],

@@ -8,6 +8,8 @@
 
 namespace mxg {
 
+int gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed, float *d_sink,
+                 cudaStream_t stream);
 int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed, int keep,
                      cudaStream_t stream, int32_t **out_p, int32_t **out_j, double **out_x64, float **out_x32,
                      int64_t *out_nnz);
@@ -291,6 +293,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_panel_mb")) return &o.spmm_panel_mb;
     if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
+    if (!strcmp(name, "spmm_cpl")) return &o.spmm_cpl;
     if (!strcmp(name, "host_threads")) return &o.host_threads;
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
     if (!strcmp(name, "host_stage")) return &o.host_stage;
@@ -577,6 +580,19 @@ int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts)
         row_starts[g] = r;
     }
     row_starts[parts] = m;
+    return MXG_OK;
+}
+
+int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
+                         float *d_sink, long long *gathers_done, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!d_table || !d_sink) return fail(MXG_ERR_ARG, "gather_probe: NULL buffer");
+    MXG_TRY(gather_probe(row_bytes, d_table, rows, gathers, seed, d_sink, static_cast<cudaStream_t>(stream)));
+    if (gathers_done) {
+        const long long teams = 148LL * 8 * 256 / (row_bytes / 16);
+        *gathers_done = teams * std::max<long long>(8, (gathers / teams + 7) / 8 * 8);
+    }
     return MXG_OK;
 }
 

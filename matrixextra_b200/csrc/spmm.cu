@@ -225,8 +225,8 @@ struct SpmmArgs {
 // in panel q to the output row (read-modify-write from the second panel on; rows without entries in the
 // panel are not touched).  Entries are consumed in stored order panel after panel, so for sorted rows the sum
 // order is unchanged; for unsorted rows the split points still partition the row (see k_panel_segments).
-template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS>
-__global__ void __launch_bounds__(SPMM_THREADS, CPL == 1 ? SPMM_MINB : 4) k_spmm(const SpmmArgs g)
+template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS, int MB = (CPL == 1 ? SPMM_MINB : 4)>
+__global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 {
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
     constexpr int BR = SPMM_WARPS * SPMM_CM_RPW;
@@ -490,6 +490,20 @@ __global__ void __launch_bounds__(256) k_fill_zero_2d(T *__restrict__ Out, size_
         Out[(i / cols) * ld + (i % cols)] = T(0);
 }
 
+// Two vectors per lane on a half-width team (LPR = half the row's vectors): one gather instruction of the warp
+// fetches 2 * SPLIT half rows, so a lane keeps 8 independent 16-byte loads in flight for the shuffle / address
+// work of 4.  Costs registers: MB resident CTAs per SM (80 / 96 registers) instead of 8 (64).  Measured on B200
+// (profiles/README.md, r01 v5 sweep): -12 % on 256-byte rows (fp32 n = 64), -11 % on 512-byte fp32 rows, -4 % fp64.
+template <typename T, int V, int LPR, bool COLMAJOR>
+static int launch_two(SpmmArgs &args, int row_blocks, cudaStream_t stream)
+{
+    constexpr int MB = sizeof(T) == 4 ? 6 : 5;
+    constexpr int NB = LPR * V * 2;
+    dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
+    MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB>), grid, SPMM_THREADS, 0, stream, args);
+    return MXG_OK;
+}
+
 template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR>
 static int launch_variant(SpmmArgs &args, int row_blocks, cudaStream_t stream)
 {
@@ -515,6 +529,17 @@ static int dispatch_geom(int lpr, int cpl, SpmmArgs &args, cudaStream_t stream)
     args.rpw = rpw;
     args.piece_blocks = ceil_div_i(args.n_pieces, SPMM_WARPS);
     const int row_blocks = ceil_div_i(args.m, SPMM_WARPS * rpw);
+    if (cpl == 2 && lpr < 32) {
+        if constexpr (V > 1) {
+            if (args.n_panels <= 1) {
+                if (lpr == 4) return launch_two<T, V, 4, COLMAJOR>(args, row_blocks, stream);
+                if (lpr == 8) return launch_two<T, V, 8, COLMAJOR>(args, row_blocks, stream);
+                if (lpr == 16) return launch_two<T, V, 16, COLMAJOR>(args, row_blocks, stream);
+            }
+        }
+        lpr *= 2; // column panels / scalar path: the one-vector geometry
+        cpl = 1;
+    }
 #define MXG_GEOM(L, C)                                                                                   \
     if (lpr == L && cpl == C) return launch_variant<T, V, L, C, 4, COLMAJOR>(args, row_blocks, stream);
     MXG_GEOM(4, 1) MXG_GEOM(8, 1) MXG_GEOM(16, 1) MXG_GEOM(32, 1) MXG_GEOM(32, 2)
@@ -609,7 +634,14 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
         if (lpr < 4) lpr = 4;
         if (lpr > 32) lpr = 32;
     }
-    const int cpl = (lpr == 32 && nvec > 32) ? 2 : 1;
+    int cpl = (lpr == 32 && nvec > 32) ? 2 : 1;
+    // rows of B of more than 128 bytes: half-width teams with two vectors per lane (launch_two); option spmm_cpl
+    // forces one (1) or two (2) vectors per lane for sweeps and tests
+    const long want_cpl = options().spmm_cpl;
+    if (vec && cpl == 1 && lpr >= 8 && want_cpl != 1 && (nvec > 8 || want_cpl == 2) && options().spmm_lpr <= 0) {
+        lpr /= 2;
+        cpl = 2;
+    }
 
     SpmmArgs args;
     args.m = A->m;

@@ -223,4 +223,60 @@ int synth_csr_arrays(int m, int K, int64_t target_nnz, int row_model, int col_mo
     return MXG_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Measurement probe (tools/sweep.py --what gatherroof): the fastest this GPU can fetch RANDOM rows of
+// `row_bytes` (128 / 256 / 512) from a table of `rows` rows — the access pattern of the dense-operand
+// gathers of K1/K2 with nothing else attached (no CSR stream, no FMAs, no output): one team of
+// row_bytes/16 lanes per row, 8 independent 16-byte loads in flight per lane, row ids from a hash of a
+// counter.  With a table far larger than L2 this is the DRAM random-access roof for that row size, with a
+// table inside L2 the L2->SM gather roof.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t probe_hash(uint64_t v)
+{
+    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+    return (uint32_t)v;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) k_gather_probe(const float4 *__restrict__ table, uint32_t rows, size_t row_vec,
+                                                      long long gathers_per_team, uint64_t seed, float *sink)
+{
+    constexpr int U = 8;
+    const int l = threadIdx.x % LPR;
+    const uint64_t team = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long g = 0; g < gathers_per_team; g += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t r = (uint32_t)(((uint64_t)probe_hash(seed + team * 0x9E3779B97F4A7C15ULL + (uint64_t)(g + u)) * rows) >> 32);
+            v[u] = __ldg(table + (size_t)r * row_vec + l);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x; // never true: keeps the loads alive
+}
+
+int gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed, float *d_sink,
+                 cudaStream_t stream)
+{
+    if (rows == 0 || rows > 0xffffffffULL || gathers <= 0) return fail(MXG_ERR_ARG, "gather_probe: bad size");
+    const int lpr = row_bytes / 16;
+    const int grid = 148 * 8;
+    const long long teams = (long long)grid * 256 / lpr;
+    const long long per_team = std::max<long long>(8, (gathers / teams + 7) / 8 * 8);
+    const float4 *t = static_cast<const float4 *>(d_table);
+    switch (lpr) {
+    case 8: MXG_LAUNCH(k_gather_probe<8>, grid, 256, 0, stream, t, (uint32_t)rows, (size_t)lpr, per_team, seed, d_sink); break;
+    case 16: MXG_LAUNCH(k_gather_probe<16>, grid, 256, 0, stream, t, (uint32_t)rows, (size_t)lpr, per_team, seed, d_sink); break;
+    case 32: MXG_LAUNCH(k_gather_probe<32>, grid, 256, 0, stream, t, (uint32_t)rows, (size_t)lpr, per_team, seed, d_sink); break;
+    default: return fail(MXG_ERR_ARG, "gather_probe: row_bytes must be 128, 256 or 512");
+    }
+    return MXG_OK;
+}
+
 } // namespace mxg

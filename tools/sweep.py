@@ -76,6 +76,36 @@ def main():
                 A.free()
             _lib.set_option("piece", 1024)
 
+    if "cpl" in what:
+        # one vs two vectors per lane (half-width teams) across row widths, types and result layouts
+        A = DeviceCSR.synth(m, K, wl["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32 | MXG_KEEP_F64)
+        for rep in range(2):
+            for dt, nn in ((MXG_F32, 64), (MXG_F32, 128), (MXG_F32, 96), (MXG_F32, 40), (MXG_F32, 32), (MXG_F64, 32),
+                           (MXG_F64, 64), (MXG_F64, 16)):
+                for layout in (MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS):
+                    for cpl in (1, 2):
+                        spmm_case(A, dt, layout, nn, "cpl", spmm_cpl=cpl)
+        A.free()
+
+    if "gatherroof" in what:
+        # random-row gathers with nothing attached: the roof of the dense-operand gathers of K1/K2
+        import ctypes as C
+        sink = torch.zeros(4, device="cuda", dtype=torch.float32)
+        for table_mb in (32, 256, 512, 2048, 8192):
+            table = torch.randn(table_mb * (1 << 20) // 4, device="cuda", dtype=torch.float32)
+            for row_bytes in (128, 256, 512):
+                rows = table.numel() * 4 // row_bytes
+                done = C.c_longlong(0)
+                gathers = 200_000_000 * 256 // row_bytes // 2
+
+                def probe():
+                    _lib.call("mxg_dev_gather_probe", row_bytes, C.c_void_p(table.data_ptr()), rows, gathers, 12345,
+                              C.c_void_p(sink.data_ptr()), C.byref(done), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                ms = _time_ms(probe, args.steps, 3)
+                emit(case="gather_probe", table_mb=table_mb, row_bytes=row_bytes, gathers=done.value, ms=ms,
+                     gather_TBps=done.value * row_bytes / ms / 1e9, Ggathers_per_s=done.value / ms / 1e6)
+            del table
+
     if "l2res" in what:
         # the same product with a dense operand that fits L2: the ceiling column-panel tiling could reach
         for KK in (62_500, 125_000, 250_000, 500_000):
