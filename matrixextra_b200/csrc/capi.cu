@@ -294,6 +294,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmm_cpl")) return &o.spmm_cpl;
+    if (!strcmp(name, "radix_bits")) return &o.radix_bits;
     if (!strcmp(name, "host_threads")) return &o.host_threads;
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
     if (!strcmp(name, "host_stage")) return &o.host_stage;

@@ -51,6 +51,7 @@ struct Options {
     long spmm_panel_cols = 0; // force a panel width in columns of A (tests / sweeps); 0 = by size
     long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
     long spmm_cpl = 0;        // vectors per lane of the SpMM teams: 0 = auto (2 when a row of B exceeds 128 bytes), 1, 2
+    long radix_bits = 8;      // CSR->CSC: largest digit of the radix passes (4 .. 10 bits)
     long spmv_lpr = 0;        // 0 = auto
     long svec_smem = 1;       // sparse-vector product: keep the presence bitmap in shared memory when it fits (<= 200 KB)
     long spmv_tex = 1;        // gather a numeric y through the texture path (7 % faster than LDG on cfg2); 0 = plain loads

@@ -8,8 +8,12 @@
 //   1. histogram  : count[c] = entries in column c (integer atomics commute => deterministic; accumulated by the
 //                   last radix pass, one atomic per run of equal ids in a tile), exclusive scan -> p2[K+1];
 //   2. row expand : rowid[e] = r for e in [p[r], p[r+1]);
-//   3. stable LSD radix sort of the records (column key, row id, value) by 8-bit digits of the key,
-//      least significant first, ceil(log2(K)/8) passes.  Per pass:
+//   3. stable LSD radix sort of the records (column key, row id, value) by digits of the key, least significant
+//      first: ceil(log2(K) / radix_bits) passes of equal width (option "radix_bits", default 8: 19 bits -> 7+7+5).
+//      The kernels take digits of up to 10 bits (two passes for K <= 2^20), but measured on B200 a 1024-bin pass
+//      costs 1.9 ms against 1.12 ms for a 128/256-bin pass (4-entry runs per digit and tile: twice the store
+//      sectors, more shared-memory conflicts), so 2 x 10 bits (4.75 ms on cfg4) loses to 3 x 7 bits (4.48 ms).
+//      Per pass:
 //        a) per-tile digit histogram (4096-entry tiles), b) exclusive scan over (digit, tile),
 //        c) scatter: every warp ranks its 32 consecutive entries with __match_any_sync against
 //           per-warp digit counters, so ranks follow entry order (=> each pass is stable); the tile is
@@ -17,6 +21,8 @@
 //           coalesced stores.  The last pass writes straight into i2 / x2.
 // All of it is HBM-bound integer/byte traffic; nothing here belongs on tensor cores.
 #include "mxg_internal.cuh"
+
+#include <algorithm>
 
 namespace mxg {
 
@@ -86,28 +92,31 @@ __global__ void __launch_bounds__(256) k_expand_rows(int m, const int32_t *__res
 constexpr int RS_THREADS = 512;                   // scatter CTA: 16 warps keep enough loads in flight at 2 CTAs / SM
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_STEPS = 8;                       // 32-entry steps per warp
-constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;      // 512 consecutive entries per warp
+constexpr int RS_WARP_ITEMS = 32 * RS_STEPS;      // 256 consecutive entries per warp
 constexpr int RS_TILE = RS_WARPS * RS_WARP_ITEMS; // 4096 entries per CTA
-constexpr int RS_BINS = 256;
-constexpr int RS_HIST_THREADS = RS_BINS;          // histogram CTA: one thread per bin
+constexpr int RS_MAX_BITS = 10;                   // widest digit the kernels support (see the header: 7-8 bits is faster)
+constexpr int RS_BINS = 1 << RS_MAX_BITS;
+constexpr int RS_HIST_THREADS = 256;
+constexpr int RS_DPT = RS_BINS / RS_THREADS;      // digits per thread in the tile-local scan (2)
+typedef unsigned short rs_cnt_t;                  // per-warp digit counters (<= RS_WARP_ITEMS) live in 16 bits
 
-// a) digit histogram of every tile, written digit-major: hist[d * ntiles + tile]
-__global__ void __launch_bounds__(RS_HIST_THREADS) k_radix_hist(size_t n, const int32_t *__restrict__ keys, int shift,
+// a) digit histogram of every tile, written digit-major: hist[d * ntiles + tile], d < nbins = 1 << nbits
+__global__ void __launch_bounds__(RS_HIST_THREADS) k_radix_hist(size_t n, const int32_t *__restrict__ keys, int shift, int nbins,
                                                                 int32_t *__restrict__ hist, int ntiles)
 {
     __shared__ int bins[RS_BINS];
-    bins[threadIdx.x] = 0;
+    for (int d = threadIdx.x; d < nbins; d += RS_HIST_THREADS) bins[d] = 0;
     __syncthreads();
     const size_t t0 = (size_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
     for (int k = 0; k < RS_TILE / RS_HIST_THREADS; k++) {
         const size_t e = t0 + (size_t)k * RS_HIST_THREADS + threadIdx.x;
         if (e < n) {
-            atomicAdd(&bins[(__ldg(keys + e) >> shift) & (RS_BINS - 1)], 1);
+            atomicAdd(&bins[(__ldg(keys + e) >> shift) & (nbins - 1)], 1);
         }
     }
     __syncthreads();
-    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = bins[threadIdx.x];
+    for (int d = threadIdx.x; d < nbins; d += RS_HIST_THREADS) hist[(size_t)d * ntiles + blockIdx.x] = bins[d];
 }
 
 struct RadixIO {
@@ -124,25 +133,30 @@ struct RadixIO {
 
 constexpr size_t radix_smem_bytes(bool h64, bool h32)
 {
-    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(int) * (RS_WARPS * RS_BINS + 2 * RS_BINS);
+    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(rs_cnt_t) * RS_WARPS * RS_BINS +
+           sizeof(int) * 2 * RS_BINS;
 }
 
 // c) stable scatter.  offs = exclusive scan of hist (digit-major): first destination of (digit, tile).
 template <bool H64, bool H32>
-__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const RadixIO io, int shift,
-                                                              const int32_t *__restrict__ offs, int ntiles)
+__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const RadixIO io, int shift, int nbins,
+                                                                 const int32_t *__restrict__ offs, int ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_x64 = reinterpret_cast<double *>(smem_raw);                                   // [RS_TILE] if H64
     int *s_key = reinterpret_cast<int *>(smem_raw + (H64 ? (size_t)RS_TILE * 8 : 0));       // [RS_TILE]
     int *s_row = s_key + RS_TILE;                                                            // [RS_TILE]
     float *s_x32 = reinterpret_cast<float *>(s_row + RS_TILE);                               // [RS_TILE] if H32
-    int *wcnt = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));              // [RS_WARPS][RS_BINS]
-    int *dig_off = wcnt + RS_WARPS * RS_BINS;                                                // [RS_BINS] tile-local digit starts
+    int *dig_off = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));           // [RS_BINS] tile-local digit starts
     int *gdelta = dig_off + RS_BINS;                                                         // [RS_BINS] global - local
+    rs_cnt_t *wcnt = reinterpret_cast<rs_cnt_t *>(gdelta + RS_BINS);                         // [RS_WARPS][RS_BINS]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) wcnt[i] = 0;
+    const int mask = nbins - 1;
+    {
+        unsigned *z = reinterpret_cast<unsigned *>(wcnt);
+        for (int i = threadIdx.x; i < RS_WARPS * RS_BINS / 2; i += RS_THREADS) z[i] = 0u;
+    }
     __syncthreads();
 
     const size_t t0 = (size_t)blockIdx.x * RS_TILE;
@@ -150,53 +164,64 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
     int key[RS_STEPS];
     int rank[RS_STEPS]; // rank of the entry among same-digit entries of this warp, in entry order
     const unsigned lt_mask = (1u << lane) - 1u;
-    int *my_cnt = wcnt + warp * RS_BINS;
+    rs_cnt_t *my_cnt = wcnt + warp * RS_BINS;
 #pragma unroll
     for (int s = 0; s < RS_STEPS; s++) {
         const size_t e = w0 + (size_t)s * 32 + lane;
         const bool valid = e < n;
         key[s] = valid ? __ldg(io.keys_in + e) : 0;
-        // invalid lanes get a digit no real lane can have (bit 8 set) so they never match a real one
-        const int d = valid ? ((key[s] >> shift) & (RS_BINS - 1)) : RS_BINS;
+        // invalid lanes get a digit no real lane can have (bit RS_MAX_BITS set) so they never match a real one
+        const int d = valid ? ((key[s] >> shift) & mask) : RS_BINS;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         int before = 0;
         if (valid) before = my_cnt[d];
         __syncwarp();
         rank[s] = before + __popc(peers & lt_mask);
-        if (valid && (peers & lt_mask) == 0) my_cnt[d] = before + __popc(peers); // lowest peer updates
+        if (valid && (peers & lt_mask) == 0) my_cnt[d] = (rs_cnt_t)(before + __popc(peers)); // lowest peer updates
         __syncwarp();
     }
     __syncthreads();
     // per-warp counts -> per-warp starts inside the digit; digit totals -> tile-local digit starts.
-    // One thread per digit (the first RS_BINS threads = the first RS_BINS / 32 warps); everybody meets at the barriers.
-    __shared__ int warp_tot[RS_BINS / 32];
-    int run = 0, incl = 0;
-    if (threadIdx.x < RS_BINS) {
-        const int d = threadIdx.x;
+    // Thread t owns the RS_DPT consecutive digits t * RS_DPT ..; everybody meets at the barriers.
+    __shared__ int warp_tot[RS_WARPS];
+    int run[RS_DPT];
+    int mine = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            const int c = wcnt[w * RS_BINS + d];
-            wcnt[w * RS_BINS + d] = run;
-            run += c;
-        }
-        incl = run; // warp-wide inclusive scan of the digit totals
+    for (int q = 0; q < RS_DPT; q++) {
+        const int d = threadIdx.x * RS_DPT + q;
+        run[q] = 0;
+        if (d < nbins) {
 #pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, dd);
-            if (lane >= dd) incl += t;
+            for (int w = 0; w < RS_WARPS; w++) {
+                const int c = wcnt[w * RS_BINS + d];
+                wcnt[w * RS_BINS + d] = (rs_cnt_t)run[q];
+                run[q] += c;
+            }
         }
-        if (lane == 31) warp_tot[warp] = incl;
+        mine += run[q];
     }
-    __syncthreads();
-    if (threadIdx.x < RS_BINS) {
-        const int d = threadIdx.x;
-        int wbase = 0;
+    int incl = mine; // warp-wide inclusive scan of the per-thread digit totals
 #pragma unroll
-        for (int w = 0; w < RS_BINS / 32; w++)
-            if (w < warp) wbase += warp_tot[w];
-        const int excl = wbase + incl - run;
-        dig_off[d] = excl;
-        gdelta[d] = offs[(size_t)d * ntiles + blockIdx.x] - excl;
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= dd) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    {
+        int excl = incl - mine;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++)
+            if (w < warp) excl += warp_tot[w];
+#pragma unroll
+        for (int q = 0; q < RS_DPT; q++) {
+            const int d = threadIdx.x * RS_DPT + q;
+            if (d < nbins) {
+                dig_off[d] = excl;
+                gdelta[d] = offs[(size_t)d * ntiles + blockIdx.x] - excl;
+                excl += run[q];
+            }
+        }
     }
     __syncthreads();
     // re-order the tile by digit in shared memory (payload read coalesced from global)
@@ -204,7 +229,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
     for (int s = 0; s < RS_STEPS; s++) {
         const size_t e = w0 + (size_t)s * 32 + lane;
         if (e < n) {
-            const int d = (key[s] >> shift) & (RS_BINS - 1);
+            const int d = (key[s] >> shift) & mask;
             const int pos = dig_off[d] + my_cnt[d] + rank[s];
             s_key[pos] = key[s];
             s_row[pos] = __ldg(io.rows_in + e);
@@ -216,7 +241,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
     const int tile_n = (int)((n - t0) < (size_t)RS_TILE ? (n - t0) : (size_t)RS_TILE);
     for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
         const int k = s_key[i];
-        const int dst = i + gdelta[(k >> shift) & (RS_BINS - 1)];
+        const int dst = i + gdelta[(k >> shift) & mask];
         if (io.keys_out) io.keys_out[dst] = k;
         io.rows_out[dst] = s_row[i];
         if (H64) io.x64_out[dst] = s_x64[i];
@@ -237,7 +262,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(size_t n, const Ra
 }
 
 template <bool H64, bool H32>
-static int launch_radix_scatter(size_t n, const RadixIO &io, int shift, const int32_t *offs, int ntiles, cudaStream_t stream)
+static int launch_radix_scatter(size_t n, const RadixIO &io, int shift, int nbins, const int32_t *offs, int ntiles,
+                                cudaStream_t stream)
 {
     constexpr size_t smem = radix_smem_bytes(H64, H32);
     static bool configured = false;
@@ -245,7 +271,7 @@ static int launch_radix_scatter(size_t n, const RadixIO &io, int shift, const in
         MXG_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<H64, H32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    MXG_LAUNCH((k_radix_scatter<H64, H32>), ntiles, RS_THREADS, smem, stream, n, io, shift, offs, ntiles);
+    MXG_LAUNCH((k_radix_scatter<H64, H32>), ntiles, RS_THREADS, smem, stream, n, io, shift, nbins, offs, ntiles);
     return MXG_OK;
 }
 
@@ -282,10 +308,14 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     // LSD radix passes over the column key, records = (key, row, values)
     int bits = 0;
     while (bits < 31 && ((int64_t)1 << bits) < (int64_t)K) bits++;
-    int passes = (bits + 7) / 8;
-    if (passes < 1) passes = 1;
+    if (bits < 1) bits = 1;
+    // as few passes as the digit width allows, split evenly
+    int max_bits = (int)options().radix_bits;
+    if (max_bits < 4 || max_bits > RS_MAX_BITS) max_bits = 8;
+    const int passes = (bits + max_bits - 1) / max_bits;
+    const int digit_bits = (bits + passes - 1) / passes;
     const int ntiles = ceil_div_i(nnz, RS_TILE);
-    const size_t hist_n = (size_t)RS_BINS * (size_t)ntiles;
+    const size_t hist_n = ((size_t)1 << digit_bits) * (size_t)ntiles;
     int32_t *d_hist = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_hist, sizeof(int32_t) * hist_n, stream));
     // ping-pong record buffers (only as many as the pass count needs)
@@ -304,7 +334,10 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     io.x64_in = x64;
     io.x32_in = x32;
     for (int pass = 0; pass < passes; pass++) {
-        const int shift = pass * 8;
+        const int shift = pass * digit_bits;
+        const int nbits = std::min(digit_bits, bits - shift);
+        const int nbins = 1 << nbits;
+        const size_t hist_used = (size_t)nbins * (size_t)ntiles;
         const bool last = pass == passes - 1;
         const Rec &o = buf[pass & 1];
         io.keys_out = last ? nullptr : o.key;
@@ -312,13 +345,13 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
         io.x64_out = last ? d_x64o : o.x64;
         io.x32_out = last ? d_x32o : o.x32;
         io.col_count = last ? d_count : nullptr;
-        MXG_LAUNCH(k_radix_hist, ntiles, RS_HIST_THREADS, 0, stream, n, io.keys_in, shift, d_hist, ntiles);
-        MXG_TRY(exclusive_scan_i32(d_hist, d_hist, hist_n, stream));
+        MXG_LAUNCH(k_radix_hist, ntiles, RS_HIST_THREADS, 0, stream, n, io.keys_in, shift, nbins, d_hist, ntiles);
+        MXG_TRY(exclusive_scan_i32(d_hist, d_hist, hist_used, stream));
         int rc;
-        if (h64 && h32) rc = launch_radix_scatter<true, true>(n, io, shift, d_hist, ntiles, stream);
-        else if (h64) rc = launch_radix_scatter<true, false>(n, io, shift, d_hist, ntiles, stream);
-        else if (h32) rc = launch_radix_scatter<false, true>(n, io, shift, d_hist, ntiles, stream);
-        else rc = launch_radix_scatter<false, false>(n, io, shift, d_hist, ntiles, stream);
+        if (h64 && h32) rc = launch_radix_scatter<true, true>(n, io, shift, nbins, d_hist, ntiles, stream);
+        else if (h64) rc = launch_radix_scatter<true, false>(n, io, shift, nbins, d_hist, ntiles, stream);
+        else if (h32) rc = launch_radix_scatter<false, true>(n, io, shift, nbins, d_hist, ntiles, stream);
+        else rc = launch_radix_scatter<false, false>(n, io, shift, nbins, d_hist, ntiles, stream);
         MXG_TRY(rc);
         io.keys_in = io.keys_out;
         io.rows_in = io.rows_out;

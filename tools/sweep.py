@@ -141,8 +141,19 @@ def main():
         def tr():
             t = A.transpose(keep=MXG_KEEP_F64)
             t.free()
-        ms = _time_ms(tr, 3, 1)
-        emit(case="cfg4_transpose", ms=ms, alg_gbps=(24 * A.nnz + 4 * (A.m + A.K + 2)) / ms / 1e6)
+        for rb in (5, 6, 7, 8, 9, 10, 7, 8, 10):
+            _lib.set_option("radix_bits", rb)
+            ms = _time_ms(tr, 5, 2)
+            emit(case="cfg4_transpose", radix_bits=rb, ms=ms, alg_gbps=(24 * A.nnz + 4 * (A.m + A.K + 2)) / ms / 1e6)
+        _lib.set_option("radix_bits", 8)
+        A.free()
+        w3 = WORKLOADS["cfg3"]
+        A = DeviceCSR.synth(w3["m"], w3["K"], w3["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32)
+        for rb in (7, 8, 10):
+            _lib.set_option("radix_bits", rb)
+            ms = _time_ms(lambda: A.transpose(keep=MXG_KEEP_F32).free(), 5, 2)
+            emit(case="cfg3_matrix_transpose_f32", radix_bits=rb, ms=ms)
+        _lib.set_option("radix_bits", 8)
         A.free()
 
     # raw copy bandwidth on this box for context (same method as MEASURED_PEAKS.json)
