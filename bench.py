@@ -56,9 +56,9 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
 # `ncu --set full` captures of exactly these workloads (profiles/README.md); None where no capture exists.
 NCU_TRAFFIC = {
-    "cfg3": (15.631161e9 + 0.518237e9, "profiles/r01_v3_spmm_f32_k64_cfg3.ncu.txt"),
-    "k64f64": (39.178352e9 + 1.051749e9, "profiles/r01_v3_spmm_f64_k64.ncu.txt"),
-    "cfg2": (1.220731e9 + 0.018394e9, "profiles/r01_v3_spmv_f64_cfg2.ncu.txt"),
+    "cfg3": (15.562139e9 + 0.517222e9, "profiles/r01_v5_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": (39.131198e9 + 1.028578e9, "profiles/r01_v5_spmm_f64_k64.ncu.txt"),
+    "cfg2": (1.220707e9 + 0.019601e9, "profiles/r01_v5_spmv_f64_cfg2.ncu.txt"),
 }
 
 

@@ -4,6 +4,7 @@
  * way R hands it SEXPs (borrowed, column-major, float32 as int bits) and copy the returned object out.
  * Return value: 0, or 1 with the R error message in gluedrv_last_error(). */
 #include "../rglue/matmul_gpu_glue.cpp"
+#include "../rglue/rowops_gpu_glue.cpp"
 
 #include <cstring>
 #include <string>
@@ -107,6 +108,79 @@ int gluedrv_csr_to_csc(const int *p, int m, const int *j, const double *x, int n
             std::memcpy(i2, r.entries[1].data, sizeof(int) * r.entries[1].size);
             std::memcpy(x2, r.entries[2].data, sizeof(double) * r.entries[2].size);
         }
+    });
+}
+
+/* ---- rglue/rowops_gpu_glue.cpp ---- */
+
+/* CSR %*% sparseVector; ytype as in mxgpu.h (4 = binary: yv ignored) */
+int gluedrv_csr_svec(int ytype, const int *p, int m, const int *j, const double *x, int nnz, const int *yi, int ny,
+                     const void *yv, double *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz), YI((int *)yi, (size_t)ny);
+        NV V((double *)x, (size_t)nnz);
+        switch (ytype) {
+        case 0: copy_out(matmul_csr_svec_numeric(P, J, V, YI, NV((double *)yv, (size_t)ny), 1), out); break;
+        case 1: copy_out(matmul_csr_svec_integer(P, J, V, YI, IV((int *)yv, (size_t)ny), 1), out); break;
+        case 2: copy_out(matmul_csr_svec_logical(P, J, V, YI, LV((int *)yv, (size_t)ny), 1), out); break;
+        case 3: copy_out(matmul_csr_svec_float32(P, J, V, YI, IV((int *)yv, (size_t)ny), 1), out); break;
+        default: copy_out(matmul_csr_svec_binary(P, J, V, YI, 1), out); break;
+        }
+    });
+}
+
+int gluedrv_rows_sorted(const int *p, int m, const int *j, int nnz, int *sorted)
+{
+    return guarded([&] { *sorted = check_indices_are_unsorted(IV((int *)p, (size_t)m + 1), IV((int *)j, (size_t)nnz)) ? 1 : 0; });
+}
+
+/* in place on the caller's arrays (the vectors borrow them); x == NULL: pattern matrix */
+int gluedrv_sort_indices(const int *p, int m, int *j, double *x, int nnz)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J(j, (size_t)nnz);
+        if (x) sort_sparse_indices_numeric(P, J, NV(x, (size_t)nnz));
+        else sort_sparse_indices_binary(P, J);
+    });
+}
+
+/* msg receives the list's "err" string ("" when the matrix is valid) */
+int gluedrv_check_valid(const int *p, int plen, const int *j, int nnz, int nrows, int ncols, char *msg, int cap)
+{
+    return guarded([&] {
+        Rcpp::List r = check_valid_csr_matrix(IV((int *)p, (size_t)plen), IV((int *)j, (size_t)nnz), nrows, ncols);
+        std::string e = r.entries.empty() ? std::string() : r.entries[0].str;
+        std::strncpy(msg, e.c_str(), (size_t)cap - 1);
+        msg[cap - 1] = 0;
+    });
+}
+
+/* elementwise CSR * dense matrix (flat column-major vector of length m * K); dtype 0 double, 1 int, 2 bool, 3 float32 */
+int gluedrv_mul_dense(int dtype, const int *p, int m, const int *j, const double *x, int nnz, const void *dense, long len,
+                      double *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        switch (dtype) {
+        case 0: copy_out(multiply_csr_by_dense_elemwise_double(P, J, V, NV((double *)dense, (size_t)len)), out); break;
+        case 1: copy_out(multiply_csr_by_dense_elemwise_int(P, J, V, IV((int *)dense, (size_t)len)), out); break;
+        case 2: copy_out(multiply_csr_by_dense_elemwise_bool(P, J, V, LV((int *)dense, (size_t)len)), out); break;
+        default: copy_out(multiply_csr_by_dense_elemwise_float32(P, J, V, IV((int *)dense, (size_t)len)), out); break;
+        }
+    });
+}
+
+int gluedrv_mul_dvec(const int *p, int m, const int *j, const double *x, int nnz, const double *dvec, long len, int ncols,
+                     int multiply, double *out)
+{
+    return guarded([&] {
+        IV P((int *)p, (size_t)m + 1), J((int *)j, (size_t)nnz);
+        NV V((double *)x, (size_t)nnz);
+        copy_out(multiply_csr_by_dvec_no_NAs_numeric(P, J, V, NV((double *)dvec, (size_t)len), ncols, multiply != 0, false,
+                                                     false, false, false, true),
+                 out);
     });
 }
 

@@ -23,6 +23,7 @@ def _build():
     from matrixextra_b200 import build_native
     build_native.build()
     srcs = [os.path.join(ROOT, "tests", "glue_driver.cpp"), os.path.join(ROOT, "rglue", "matmul_gpu_glue.cpp"),
+            os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp"),
             os.path.join(ROOT, "include", "mxgpu.h"), os.path.join(ROOT, "oracle", "shim", "Rcpp.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return LIB
@@ -136,3 +137,95 @@ def test_glue_vectors_and_transpose(drv, port):
     jb[7] = 300
     assert drv.gluedrv_csr_dvec(0, _p(p), 900, _p(jb), _p(x), j.size, _p(y), 300, _p(out)) == 1
     assert "column index" in drv.gluedrv_last_error().decode()
+
+
+# ---- rglue/rowops_gpu_glue.cpp: the exports either side of the product ----------------
+def test_rowops_glue_keeps_the_reference_export_names():
+    text = open(os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp")).read()
+    for name in ("matmul_csr_svec_numeric", "matmul_csr_svec_integer", "matmul_csr_svec_logical", "matmul_csr_svec_binary",
+                 "matmul_csr_svec_float32", "check_indices_are_unsorted", "sort_sparse_indices_numeric",
+                 "sort_sparse_indices_binary", "check_valid_csr_matrix", "multiply_csr_by_dense_elemwise_double",
+                 "multiply_csr_by_dense_elemwise_float32", "multiply_csr_by_dense_elemwise_int",
+                 "multiply_csr_by_dense_elemwise_bool", "multiply_csr_by_dvec_no_NAs_numeric"):
+        assert text.count(name + "(") >= 1, name
+    assert text.count("\n// [[Rcpp::export(rng = false)]]\n") == 14
+
+
+@pytest.mark.gpu
+def test_rowops_glue_sparse_vector_products(drv, port):
+    p, j, x = powerlaw_csr(700, 400, 12, seed=43, cap=380)
+    rng = np.random.default_rng(43)
+    yi = (np.sort(rng.choice(400, size=90, replace=False)) + 1).astype(np.int32)
+    out = np.empty(700)
+    yv = rng.standard_normal(90)
+    assert drv.gluedrv_csr_svec(0, _p(p), 700, _p(j), _p(x), j.size, _p(yi), 90, _p(yv), _p(out)) == 0
+    assert rel_err(out, port.matmul_csr_svec_numeric(p, j, x, yi, yv)) <= FP64_TOL
+    iv = rng.integers(-4, 5, 90).astype(np.int32)
+    iv[::7] = NA_INT
+    for ytype, fn in ((1, port.matmul_csr_svec_integer), (2, port.matmul_csr_svec_logical)):
+        assert drv.gluedrv_csr_svec(ytype, _p(p), 700, _p(j), _p(x), j.size, _p(yi), 90, _p(iv), _p(out)) == 0
+        want = fn(p, j, x, yi, iv)
+        assert np.array_equal(np.isnan(out), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert rel_err(out[ok], want[ok]) <= FP64_TOL
+    fv = rng.standard_normal(90).astype(np.float32)
+    assert drv.gluedrv_csr_svec(3, _p(p), 700, _p(j), _p(x), j.size, _p(yi), 90, _p(fv), _p(out)) == 0
+    assert rel_err(out, port.matmul_csr_svec_float32(p, j, x, yi, fv)) <= FP64_TOL
+    assert drv.gluedrv_csr_svec(4, _p(p), 700, _p(j), _p(x), j.size, _p(yi), 90, None, _p(out)) == 0
+    assert rel_err(out, port.matmul_csr_svec_binary(p, j, x, yi)) <= FP64_TOL
+
+
+@pytest.mark.gpu
+def test_rowops_glue_sort_validity_and_elementwise(drv, port):
+    p, j, x = powerlaw_csr(600, 500, 14, seed=44, cap=450)
+    rng = np.random.default_rng(44)
+    ju, xu = j.copy(), x.copy()
+    for r in range(0, 600, 3):  # shuffle every third row
+        a, b = p[r], p[r + 1]
+        perm = rng.permutation(b - a)
+        ju[a:b], xu[a:b] = ju[a:b][perm], xu[a:b][perm]
+    s = C.c_int(-1)
+    assert drv.gluedrv_rows_sorted(_p(p), 600, _p(j), j.size, C.byref(s)) == 0 and s.value == 1
+    assert drv.gluedrv_rows_sorted(_p(p), 600, _p(ju), j.size, C.byref(s)) == 0 and s.value == 0
+    js, xs = ju.copy(), xu.copy()
+    assert drv.gluedrv_sort_indices(_p(p), 600, _p(js), _p(xs), j.size) == 0  # in place, values follow
+    assert np.array_equal(js, j) and np.array_equal(xs, x)
+    js = ju.copy()
+    assert drv.gluedrv_sort_indices(_p(p), 600, _p(js), None, j.size) == 0    # pattern matrix
+    assert np.array_equal(js, j)
+    # validity: the reference's messages, first failing check first (src/misc.cpp:970-1016)
+    msg = C.create_string_buffer(256)
+    assert drv.gluedrv_check_valid(_p(p), p.size, _p(j), j.size, 600, 500, msg, 256) == 0 and msg.value == b""
+    jb = j.copy()
+    jb[5] = -1
+    assert drv.gluedrv_check_valid(_p(p), p.size, _p(jb), j.size, 600, 500, msg, 256) == 0
+    assert msg.value.decode() == "Matrix has negative indices."
+    assert msg.value.decode() == port.check_valid_csr_matrix(p, jb, 600, 500)
+    jb[5] = 500
+    assert drv.gluedrv_check_valid(_p(p), p.size, _p(jb), j.size, 600, 500, msg, 256) == 0
+    assert msg.value.decode() == "Matrix has invalid column indices."
+    pb = p.copy()
+    pb[10], pb[11] = pb[11], pb[10]
+    if pb[10] > pb[11]:
+        assert drv.gluedrv_check_valid(_p(pb), pb.size, _p(j), j.size, 600, 500, msg, 256) == 0
+        assert msg.value.decode() == "Matrix index pointer is not monotonicaly increasing."
+    # elementwise products: one multiply per entry, bit-exact
+    D = np.asfortranarray(rng.standard_normal((600, 500)))
+    out = np.empty(j.size)
+    assert drv.gluedrv_mul_dense(0, _p(p), 600, _p(j), _p(x), j.size, _p(D), C.c_long(D.size), _p(out)) == 0
+    assert np.array_equal(out, port.multiply_csr_by_dense_elemwise_double(p, j, x, D.ravel(order="F")))
+    Df = np.asfortranarray(D.astype(np.float32))
+    assert drv.gluedrv_mul_dense(3, _p(p), 600, _p(j), _p(x), j.size, _p(Df), C.c_long(Df.size), _p(out)) == 0
+    assert np.array_equal(out, port.multiply_csr_by_dense_elemwise_float32(p, j, x, Df.ravel(order="F")))
+    Di = np.asfortranarray(rng.integers(-3, 4, (600, 500)).astype(np.int32))
+    Di[::17, ::13] = NA_INT
+    for dtype, fn in ((1, port.multiply_csr_by_dense_elemwise_int), (2, port.multiply_csr_by_dense_elemwise_bool)):
+        assert drv.gluedrv_mul_dense(dtype, _p(p), 600, _p(j), _p(x), j.size, _p(Di), C.c_long(Di.size), _p(out)) == 0
+        want = fn(p, j, x, Di.ravel(order="F"))
+        assert np.array_equal(np.isnan(out), np.isnan(want))
+        assert np.array_equal(out[~np.isnan(want)], want[~np.isnan(want)])
+    v = rng.standard_normal(600)  # one value per row, recycled along the columns (R/operators.R:236-397)
+    assert drv.gluedrv_mul_dvec(_p(p), 600, _p(j), _p(x), j.size, _p(v), C.c_long(v.size), 500, 1, _p(out)) == 0
+    assert np.array_equal(out, port.multiply_csr_by_dvec_no_NAs_numeric(p, j, x, v, 500))
+    assert drv.gluedrv_mul_dvec(_p(p), 600, _p(j), _p(x), j.size, _p(v), C.c_long(v.size), 500, 0, _p(out)) == 1
+    assert "only the multiplication" in drv.gluedrv_last_error().decode()
