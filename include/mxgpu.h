@@ -257,9 +257,12 @@ int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
  * reference's `nthreads` argument of src/matmul.cpp:221-483 now controls; 0 = all logical CPUs up to 16).
  * mxg_host_narrow: dst[i] = (float)src[i], round-to-nearest-even — the reference's per-entry cast
  * (src/matmul.cpp:53-57) done once, before the values cross PCIe.  mxg_host_copy_2d: `height` lines of `width`
- * bytes between pitched host buffers (how pageable R memory enters and leaves the page-locked staging arena). */
+ * bytes between pitched host buffers (how pageable R memory enters and leaves the page-locked staging arena);
+ * streaming_stores != 0 writes the destination with cache-bypassing stores (used when it is a ring slot that the
+ * DMA engine reads next). */
 int mxg_host_narrow(const double *src, float *dst, size_t n);
-int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height);
+int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                     int streaming_stores);
 
 /* ============ synthetic inputs for bench.py / tests (device-side, counter-based RNG) ============
  * Power-law row lengths, stratified sorted unique columns; see DESIGN.md "Synthetic inputs". */

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "mxg_row_partition": [_i32, _vp, _i32, _vp],
     "mxg_dev_gather_probe": [_i32, _vp, _sz, C.c_longlong, C.c_uint64, _vp, C.POINTER(C.c_longlong), _vp],
     "mxg_host_narrow": [_vp, _vp, _sz],
-    "mxg_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz],
+    "mxg_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz, _i32],
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],
 }
 _RESTYPES = {"mxg_last_error": C.c_char_p, "mxg_launch_count": C.c_ulonglong, "mxg_csr_error_string": C.c_char_p}

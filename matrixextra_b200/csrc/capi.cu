@@ -117,17 +117,28 @@ static int upload_csr(int m, int K, const int32_t *p, const int32_t *j, const do
         MXG_UP_TRY(cudaStreamSynchronize(stream));
     }
     if (nnz > 0) {
-        MXG_UP_TRY(cudaMemcpyAsync(d_j, j + base, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+        // pageable (R) arrays are bounced through the page-locked arena by the host threads (hoststage.cu)
+        DeviceState *st = nullptr;
+        {
+            int rc = current_state(&st);
+            if (rc == MXG_OK) rc = staged_h2d(st, d_j, j + base, sizeof(int32_t) * (size_t)nnz, stream);
+            if (rc != MXG_OK) { free_handle(h); return rc; }
+        }
         if (want64) {
             MXG_UP_TRY(cudaMallocAsync(&d_x64, sizeof(double) * nz, stream));
             h->d_x64 = d_x64;
-            MXG_UP_TRY(cudaMemcpyAsync(d_x64, x + base, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, stream));
+            int rc = staged_h2d(st, d_x64, x + base, sizeof(double) * (size_t)nnz, stream);
+            if (rc != MXG_OK) { free_handle(h); return rc; }
         }
         if (want32) {
             MXG_UP_TRY(cudaMallocAsync(&d_x32, sizeof(float) * nz, stream));
             h->d_x32 = d_x32;
             if (d_x64) {
                 int rc = convert_f64_to_f32(d_x64, d_x32, (size_t)nnz, stream);
+                if (rc != MXG_OK) { free_handle(h); return rc; }
+            } else if (options().host_narrow != 0) {
+                // float32 only: narrowed by the host threads, 4 instead of 8 bytes per value over PCIe
+                int rc = staged_h2d_narrow(st, d_x32, x + base, (size_t)nnz, stream);
                 if (rc != MXG_OK) { free_handle(h); return rc; }
             } else {
                 // stage the float64 values through pool memory in chunks and narrow them on device (K6)
@@ -171,12 +182,24 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
         if (b_layout == MXG_ROWS_CONTIGUOUS) {
             if (ldb < n) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
             if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
-            MXG_CUDA_TRY(cudaMemcpy2DAsync(d_B, ld * s, B, ldb * s, n * s, K, cudaMemcpyHostToDevice, stream));
+            if (ld == n && ldb == n) {
+                DeviceState *st = nullptr;
+                MXG_TRY(current_state(&st));
+                MXG_TRY(staged_h2d(st, d_B, B, K * n * s, stream));
+            } else {
+                MXG_CUDA_TRY(cudaMemcpy2DAsync(d_B, ld * s, B, ldb * s, n * s, K, cudaMemcpyHostToDevice, stream));
+            }
         } else if (b_layout == MXG_COLS_CONTIGUOUS) {
             if (ldb < K) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
             void *d_tmp = nullptr;
             MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, K * n * s, stream));
-            MXG_CUDA_TRY(cudaMemcpy2DAsync(d_tmp, K * s, B, ldb * s, K * s, n, cudaMemcpyHostToDevice, stream));
+            if (ldb == K) {
+                DeviceState *st = nullptr;
+                MXG_TRY(current_state(&st));
+                MXG_TRY(staged_h2d(st, d_tmp, B, K * n * s, stream));
+            } else {
+                MXG_CUDA_TRY(cudaMemcpy2DAsync(d_tmp, K * s, B, ldb * s, K * s, n, cudaMemcpyHostToDevice, stream));
+            }
             if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
             // d_tmp is n rows of K contiguous -> d_B is K rows of n contiguous
             MXG_TRY(launch_transpose_dense((int)s, n, K, d_tmp, K, d_B, ld, stream));
@@ -216,10 +239,16 @@ static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, i
         return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
     }
     MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, stream));
-    if (out_layout == MXG_ROWS_CONTIGUOUS)
-        MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, (size_t)n * s, rows, cudaMemcpyDeviceToHost, stream));
-    else
-        MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, rows * s, (size_t)n, cudaMemcpyDeviceToHost, stream));
+    {
+        DeviceState *st = nullptr;
+        MXG_TRY(current_state(&st));
+        const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
+        const size_t width = rm ? (size_t)n * s : rows * s, height = rm ? rows : (size_t)n;
+        if (ldc * s == width && ld_o * s == width) // tight on both sides: one staged block copy
+            MXG_TRY(staged_d2h(st, Out, d_Out, width * height, stream));
+        else
+            MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, width, height, cudaMemcpyDeviceToHost, stream));
+    }
     MXG_CUDA_TRY(cudaFreeAsync(d_B, stream));
     MXG_CUDA_TRY(cudaFreeAsync(d_Out, stream));
     MXG_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -333,11 +362,12 @@ int mxg_host_narrow(const double *src, float *dst, size_t n)
     return MXG_OK;
 }
 
-int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height)
+int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
+                     int streaming_stores)
 {
     if (width > 0 && height > 0 && (!src || !dst)) return fail(MXG_ERR_ARG, "host_copy_2d: NULL buffer");
     if (height > 1 && (dpitch < width || spitch < width)) return fail(MXG_ERR_ARG, "host_copy_2d: pitch < width");
-    host_copy_2d(dst, dpitch, src, spitch, width, height);
+    host_copy_2d(dst, dpitch, src, spitch, width, height, streaming_stores != 0);
     return MXG_OK;
 }
 
@@ -976,11 +1006,11 @@ int mxg_csr2csc(int m, int K, const int32_t *p, const int32_t *j, const double *
     if (rc == MXG_OK) {
         cudaStream_t s = st->stream;
         auto body = [&]() -> int {
-            MXG_CUDA_TRY(cudaMemcpyAsync(p2, At->d_p, sizeof(int32_t) * ((size_t)K + 1), cudaMemcpyDeviceToHost, s));
+            MXG_TRY(staged_d2h(st, p2, At->d_p, sizeof(int32_t) * ((size_t)K + 1), s));
             if (At->nnz > 0) {
                 if (!i2) return fail(MXG_ERR_ARG, "i2 is NULL");
-                MXG_CUDA_TRY(cudaMemcpyAsync(i2, At->d_j, sizeof(int32_t) * (size_t)At->nnz, cudaMemcpyDeviceToHost, s));
-                if (vals) MXG_CUDA_TRY(cudaMemcpyAsync(x2, At->d_x64, sizeof(double) * (size_t)At->nnz, cudaMemcpyDeviceToHost, s));
+                MXG_TRY(staged_d2h(st, i2, At->d_j, sizeof(int32_t) * (size_t)At->nnz, s));
+                if (vals) MXG_TRY(staged_d2h(st, x2, At->d_x64, sizeof(double) * (size_t)At->nnz, s));
             }
             MXG_CUDA_TRY(cudaStreamSynchronize(s));
             return MXG_OK;

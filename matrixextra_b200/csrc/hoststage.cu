@@ -108,6 +108,36 @@ private:
     unsigned long long generation_ = 0;
 };
 
+// memcpy whose stores bypass the caches (destination = a ring slot the DMA engine reads next: no dirty lines to
+// snoop out of the cores, and the caller's data does not get evicted by a copy of itself)
+void copy_block_nt(char *d, const char *s, size_t n)
+{
+    size_t i = 0;
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+    if (head && head <= n) {
+        memcpy(d, s, head);
+        i = head;
+    }
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 48), e);
+    }
+    if (i < n) memcpy(d + i, s + i, n - i);
+    _mm_sfence();
+}
+
+inline void copy_block(char *d, const char *s, size_t n, bool nt)
+{
+    if (nt && n >= 256) copy_block_nt(d, s, n);
+    else memcpy(d, s, n);
+}
+
 void narrow_block(const double *s, float *d, size_t n)
 {
     size_t i = 0;
@@ -126,6 +156,18 @@ void narrow_block(const double *s, float *d, size_t n)
 
 } // namespace
 
+int host_threads();
+
+// Threads for a region that moves `bytes`: one per MiB up to the pool size.  Small regions stay on one or two
+// cores on purpose: lines of a slot that sit in many cores' caches make the DMA that follows snoop all of them
+// (measured on the B200 box: a 2.5 MB download into a slot last read by 16 threads takes 0.41 ms, by one thread
+// 0.055 ms), which costs a small call more than the parallel copy saves.
+static int threads_for(size_t bytes)
+{
+    const size_t want = std::max<size_t>(1, bytes >> 20);
+    return (int)std::min<size_t>(want, (size_t)host_threads());
+}
+
 int host_threads()
 {
     long t = options().host_threads;
@@ -139,43 +181,43 @@ int host_threads()
 
 void host_narrow_f64_to_f32(const double *src, float *dst, size_t n)
 {
-    const size_t grain = (size_t)1 << 17;
-    HostPool::get().run((n + grain - 1) / grain, host_threads(), [&](size_t t) {
+    const size_t grain = (size_t)1 << 15; // 256 KiB of doubles per task: small calls still spread over the pool
+    HostPool::get().run((n + grain - 1) / grain, threads_for(n * sizeof(double)), [&](size_t t) {
         const size_t a = t * grain, b = std::min(n, a + grain);
         narrow_block(src + a, dst + a, b - a);
     });
 }
 
-void host_copy(void *dst, const void *src, size_t bytes)
+void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst)
 {
-    const size_t grain = (size_t)1 << 20;
-    HostPool::get().run((bytes + grain - 1) / grain, host_threads(), [&](size_t t) {
+    const size_t grain = (size_t)1 << 18;
+    HostPool::get().run((bytes + grain - 1) / grain, threads_for(bytes), [&](size_t t) {
         const size_t a = t * grain, b = std::min(bytes, a + grain);
-        memcpy(static_cast<char *>(dst) + a, static_cast<const char *>(src) + a, b - a);
+        copy_block(static_cast<char *>(dst) + a, static_cast<const char *>(src) + a, b - a, nt_dst);
     });
 }
 
-void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height)
+void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, bool nt_dst)
 {
     if (width == 0 || height == 0) return;
     if (dpitch == width && spitch == width) {
-        host_copy(dst, src, width * height);
+        host_copy(dst, src, width * height, nt_dst);
         return;
     }
-    // tasks of about 1 MiB: several short lines, or a slice of a long one
-    const size_t target = (size_t)1 << 20;
+    // tasks of about 256 KiB: several short lines, or a slice of a long one
+    const size_t target = (size_t)1 << 18;
     if (width >= target) {
         const size_t per_line = (width + target - 1) / target;
-        HostPool::get().run(height * per_line, host_threads(), [&](size_t t) {
+        HostPool::get().run(height * per_line, threads_for(width * height), [&](size_t t) {
             const size_t line = t / per_line, a = (t % per_line) * target, b = std::min(width, a + target);
-            memcpy(static_cast<char *>(dst) + line * dpitch + a, static_cast<const char *>(src) + line * spitch + a, b - a);
+            copy_block(static_cast<char *>(dst) + line * dpitch + a, static_cast<const char *>(src) + line * spitch + a, b - a, nt_dst);
         });
     } else {
         const size_t lines = std::max<size_t>(1, target / width);
-        HostPool::get().run((height + lines - 1) / lines, host_threads(), [&](size_t t) {
+        HostPool::get().run((height + lines - 1) / lines, threads_for(width * height), [&](size_t t) {
             const size_t l0 = t * lines, l1 = std::min(height, l0 + lines);
             for (size_t l = l0; l < l1; l++)
-                memcpy(static_cast<char *>(dst) + l * dpitch, static_cast<const char *>(src) + l * spitch, width);
+                copy_block(static_cast<char *>(dst) + l * dpitch, static_cast<const char *>(src) + l * spitch, width, nt_dst);
         });
     }
 }
@@ -222,6 +264,119 @@ int pinned_arena_release(DeviceState *st)
         st->pin_base = nullptr;
         st->pin_bytes = 0;
     }
+    return MXG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Staged one-shot copies for the entry points that are not streamed chunk by chunk (handle uploads, crossprod,
+// CSR->CSC): the same bounce through the arena, 16 MiB blocks over a 4-slot ring on `stream`.  They return with
+// every slot idle again (the arena is shared with the streamed calls), i.e. after the last block has been copied.
+// Page-locked caller memory, or staging switched off, takes the plain cudaMemcpyAsync.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr size_t ST_BLOCK = (size_t)16 << 20;
+constexpr int ST_SLOTS = 4;
+
+struct StagedRing {
+    char *base = nullptr;
+    cudaEvent_t ev[ST_SLOTS] = {};
+    bool used[ST_SLOTS] = {};
+    int made = 0;
+    int init(DeviceState *st)
+    {
+        MXG_TRY(pinned_arena(st, ST_BLOCK * ST_SLOTS, &base));
+        for (; made < ST_SLOTS; made++) MXG_CUDA_TRY(cudaEventCreateWithFlags(&ev[made], cudaEventDisableTiming));
+        return MXG_OK;
+    }
+    ~StagedRing()
+    {
+        for (int i = 0; i < made; i++) {
+            if (used[i]) cudaEventSynchronize(ev[i]);
+            cudaEventDestroy(ev[i]);
+        }
+    }
+};
+
+bool use_staging(const void *host_ptr, size_t bytes)
+{
+    return options().host_stage != 0 && bytes >= ((size_t)1 << 20) && !host_is_pinned(host_ptr);
+}
+
+} // namespace
+
+int staged_h2d(DeviceState *st, void *d_dst, const void *src, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return MXG_OK;
+    if (!use_staging(src, bytes)) {
+        MXG_CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return MXG_OK;
+    }
+    StagedRing ring;
+    MXG_TRY(ring.init(st));
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += ST_BLOCK, k = (k + 1) % ST_SLOTS) {
+        const size_t len = std::min(ST_BLOCK, bytes - off);
+        if (ring.used[k]) MXG_CUDA_TRY(cudaEventSynchronize(ring.ev[k]));
+        char *slot = ring.base + (size_t)k * ST_BLOCK;
+        host_copy(slot, static_cast<const char *>(src) + off, len, /*nt_dst=*/true);
+        MXG_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, slot, len, cudaMemcpyHostToDevice, stream));
+        MXG_CUDA_TRY(cudaEventRecord(ring.ev[k], stream));
+        ring.used[k] = true;
+    }
+    return MXG_OK; // ~StagedRing waits for the copies still reading the slots
+}
+
+// float32 device array from float64 host values: narrowed by the host threads, half the bytes on the link
+int staged_h2d_narrow(DeviceState *st, float *d_dst, const double *src, size_t n, cudaStream_t stream)
+{
+    if (n == 0) return MXG_OK;
+    StagedRing ring;
+    MXG_TRY(ring.init(st));
+    const size_t block = ST_BLOCK / sizeof(float);
+    int k = 0;
+    for (size_t off = 0; off < n; off += block, k = (k + 1) % ST_SLOTS) {
+        const size_t len = std::min(block, n - off);
+        if (ring.used[k]) MXG_CUDA_TRY(cudaEventSynchronize(ring.ev[k]));
+        float *slot = reinterpret_cast<float *>(ring.base + (size_t)k * ST_BLOCK);
+        host_narrow_f64_to_f32(src + off, slot, len);
+        MXG_CUDA_TRY(cudaMemcpyAsync(d_dst + off, slot, sizeof(float) * len, cudaMemcpyHostToDevice, stream));
+        MXG_CUDA_TRY(cudaEventRecord(ring.ev[k], stream));
+        ring.used[k] = true;
+    }
+    return MXG_OK;
+}
+
+// device -> pageable host: blocks land in the ring and the host threads move them out (first touch in parallel)
+int staged_d2h(DeviceState *st, void *dst, const void *d_src, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return MXG_OK;
+    if (!use_staging(dst, bytes)) {
+        MXG_CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, stream));
+        return MXG_OK;
+    }
+    StagedRing ring;
+    MXG_TRY(ring.init(st));
+    const size_t nblocks = (bytes + ST_BLOCK - 1) / ST_BLOCK;
+    auto drain = [&](size_t b) -> int {
+        const int k = (int)(b % ST_SLOTS);
+        const size_t off = b * ST_BLOCK, len = std::min(ST_BLOCK, bytes - off);
+        MXG_CUDA_TRY(cudaEventSynchronize(ring.ev[k]));
+        ring.used[k] = false;
+        host_copy(static_cast<char *>(dst) + off, ring.base + (size_t)k * ST_BLOCK, len);
+        return MXG_OK;
+    };
+    for (size_t b = 0; b < nblocks; b++) {
+        const int k = (int)(b % ST_SLOTS);
+        if (b >= ST_SLOTS) MXG_TRY(drain(b - ST_SLOTS)); // the slot's previous block leaves first
+        const size_t off = b * ST_BLOCK, len = std::min(ST_BLOCK, bytes - off);
+        MXG_CUDA_TRY(cudaMemcpyAsync(ring.base + (size_t)k * ST_BLOCK, static_cast<const char *>(d_src) + off, len,
+                                     cudaMemcpyDeviceToHost, stream));
+        MXG_CUDA_TRY(cudaEventRecord(ring.ev[k], stream));
+        ring.used[k] = true;
+    }
+    for (size_t b = nblocks > ST_SLOTS ? nblocks - ST_SLOTS : 0; b < nblocks; b++) MXG_TRY(drain(b));
     return MXG_OK;
 }
 

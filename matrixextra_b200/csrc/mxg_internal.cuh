@@ -131,11 +131,16 @@ int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaS
 // hoststage.cu: worker threads + page-locked arena for pageable caller memory and host-side narrowing
 int host_threads();
 void host_narrow_f64_to_f32(const double *src, float *dst, size_t n);
-void host_copy(void *dst, const void *src, size_t bytes);
-void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height);
+// nt_dst: the destination is a ring slot the DMA engine reads next -> cache-bypassing stores
+void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst = false);
+void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, bool nt_dst = false);
 bool host_is_pinned(const void *ptr);
 int pinned_arena(DeviceState *st, size_t bytes, char **base);
 int pinned_arena_release(DeviceState *st);
+// one-shot staged copies (non-streamed entry points); every slot is idle again when they return
+int staged_h2d(DeviceState *st, void *d_dst, const void *src, size_t bytes, cudaStream_t stream);
+int staged_h2d_narrow(DeviceState *st, float *d_dst, const double *src, size_t n, cudaStream_t stream);
+int staged_d2h(DeviceState *st, void *dst, const void *d_src, size_t bytes, cudaStream_t stream);
 
 // layout.cu: device-side completion barrier between the GPUs of a box (bcast products)
 int launch_peer_barrier(int rank, int world, int *const *peer_flags, int epoch, cudaStream_t stream);

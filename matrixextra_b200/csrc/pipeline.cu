@@ -44,13 +44,33 @@ struct Trace {
         on = e && *e && *e != '0';
         t0 = std::chrono::steady_clock::now();
     }
+    cudaEvent_t g[4] = {nullptr, nullptr, nullptr, nullptr}; // GPU-side marks: start, last upload, last kernel, last download
+    void mark(int i, cudaStream_t s)
+    {
+        if (!on) return;
+        if (!g[i]) cudaEventCreate(&g[i]);
+        cudaEventRecord(g[i], s);
+    }
+    ~Trace()
+    {
+        for (cudaEvent_t e : g)
+            if (e) cudaEventDestroy(e);
+    }
     double now() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
     void report(const char *what, int chunks) const
     {
-        if (on)
-            fprintf(stderr, "[mxg trace] %s: %d chunks, total %.2f ms | plan %.2f | slot waits %.2f | host fill %.2f | "
-                            "out waits %.2f | out copies %.2f | finish %.2f\n",
-                    what, chunks, now(), plan_ms, wait_ms, fill_ms, drain_wait_ms, drain_ms, finish_ms);
+        if (!on) return;
+        float up = -1, comp = -1, down = -1;
+        if (g[0] && g[1] && g[2] && g[3]) {
+            cudaEventSynchronize(g[3]);
+            cudaEventElapsedTime(&up, g[0], g[1]);
+            cudaEventElapsedTime(&comp, g[1], g[2]);
+            cudaEventElapsedTime(&down, g[2], g[3]);
+        }
+        fprintf(stderr, "[mxg trace] %s: %d chunks, total %.2f ms | plan %.2f | slot waits %.2f | host fill %.2f | "
+                        "out waits %.2f | out copies %.2f | finish %.2f | gpu: uploads %.3f, last kernel after last upload %.3f, "
+                        "last download %.3f\n",
+                what, chunks, now(), plan_ms, wait_ms, fill_ms, drain_wait_ms, drain_ms, finish_ms, up, comp, down);
     }
 };
 
@@ -218,7 +238,7 @@ int upload_lines(InRing *ring, void *dst, size_t dpitch, const void *src, size_t
         const size_t nl = std::min(lines, height - l0);
         char *slot = nullptr;
         MXG_TRY(ring->acquire(&slot));
-        host_copy_2d(slot, width, static_cast<const char *>(src) + l0 * spitch, spitch, width, nl);
+        host_copy_2d(slot, width, static_cast<const char *>(src) + l0 * spitch, spitch, width, nl, /*nt_dst=*/true);
         MXG_TRY(copy_rows(static_cast<char *>(dst) + l0 * dpitch, dpitch, slot, width, width, nl, cudaMemcpyHostToDevice, stream));
         MXG_TRY(ring->release(stream));
     }
@@ -345,7 +365,7 @@ struct CsrStream {
                 MXG_CUDA_TRY(cudaMemcpyAsync(d_x32 + e0, slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
             } else {
                 if (stage_x) {
-                    host_copy(slot, x + e0, sizeof(double) * len);
+                    host_copy(slot, x + e0, sizeof(double) * len, /*nt_dst=*/true);
                     xsrc = slot;
                     if (g_trace) g_trace->fill_ms += g_trace->now() - tf;
                 }
@@ -360,7 +380,7 @@ struct CsrStream {
             const void *jsrc = j + e0;
             if (stage_j) {
                 const double tj = g_trace ? g_trace->now() : 0;
-                host_copy(slot + x_part, j + e0, sizeof(int32_t) * len);
+                host_copy(slot + x_part, j + e0, sizeof(int32_t) * len, /*nt_dst=*/true);
                 jsrc = slot + x_part;
                 if (g_trace) g_trace->fill_ms += g_trace->now() - tj;
             }
@@ -472,6 +492,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS) MXG_TRY(sc.alloc((void **)&d_tmp, Kz * nz * s));
     if (K > 0 && ld_b != nz) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, Kz * ld_b * s, st->stream));
     MXG_TRY(chain(sc, st->stream, st->h2d));
+    trace.mark(0, st->h2d);
     auto upload_dense = [&](InRing *ring) -> int {
         if (K == 0) return MXG_OK;
         if (b_layout == MXG_ROWS_CONTIGUOUS) return upload_lines(ring, d_B, ld_b * s, B, ldb * s, nz * s, Kz, st->h2d);
@@ -500,8 +521,10 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
         MXG_TRY(cs.prepare_chunk(c, h));
         const size_t r0 = (size_t)cs.plan.chunk_row[(size_t)c], nr = (size_t)h.m;
         char *d_o = d_Out + (rm ? r0 * ld_o * s : r0 * s);
+        if (c == C - 1) trace.mark(1, st->h2d);
         MXG_TRY(launch_spmm(&h, dtype, out_layout, n, d_B, ld_b, d_o, ld_o, st->stream));
         if (h.d_seg) MXG_CUDA_TRY(cudaFreeAsync(h.d_seg, st->stream)); // the chunk's column-panel table
+        if (c == C - 1) trace.mark(2, st->stream);
         MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)c], st->stream));
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
         const size_t width = rm ? nz * s : nr * s, height = rm ? nr : nz;
@@ -512,6 +535,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
             char *h_o = static_cast<char *>(Out) + (rm ? r0 * ldc * s : r0 * s);
             MXG_TRY(copy_rows(h_o, ldc * s, d_o, ld_o * s, width, height, cudaMemcpyDeviceToHost, st->d2h));
         }
+        if (c == C - 1) trace.mark(3, st->d2h);
         return MXG_OK;
     };
     auto drain = [&](int c) -> int {

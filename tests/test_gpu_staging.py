@@ -167,3 +167,55 @@ def test_bad_column_index_is_still_reported_through_the_staged_route(rx, options
     # and the library is usable afterwards
     j[len(j) // 2] = 0
     rx.tcrossprod_dense_csr_float32(X, p, j, x, 1, 200)
+
+
+def _big_random_csr(m, K, per_row, seed):
+    """Large enough (> 1 MiB per array) for the one-shot staged copies to engage."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(per_row // 2, per_row * 3 // 2, size=m)
+    p = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum(lens, out=p[1:])
+    j = np.empty(p[-1], dtype=np.int32)
+    for r in range(m):
+        j[p[r]:p[r + 1]] = np.sort(rng.choice(K, size=lens[r], replace=False))
+    return p, j, rng.uniform(-1, 1, size=p[-1])
+
+
+def test_one_shot_staged_copies_upload_crossprod_and_csr2csc(rx, port, options):
+    """Handle upload, crossprod (device transpose + product) and CSR->CSC through the staged one-shot copies:
+    identical bits with staging / host narrowing on and off, CSR->CSC equal to scipy's tocsc()."""
+    import scipy.sparse as sp
+    from matrixextra_b200._lib import MXG_F32, MXG_F64, MXG_KEEP_F32, MXG_KEEP_F64
+    from matrixextra_b200.device import DeviceCSR
+    m, K, n = 20_000, 3_000, 80  # ~400k entries: j 1.6 MB, x 3.2 MB, Y 6.4 MB (fp32) / 12.8 MB, result 1-2 MB
+    p, j, x = _big_random_csr(m, K, 20, seed=31)
+    assert j.nbytes > (1 << 20)
+    rng = np.random.default_rng(31)
+    Y = np.asfortranarray(rng.standard_normal((m, n)))
+    q2, k2, y2 = port.csr2csc(m, K, p, j, x)
+    want64 = port.matmul_dense_csc_numeric(np.asfortranarray(Y.T), q2, k2, y2).T
+    want32 = port.matmul_dense_csc_float32(np.asfortranarray(Y.T.astype(np.float32)), q2, k2, y2).T
+    ref = {}
+    for stage, narrow in ((1, 1), (1, 0), (0, 0)):
+        options.set_option("host_stage", stage)
+        options.set_option("host_narrow", narrow)
+        # level-2 upload: float32-only handles take the host-narrowing route
+        for keep in (MXG_KEEP_F64, MXG_KEEP_F32, MXG_KEEP_F64 | MXG_KEEP_F32):
+            A = DeviceCSR.upload(m, K, p, j, x, keep=keep)
+            pp, jj, xx = A.to_host()
+            A.free()
+            assert np.array_equal(pp, p) and np.array_equal(jj, j)
+            if keep & MXG_KEEP_F64:
+                assert np.array_equal(xx, x)
+            else:  # values come back widened from the float32 copy
+                assert np.array_equal(xx, x.astype(np.float32).astype(np.float64))
+        got64 = rx.crossprod_csr_dense(p, j, x, K, Y, MXG_F64)
+        got32 = rx.crossprod_csr_dense(p, j, x, K, Y.astype(np.float32), MXG_F32)
+        p2, i2, x2 = rx.csr_to_csc(m, K, p, j, x)
+        if not ref:
+            ref = dict(g64=got64.copy(), g32=got32.copy())
+            assert rel_err(got64, want64) <= FP64_TOL and rel_err(got32, want32) <= FP32_TOL
+            S = sp.csr_matrix((x, j, p), shape=(m, K)).tocsc()
+            assert np.array_equal(p2, S.indptr) and np.array_equal(i2, S.indices) and np.array_equal(x2, S.data)
+        assert np.array_equal(got64, ref["g64"]) and np.array_equal(got32, ref["g32"]), (stage, narrow)
+        assert np.array_equal(p2, q2) and np.array_equal(i2, k2) and np.array_equal(x2, y2)

@@ -93,12 +93,15 @@ def test_host_copy_2d_pitched_lines():
     rng = np.random.default_rng(5)
     for width, height, sp, dp in [(256, 70_000, 256, 256), (256, 5_000, 320, 272), (3 << 20, 3, (3 << 20) + 64, 3 << 20),
                                   (1, 1, 1, 1), (0, 10, 8, 8), (100, 1, 50, 60)]:
-        src = rng.integers(0, 255, size=max(sp * height, width, 1), dtype=np.uint8)
-        dst = np.full(max(dp * height, width, 1), 7, dtype=np.uint8)
-        _lib.call("mxg_host_copy_2d", _vp(dst), dp, _vp(src), sp, width, height)
-        want = np.full_like(dst, 7)
-        for l in range(height):
-            want[l * dp:l * dp + width] = src[l * sp:l * sp + width]
-        assert np.array_equal(dst, want)
+        for streaming, off in ((0, 0), (1, 0), (1, 5)):  # cache-bypassing stores too, also to an unaligned destination
+            src = rng.integers(0, 255, size=max(sp * height, width, 1), dtype=np.uint8)
+            buf = np.full(max(dp * height, width, 1) + 8, 7, dtype=np.uint8)
+            dst = buf[off:off + max(dp * height, width, 1)]
+            _lib.call("mxg_host_copy_2d", _vp(dst), dp, _vp(src), sp, width, height, streaming)
+            want = np.full_like(dst, 7)
+            for l in range(height):
+                want[l * dp:l * dp + width] = src[l * sp:l * sp + width]
+            assert np.array_equal(dst, want)
+            assert np.all(buf[:off] == 7) and np.all(buf[off + dst.size:] == 7)
     with pytest.raises(_lib.MxgError):
-        _lib.call("mxg_host_copy_2d", _vp(dst), 4, _vp(src), 4, 8, 2)
+        _lib.call("mxg_host_copy_2d", _vp(dst), 4, _vp(src), 4, 8, 2, 0)

@@ -54,7 +54,7 @@ def main():
         _lib.set_option("host_threads", t)
         ms = best(lambda: _lib.call("mxg_host_narrow", vp(x), vp(dst), n))
         emit(what="narrow 100M f64->f32 (touched dst)", threads=t, ms=ms, GBps_read_plus_write=1.2e9 / ms / 1e6)
-        ms = best(lambda: _lib.call("mxg_host_copy_2d", vp(dst8), 256, vp(src8), 256, 256, 2_000_000))
+        ms = best(lambda: _lib.call("mxg_host_copy_2d", vp(dst8), 256, vp(src8), 256, 256, 2_000_000, 0))
         emit(what="copy 512 MB (touched dst)", threads=t, ms=ms, GBps_read_plus_write=1.024e9 / ms / 1e6)
 
         def fresh(advise):
@@ -66,7 +66,7 @@ def main():
                 if rc != 0:
                     emit(madvise_errno=C.get_errno())
             t0 = time.perf_counter()
-            _lib.call("mxg_host_copy_2d", vp(out), 256, vp(src8), 256, 256, 2_000_000)
+            _lib.call("mxg_host_copy_2d", vp(out), 256, vp(src8), 256, 256, 2_000_000, 0)
             dt = time.perf_counter() - t0
             del out
             return dt * 1e3
