@@ -382,6 +382,15 @@ def run_ours(args):
                      "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
                      "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1] if world == 1 else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": w_alg,
+                     # the binding roof: HBM on the ACTUAL traffic of the launch (ncu dram bytes), which is
+                     # ~10x the algorithmic bytes because the dense operand overflows L2 and its rows are re-fetched
+                     "actual_traffic_GBps": (NCU_TRAFFIC[args.workload][0] / ms_kernel / 1e6
+                                             if world == 1 and args.workload in NCU_TRAFFIC else None),
+                     "actual_traffic_frac_of_peak": (NCU_TRAFFIC[args.workload][0] / ms_kernel / 1e6 / peak
+                                                     if world == 1 and args.workload in NCU_TRAFFIC else None),
+                     "gather_roofs": "random 256-byte rows, nothing attached (mxg_dev_gather_probe, profiles/"
+                                     "r01_v5_gather_roof_probe.jsonl): 14.0 TB/s from L2, 9.0 TB/s on a 256 MB table, "
+                                     "6.4 TB/s from DRAM",
                      "note": "W_alg = nnz*(4+s)+4(m+1)+s*K*n+s*m*n per GPU; gather-model bytes (B row per entry) = %.2f GB"
                              % ((nnz * (4 + s) + 4 * (m + 1) + s * nnz * n + s * m * n) / 1e9)},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -397,6 +406,13 @@ def run_ours(args):
     cpu = None
     if not args.skip_e2e:
         p_h, j_h, x_h = A.to_host()
+        # host staging threads of this rank (the exports' `nthreads`): the box's cores are shared by the ranks
+        nth = max(1, min(16, (os.cpu_count() or 4) // max(world, 1)))
+        # With several ranks calling at once the host's memory bandwidth, not the per-GPU PCIe links, bounds the
+        # calls, and narrowing on the host costs 20 instead of 12 bytes of host memory traffic per entry (measured:
+        # 8 ranks 127 ms per call with host narrowing, 100 ms without; 2 ranks 31.9 vs 30.2 ms): narrow on the device.
+        if world >= 2:
+            _lib.set_option("host_narrow", 0)
         np_t = np.float32 if f32 else np.float64
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
         p_h, j_h, x_h = pin(p_h), pin(j_h), pin(x_h)
@@ -406,7 +422,7 @@ def run_ours(args):
         if op == "spmv":
             d_h = pin(dense.cpu().numpy())
             o_h = pinned_out((m,), torch.float64)
-            call = lambda out=o_h: rx.matmul_csr_dvec_numeric(p_h, j_h, x_h, d_h, 0, out=out)  # noqa: E731
+            call = lambda out=o_h: rx.matmul_csr_dvec_numeric(p_h, j_h, x_h, d_h, nth, out=out)  # noqa: E731
             h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
             d2h = 8 * m
         elif op == "crossprod":
@@ -421,10 +437,10 @@ def run_ours(args):
                   ("csr_dense", True): rx.tcrossprod_csr_dense_float32, ("csr_dense", False): rx.tcrossprod_csr_dense_numeric}[(op, f32)]
             if op == "dense_tcsr":
                 o_h = pinned_out((n, m), tdt)
-                call = lambda out=o_h: fn(d_h, p_h, j_h, x_h, 0, K, out=out)  # noqa: E731
+                call = lambda out=o_h: fn(d_h, p_h, j_h, x_h, nth, K, out=out)  # noqa: E731
             else:
                 o_h = pinned_out((m, n), tdt)
-                call = lambda out=o_h: fn(p_h, j_h, x_h, d_h, 0, out=out)  # noqa: E731
+                call = lambda out=o_h: fn(p_h, j_h, x_h, d_h, nth, out=out)  # noqa: E731
             h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
             d2h = s * m * n
         call()  # warm-up (allocator pools)
@@ -457,7 +473,7 @@ def run_ours(args):
                               "result into a page-locked host buffer"
                               + ("; float64 values narrowed to float32 by the library's host threads before the copy "
                                  "(h2d bytes counted after narrowing)" if host_narrow else ""),
-               "host_threads": min(os.cpu_count() or 4, 16),
+               "host_threads": nth,
                "fresh_pageable_result": {"value": 2.0 * nnz_all * n / t_fresh / 1e9, "ms_per_step": t_fresh * 1e3,
                                          "note": "same call returning a newly allocated pageable matrix, as the Rcpp glue does"}}
         if op not in ("crossprod",) and world == 1:
@@ -465,11 +481,11 @@ def run_ours(args):
             pg = lambda a: np.array(a, copy=True, order="K")  # noqa: E731
             p_g, j_g, x_g, d_g = pg(p_h), pg(j_h), pg(x_h), pg(d_h)
             if op == "spmv":
-                call_pg = lambda: rx.matmul_csr_dvec_numeric(p_g, j_g, x_g, d_g, 0)  # noqa: E731
+                call_pg = lambda: rx.matmul_csr_dvec_numeric(p_g, j_g, x_g, d_g, nth)  # noqa: E731
             elif op == "dense_tcsr":
-                call_pg = lambda: fn(d_g, p_g, j_g, x_g, 0, K)  # noqa: E731
+                call_pg = lambda: fn(d_g, p_g, j_g, x_g, nth, K)  # noqa: E731
             else:
-                call_pg = lambda: fn(p_g, j_g, x_g, d_g, 0)  # noqa: E731
+                call_pg = lambda: fn(p_g, j_g, x_g, d_g, nth)  # noqa: E731
             call_pg()
             t_pg, res = time_calls(call_pg, 3)
             e2e["all_pageable"] = {"value": 2.0 * nnz_all * n / t_pg / 1e9, "ms_per_step": t_pg * 1e3,
