@@ -246,7 +246,10 @@ def run_ours(args):
     out_rows = K if op == "crossprod" else m
     # N > 1: the products store every finished row into ALL ranks' results over NVLink (PeerResult), so the
     # all-gather of north_star subsystem 4 is fused into the kernel; crossprod keeps the NCCL collective
-    fused = world > 1 and op in ("spmv", "dense_tcsr", "csr_dense")
+    # (column-major results, op csr_dense, keep the NCCL collective: peer stores of 128-byte column segments 200 MB
+    #  apart reach only ~130 GB/s — cfg5 sharded over 8 GPUs: fused 170 ms, product + NCCL all-gather 53.6 ms,
+    #  profiles/r01_v5_bench_cfg5_sharded_8gpu.json — so the fused kernel is used where it wins: row-major rows)
+    fused = world > 1 and op in ("spmv", "dense_tcsr")
     peer = None
     if op == "spmv":
         dense = torch.randn(K, device="cuda", dtype=torch.float64, generator=g)

@@ -108,13 +108,16 @@ __global__ void __launch_bounds__(RS_HIST_THREADS) k_radix_hist(size_t n, const 
     for (int d = threadIdx.x; d < nbins; d += RS_HIST_THREADS) bins[d] = 0;
     __syncthreads();
     const size_t t0 = (size_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int k = 0; k < RS_TILE / RS_HIST_THREADS; k++) {
+    constexpr int PER = RS_TILE / RS_HIST_THREADS; // 16 keys per thread: all loads in flight before the first atomic
+    int key[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
         const size_t e = t0 + (size_t)k * RS_HIST_THREADS + threadIdx.x;
-        if (e < n) {
-            atomicAdd(&bins[(__ldg(keys + e) >> shift) & (nbins - 1)], 1);
-        }
+        key[k] = e < n ? __ldg(keys + e) : 0;
     }
+#pragma unroll
+    for (int k = 0; k < PER; k++)
+        if (t0 + (size_t)k * RS_HIST_THREADS + threadIdx.x < n) atomicAdd(&bins[(key[k] >> shift) & (nbins - 1)], 1);
     __syncthreads();
     for (int d = threadIdx.x; d < nbins; d += RS_HIST_THREADS) hist[(size_t)d * ntiles + blockIdx.x] = bins[d];
 }
