@@ -157,8 +157,11 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mask = nbins - 1;
     {
+        // counters are 16-bit and handled two at a time as one 32-bit word (digits 2k, 2k+1); only the digits this
+        // pass can produce are cleared
         unsigned *z = reinterpret_cast<unsigned *>(wcnt);
-        for (int i = threadIdx.x; i < RS_WARPS * RS_BINS / 2; i += RS_THREADS) z[i] = 0u;
+        const int words = nbins > 1 ? nbins / 2 : 1;
+        for (int i = threadIdx.x; i < RS_WARPS * words; i += RS_THREADS) z[(i / words) * (RS_BINS / 2) + (i % words)] = 0u;
     }
     __syncthreads();
 
@@ -185,24 +188,27 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
     }
     __syncthreads();
     // per-warp counts -> per-warp starts inside the digit; digit totals -> tile-local digit starts.
-    // Thread t owns the RS_DPT consecutive digits t * RS_DPT ..; everybody meets at the barriers.
+    // Thread t owns the digit pair (2t, 2t+1) = one 32-bit word per warp row: both 16-bit prefix sums advance with
+    // a single 32-bit add (a digit's total is at most RS_TILE = 4096, so the low half never carries into the high).
     __shared__ int warp_tot[RS_WARPS];
-    int run[RS_DPT];
-    int mine = 0;
-#pragma unroll
-    for (int q = 0; q < RS_DPT; q++) {
-        const int d = threadIdx.x * RS_DPT + q;
-        run[q] = 0;
-        if (d < nbins) {
+    static_assert(RS_DPT == 2, "the packed scan handles two digits per thread");
+    int run[RS_DPT] = {0, 0};
+    {
+        unsigned *wc32 = reinterpret_cast<unsigned *>(wcnt);
+        const int words = nbins > 1 ? nbins / 2 : 1;
+        if ((int)threadIdx.x < words) {
+            unsigned acc = 0;
 #pragma unroll
             for (int w = 0; w < RS_WARPS; w++) {
-                const int c = wcnt[w * RS_BINS + d];
-                wcnt[w * RS_BINS + d] = (rs_cnt_t)run[q];
-                run[q] += c;
+                const unsigned c = wc32[w * (RS_BINS / 2) + threadIdx.x];
+                wc32[w * (RS_BINS / 2) + threadIdx.x] = acc;
+                acc += c;
             }
+            run[0] = (int)(acc & 0xffffu);
+            run[1] = (int)(acc >> 16);
         }
-        mine += run[q];
     }
+    const int mine = run[0] + run[1];
     int incl = mine; // warp-wide inclusive scan of the per-thread digit totals
 #pragma unroll
     for (int dd = 1; dd < 32; dd <<= 1) {
