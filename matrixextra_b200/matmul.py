@@ -63,7 +63,12 @@ def gemm_dense_csc(x, y: dgCMatrix):
 # ---- R/matmul.R:202-277 (matrix branch 264-276: no dimension check) ---------------------------------
 def gemm_f32_csc(x: float32, y: dgCMatrix):
     if x.is_vector():
-        raise NotImplementedError("float32 vector %*% CSC is outside the scoped path (R/matmul.R:209-262)")
+        check_valid_matrix(y)
+        if y.Dim[0] == 1:  # R/matmul.R:221-241: [n,1] %*% [1,k] outer product with a sparse result
+            raise NotImplementedError("single-row outer product (sparse result) is outside the scoped path (R/matmul.R:221-241)")
+        if y.Dim[0] != x.Data.size:  # R/matmul.R:243-244
+            raise ValueError("(row) vector-Matrix multiplication dimensions do not match.")
+        return float32(rx.matmul_rowvec_by_csc(x.Data.ravel(), y.p, y.i, y.x))  # R/matmul.R:246-259
     check_valid_matrix(y)
     return float32(rx.matmul_dense_csc_float32(x.Data, y.p, y.i, y.x, _nthreads()))
 
@@ -79,7 +84,12 @@ def tcrossprod_dense_csr(x, y: dgRMatrix):
 # ---- R/matmul.R:309-381 (matrix branch 369-380: no dimension check) ---------------------------------
 def tcrossprod_f32_csr(x: float32, y: dgRMatrix):
     if x.is_vector():
-        raise NotImplementedError("tcrossprod(float32 vector, CSR) is outside the scoped path (R/matmul.R:316-367)")
+        check_valid_matrix(y)
+        if y.Dim[1] == 1:  # R/matmul.R:326-348: outer product with a sparse result
+            raise NotImplementedError("single-column outer product (sparse result) is outside the scoped path (R/matmul.R:326-348)")
+        if y.Dim[1] != x.Data.size:
+            raise ValueError("(row) vector-Matrix multiplication dimensions do not match.")
+        return float32(rx.matmul_rowvec_by_csc(x.Data.ravel(), y.p, y.j, y.x))  # R/matmul.R:350-366: CSR(y) == CSC(t(y))
     check_valid_matrix(y)
     return float32(rx.tcrossprod_dense_csr_float32(x.Data, y.p, y.j, y.x, _nthreads(), y.Dim[1]))
 
@@ -91,8 +101,11 @@ def crossprod_dense_csc(x, y: dgCMatrix):
 
 # ---- R/matmul.R:395-430 ---------------------------------------------------------------------------
 def crossprod_f32_csc(x: float32, y: dgCMatrix):
-    if x.is_vector():
-        raise NotImplementedError("crossprod(float32 vector, CSC) is outside the scoped path (R/matmul.R:402-427)")
+    if x.is_vector():  # R/matmul.R:402-427
+        if x.Data.size != y.Dim[0]:
+            raise ValueError("(column) vector-Matrix crossprod dimensions do not match.")
+        check_valid_matrix(y)
+        return float32(rx.matmul_rowvec_by_csc(x.Data.ravel(), y.p, y.i, y.x))
     return gemm_f32_csc(float32(x.Data.T), y)
 
 

@@ -139,6 +139,20 @@ def matmul_csr_dvec_float32(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, 
     return _csr_dvec(X_csr_indptr, X_csr_indices, X_csr_values, y_dense, MXG_Y_FLOAT32, np.float32, np.float32, out)
 
 
+# ---- float32 (row) vector %*% CSC (src/matmul.cpp:643-684; R/matmul.R:243-259, 350-366) ---------------------------
+
+def matmul_rowvec_by_csc(rowvec_, indptr, indices, values):
+    """out(1 x ncol, float32) = rowvec . Y for a CSC matrix: the float32 SpMV with the CSC arrays read as the CSR of
+    t(Y).  ``rowvec_`` holds float32 values (the reference passes them as int bits, float32@Data)."""
+    y = np.ascontiguousarray(rowvec_, dtype=np.float32)
+    return _csr_dvec(indptr, indices, values, y, MXG_Y_FLOAT32, np.float32, np.float32).reshape(1, -1)
+
+
+def matmul_rowvec_by_cscbin(rowvec_, indptr, indices):
+    """Pattern matrix: every stored entry counts as 1 (src/matmul.cpp:664-684)."""
+    return matmul_rowvec_by_csc(rowvec_, indptr, indices, np.ones(np.asarray(indices).size, dtype=np.float64))
+
+
 # ---- CSR %*% sparseVector (src/matmul.cpp:553-641; SURVEY.md §8 f2) ---------------------------------
 
 def _csr_svec(indptr, indices, values, y_indices_base1, y_values, ytype, y_np, ncols=0, out=None):

@@ -176,6 +176,13 @@ class Port:
         return self._spmv(self.lib.mxo_spmv_float32, p, j, x, y_dense, np.float32, np.float32,
                           nthreads or self.nthreads)
 
+    def matmul_rowvec_by_csc(self, rowvec, p, i, x=None):
+        """float32 row vector %*% CSC (src/matmul.cpp:643-684; x=None: matmul_rowvec_by_cscbin): per column
+        `out[col] += values[ix] * rowvec[indices[ix]]` with a float accumulator — the float32 SpMV loop over the CSC
+        arrays, restated by mxo_spmv_float32."""
+        x = np.ones(np.asarray(i).size) if x is None else x
+        return self._spmv(self.lib.mxo_spmv_float32, p, i, x, rowvec, np.float32, np.float32, 1).reshape(1, -1)
+
     # -- SURVEY.md §8 f2: CSR %*% sparse vector (src/matmul.cpp:486-641) ------------------------------
     def _svec(self, ytype, p, j, x, yi, yv, np_t, nt):
         p, j, x = _as_i32(p), _as_i32(j), _as_f64(x)
@@ -376,6 +383,19 @@ class Ref:
     def matmul_csr_dvec_float32(self, p, j, x, y, nthreads=None):
         return self._spmv(self.lib.mxref_matmul_csr_dvec_float32, p, j, x, y, np.float32, np.float32,
                           nthreads or self.nthreads)
+
+    def matmul_rowvec_by_csc(self, rowvec, p, i, x=None):
+        """The reference's own matmul_rowvec_by_csc / matmul_rowvec_by_cscbin (src/matmul.cpp:643-684)."""
+        p, i = _as_i32(p), _as_i32(i)
+        rv = np.ascontiguousarray(rowvec, dtype=np.float32)
+        xx = None if x is None else _as_f64(x)
+        out = np.zeros(p.size - 1, dtype=np.float32)
+        rc = self.lib.mxref_matmul_rowvec_by_csc(C.c_void_p(rv.ctypes.data), rv.size, _ptr(p, _i32p), p.size - 1,
+                                                 _ptr(i, _i32p), None if xx is None else _ptr(xx, _f64p), i.size,
+                                                 C.c_void_p(out.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(f"reference driver returned {rc}")
+        return out.reshape(1, -1)
 
     # -- SURVEY.md §8 f2: CSR %*% sparse vector, the reference's own exports (src/matmul.cpp:553-641) ---
     def _svec(self, fn, p, j, x, yi, yv, np_t, nt):

@@ -230,6 +230,21 @@ int mxref_matmul_csr_dvec_float32(const int *p, int nrowsX, const int *j, const 
 
 } /* extern "C" */
 
+/* ---- src/matmul.cpp:643-684 : float32 row vector %*% CSC (values == NULL: the pattern-matrix export) ---- */
+extern "C" {
+
+int mxref_matmul_rowvec_by_csc(const int *rowvec_f32_bits, int K, const int *p, int ncols, const int *i, const double *x,
+                               int nnz, int *out)
+{
+    IV RV((int *)rowvec_f32_bits, (size_t)K), P((int *)p, (size_t)ncols + 1), I((int *)i, (size_t)nnz);
+    if (x) hold_matrix(matmul_rowvec_by_csc(RV, P, I, NV((double *)x, (size_t)nnz)));
+    else hold_matrix(matmul_rowvec_by_cscbin(RV, P, I));
+    maybe_copy<int>(out);
+    return 0;
+}
+
+} /* extern "C" */
+
 /* ---- src/matmul.cpp:553-641 : CSR %*% sparse vector.  y indices are 1-based. ---- */
 extern "C" {
 

@@ -1,5 +1,5 @@
 /* rglue/rowops_gpu_glue.cpp — Rcpp glue for the steps either side of the multiplication path:
- * CSR %*% sparseVector, per-row index sorting, CSR validity checks and elementwise CSR * dense products, on
+ * CSR %*% sparseVector, float32 vector %*% CSC, per-row index sorting, CSR validity checks and elementwise CSR * dense products, on
  * libmxgpu.so.  Same rules as rglue/matmul_gpu_glue.cpp: the `// [[Rcpp::export(rng = false)]]` signatures are the
  * reference's (src/matmul.cpp:553-641, src/misc.cpp:177-330, 970-1016, src/operators.cpp:288-322, 2146-2178), so
  * Rcpp::compileAttributes() regenerates identical R wrappers and R/matmul.R, R/utils.R, R/operators.R do not
@@ -99,6 +99,33 @@ Rcpp::NumericVector matmul_csr_svec_float32(Rcpp::IntegerVector X_csr_indptr, Rc
                                             Rcpp::IntegerVector y_values, int nthreads)
 {
     return csr_times_svec(MXG_Y_FLOAT32, X_csr_indptr, X_csr_indices, X_csr_values, y_indices_base1, INTEGER(y_values), nthreads);
+}
+
+/* ---- float32 (row) vector %*% CSC, tcrossprod(float32 vector, CSR) : src/matmul.cpp:643-684 ----
+ * out[col] = sum over the column's entries of values * rowvec[index]: the float32 SpMV with the CSC arrays read as
+ * the CSR of the transpose (K = length(rowvec)); result 1 x ncol, float32 bits in an integer matrix. */
+// [[Rcpp::export(rng = false)]]
+Rcpp::IntegerMatrix matmul_rowvec_by_csc(Rcpp::IntegerVector rowvec_, Rcpp::IntegerVector indptr, Rcpp::IntegerVector indices,
+                                         Rcpp::NumericVector values)
+{
+    const int ncols = (int)indptr.size() - 1;
+    Rcpp::IntegerMatrix out(1, ncols);
+    mxgpu_rowops_check(mxg_spmv_csr(MXG_Y_FLOAT32, ncols, (int)rowvec_.size(), INTEGER(indptr), INTEGER(indices), REAL(values),
+                                    INTEGER(rowvec_), INTEGER(out)));
+    return out;
+}
+
+/* pattern matrix (ngCMatrix / ngRMatrix): every stored entry counts as 1 */
+// [[Rcpp::export(rng = false)]]
+Rcpp::IntegerMatrix matmul_rowvec_by_cscbin(Rcpp::IntegerVector rowvec_, Rcpp::IntegerVector indptr, Rcpp::IntegerVector indices)
+{
+    const int ncols = (int)indptr.size() - 1;
+    Rcpp::NumericVector ones(indices.size());
+    for (size_t e = 0; e < (size_t)indices.size(); e++) ones[e] = 1.0;
+    Rcpp::IntegerMatrix out(1, ncols);
+    mxgpu_rowops_check(mxg_spmv_csr(MXG_Y_FLOAT32, ncols, (int)rowvec_.size(), INTEGER(indptr), INTEGER(indices), REAL(ones),
+                                    INTEGER(rowvec_), INTEGER(out)));
+    return out;
 }
 
 /* ---- index sorting and validity : src/misc.cpp:177-189, 300-330, 970-1016 ---- */

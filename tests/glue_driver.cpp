@@ -130,6 +130,16 @@ int gluedrv_csr_svec(int ytype, const int *p, int m, const int *j, const double 
     });
 }
 
+/* float32 row vector (K) %*% CSC with ncols columns; x == NULL: pattern matrix */
+int gluedrv_rowvec_by_csc(const float *rowvec, int K, const int *p, int ncols, const int *i, const double *x, int nnz, float *out)
+{
+    return guarded([&] {
+        IV RV((int *)rowvec, (size_t)K), P((int *)p, (size_t)ncols + 1), I((int *)i, (size_t)nnz);
+        if (x) copy_out(matmul_rowvec_by_csc(RV, P, I, NV((double *)x, (size_t)nnz)), (int *)out);
+        else copy_out(matmul_rowvec_by_cscbin(RV, P, I), (int *)out);
+    });
+}
+
 int gluedrv_rows_sorted(const int *p, int m, const int *j, int nnz, int *sorted)
 {
     return guarded([&] { *sorted = check_indices_are_unsorted(IV((int *)p, (size_t)m + 1), IV((int *)j, (size_t)nnz)) ? 1 : 0; });

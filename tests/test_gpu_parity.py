@@ -479,3 +479,33 @@ def test_properties_at_scale():
     assert np.max(np.abs(colsum.cpu().numpy() - want)) <= 1e-12 * max(1.0, np.abs(want).max())
     for h in (Att, At, A):
         h.free()
+
+
+# ---------------------------------------------------------------------------------------------------
+# float32 vector %*% CSC / tcrossprod(float32 vector, CSR) / crossprod(float32 vector, CSC)
+# (matmul_rowvec_by_csc[bin], src/matmul.cpp:643-684; R/matmul.R:243-259, 350-366, 402-427)
+# ---------------------------------------------------------------------------------------------------
+def test_float32_row_vector_times_csc(rx, port):
+    from matrixextra_b200 import crossprod, dgCMatrix, dgRMatrix, float32, matmul, tcrossprod
+    rng = np.random.default_rng(77)
+    for K, ncols, dens in ((300, 120, 0.2), (50, 1, 0.6), (2000, 900, 0.01)):
+        Y = rsparsematrix(K, ncols, dens, 7, "csc")
+        rv = rng.standard_normal(K).astype(np.float32)
+        want = port.matmul_rowvec_by_csc(rv, Y.indptr, Y.indices, Y.data)
+        got = rx.matmul_rowvec_by_csc(rv, Y.indptr, Y.indices, Y.data)
+        assert got.shape == (1, ncols) and got.dtype == np.float32
+        assert rel_err(got, want) <= FP32_TOL
+        got_bin = rx.matmul_rowvec_by_cscbin(rv, Y.indptr, Y.indices)
+        assert rel_err(got_bin, port.matmul_rowvec_by_csc(rv, Y.indptr, Y.indices, None)) <= FP32_TOL
+        if K > 1:
+            # the S4 routes that end in it
+            Yc = dgCMatrix.from_scipy(Y)
+            assert np.array_equal(matmul(float32(rv), Yc).Data, got)
+            assert np.array_equal(crossprod(float32(rv), Yc).Data, got)
+            if ncols > 1:
+                Yr = dgRMatrix.from_scipy(sp.csr_matrix(Y.T))  # CSR of t(Y): tcrossprod(x, t(Y)) == x %*% Y
+                assert np.array_equal(tcrossprod(float32(rv), Yr).Data, got)
+    with pytest.raises(ValueError, match="vector-Matrix multiplication dimensions do not match"):
+        matmul(float32(np.ones(5, dtype=np.float32)), dgCMatrix.from_scipy(rsparsematrix(7, 3, 0.5, 1, "csc")))
+    with pytest.raises(ValueError, match="vector-Matrix crossprod dimensions do not match"):
+        crossprod(float32(np.ones(5, dtype=np.float32)), dgCMatrix.from_scipy(rsparsematrix(7, 3, 0.5, 1, "csc")))

@@ -142,3 +142,23 @@ def test_long_rows_and_powerlaw_inputs(port):
     assert rel_err(port.matmul_csr_dvec_numeric(p, j, x, y), want) <= FP64_TOL
     got32 = port.matmul_csr_dvec_float32(p, j, x, y.astype(np.float32))
     assert rel_err(got32, want) <= 20 * FP32_TOL  # the reference narrows after every term (src/matmul.cpp:403, 476)
+
+
+def test_rowvec_by_csc_restatement_equals_reference(port, ref):
+    """src/matmul.cpp:643-684 (float32 row vector %*% CSC, with and without stored values): the plain-C restatement
+    is the reference bit for bit, and both are the dense product within float32 rounding."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(12)
+    for (K, ncols, dens) in ((50, 30, 0.3), (1, 7, 1.0), (200, 1, 0.5), (64, 40, 0.0)):
+        Y = sp.random(K, ncols, dens, format="csc", random_state=rng, dtype=np.float64)
+        Y.sort_indices()
+        rv = rng.standard_normal(K).astype(np.float32)
+        for x in (Y.data, None):
+            a = port.matmul_rowvec_by_csc(rv, Y.indptr, Y.indices, x)
+            b = ref.matmul_rowvec_by_csc(rv, Y.indptr, Y.indices, x)
+            assert a.shape == (1, ncols) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            dense = Y.toarray() if x is not None else (Y.toarray() != 0).astype(np.float64)
+            if x is None and dens > 0:
+                dense = np.zeros((K, ncols))
+                dense[Y.indices, np.repeat(np.arange(ncols), np.diff(Y.indptr))] = 1.0
+            assert np.allclose(a.ravel(), rv.astype(np.float64) @ dense, rtol=1e-5, atol=1e-5)

@@ -143,12 +143,12 @@ def test_glue_vectors_and_transpose(drv, port):
 def test_rowops_glue_keeps_the_reference_export_names():
     text = open(os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp")).read()
     for name in ("matmul_csr_svec_numeric", "matmul_csr_svec_integer", "matmul_csr_svec_logical", "matmul_csr_svec_binary",
-                 "matmul_csr_svec_float32", "check_indices_are_unsorted", "sort_sparse_indices_numeric",
+                 "matmul_csr_svec_float32", "matmul_rowvec_by_csc", "matmul_rowvec_by_cscbin", "check_indices_are_unsorted", "sort_sparse_indices_numeric",
                  "sort_sparse_indices_binary", "check_valid_csr_matrix", "multiply_csr_by_dense_elemwise_double",
                  "multiply_csr_by_dense_elemwise_float32", "multiply_csr_by_dense_elemwise_int",
                  "multiply_csr_by_dense_elemwise_bool", "multiply_csr_by_dvec_no_NAs_numeric"):
         assert text.count(name + "(") >= 1, name
-    assert text.count("\n// [[Rcpp::export(rng = false)]]\n") == 14
+    assert text.count("\n// [[Rcpp::export(rng = false)]]\n") == 16
 
 
 @pytest.mark.gpu
@@ -229,3 +229,15 @@ def test_rowops_glue_sort_validity_and_elementwise(drv, port):
     assert np.array_equal(out, port.multiply_csr_by_dvec_no_NAs_numeric(p, j, x, v, 500))
     assert drv.gluedrv_mul_dvec(_p(p), 600, _p(j), _p(x), j.size, _p(v), C.c_long(v.size), 500, 0, _p(out)) == 1
     assert "only the multiplication" in drv.gluedrv_last_error().decode()
+
+
+@pytest.mark.gpu
+def test_rowops_glue_float32_row_vector_by_csc(drv, port):
+    Y = rsparsematrix(400, 150, 0.1, 45, "csc")
+    p, i, x = _i32(Y.indptr), _i32(Y.indices), Y.data
+    rv = np.random.default_rng(45).standard_normal(400).astype(np.float32)
+    out = np.empty(150, dtype=np.float32)
+    assert drv.gluedrv_rowvec_by_csc(_p(rv), 400, _p(p), 150, _p(i), _p(x), i.size, _p(out)) == 0
+    assert rel_err(out, port.matmul_rowvec_by_csc(rv, p, i, x).ravel()) <= FP32_TOL
+    assert drv.gluedrv_rowvec_by_csc(_p(rv), 400, _p(p), 150, _p(i), None, i.size, _p(out)) == 0
+    assert rel_err(out, port.matmul_rowvec_by_csc(rv, p, i, None).ravel()) <= FP32_TOL
