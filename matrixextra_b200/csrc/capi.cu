@@ -136,11 +136,10 @@ static int upload_csr(int m, int K, const int32_t *p, const int32_t *j, const do
             if (d_x64) {
                 int rc = convert_f64_to_f32(d_x64, d_x32, (size_t)nnz, stream);
                 if (rc != MXG_OK) { free_handle(h); return rc; }
-            } else if (options().host_narrow != 0) {
+            } else if (options().host_narrow != 0 && staged_h2d_narrow(st, d_x32, x + base, (size_t)nnz, stream) == MXG_OK) {
                 // float32 only: narrowed by the host threads, 4 instead of 8 bytes per value over PCIe
-                int rc = staged_h2d_narrow(st, d_x32, x + base, (size_t)nnz, stream);
-                if (rc != MXG_OK) { free_handle(h); return rc; }
             } else {
+                cudaGetLastError(); // (no page-locked arena: narrow on the device instead)
                 // stage the float64 values through pool memory in chunks and narrow them on device (K6)
                 const size_t chunk = (size_t)std::max<long>(1, options().h2d_chunk_mb) * (1u << 20) / sizeof(double);
                 double *d_tmp = nullptr;
@@ -328,6 +327,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
     if (!strcmp(name, "host_stage")) return &o.host_stage;
     if (!strcmp(name, "pipe_slots")) return &o.pipe_slots;
+    if (!strcmp(name, "host_arena_max_mb")) return &o.host_arena_max_mb;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
     if (!strcmp(name, "spmv_tex")) return &o.spmv_tex;
     if (!strcmp(name, "svec_smem")) return &o.svec_smem;

@@ -236,6 +236,9 @@ bool host_is_pinned(const void *ptr)
 
 int pinned_arena(DeviceState *st, size_t bytes, char **base)
 {
+    const long cap_mb = options().host_arena_max_mb;
+    if (cap_mb > 0 && bytes > ((size_t)cap_mb << 20))
+        return fail(MXG_ERR_CUDA, "staging arena of %zu MiB exceeds host_arena_max_mb = %ld", bytes >> 20, cap_mb);
     if (bytes > st->pin_bytes) {
         if (st->pin_base) {
             MXG_CUDA_TRY(cudaFreeHost(st->pin_base));
@@ -314,7 +317,11 @@ int staged_h2d(DeviceState *st, void *d_dst, const void *src, size_t bytes, cuda
         return MXG_OK;
     }
     StagedRing ring;
-    MXG_TRY(ring.init(st));
+    if (ring.init(st) != MXG_OK) { // no page-locked memory: the driver's own bounce
+        cudaGetLastError();
+        MXG_CUDA_TRY(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return MXG_OK;
+    }
     int k = 0;
     for (size_t off = 0; off < bytes; off += ST_BLOCK, k = (k + 1) % ST_SLOTS) {
         const size_t len = std::min(ST_BLOCK, bytes - off);
@@ -357,7 +364,11 @@ int staged_d2h(DeviceState *st, void *dst, const void *d_src, size_t bytes, cuda
         return MXG_OK;
     }
     StagedRing ring;
-    MXG_TRY(ring.init(st));
+    if (ring.init(st) != MXG_OK) {
+        cudaGetLastError();
+        MXG_CUDA_TRY(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, stream));
+        return MXG_OK;
+    }
     const size_t nblocks = (bytes + ST_BLOCK - 1) / ST_BLOCK;
     auto drain = [&](size_t b) -> int {
         const int k = (int)(b % ST_SLOTS);

@@ -62,6 +62,7 @@ struct Options {
     long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry)
     long host_stage = 1;      // bounce pageable caller memory through the page-locked arena with the host threads
     long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
+    long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
 };
 Options &options();
 

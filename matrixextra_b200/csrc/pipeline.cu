@@ -89,12 +89,18 @@ struct HostPlan {
 
 // One pass over the host indptr: chunk boundaries, monotonicity check, long-row tables (the host twin of
 // k_row_stats / k_fill_long_tables in layout.cu; same table format, rows numbered from the chunk start).
-int build_plan(int m, const int32_t *p, HostPlan &plan)
+int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
 {
     plan.piece = (int)std::max<long>(32, options().piece);
     const int64_t nnz = p[m];
-    int64_t target_nnz = std::max<int64_t>(nnz / 16, (int64_t)1 << 20);
+    // ~16 chunks, but never more than 16 Mi entries or 64 MiB of result rows per chunk: the ring slots of the
+    // page-locked arena are sized by the largest chunk (a 2-billion-entry call must not pin gigabytes)
+    int64_t target_nnz = std::min<int64_t>(std::max<int64_t>(nnz / 16, (int64_t)1 << 20), (int64_t)16 << 20);
     int target_rows = std::max(m / 16, 1 << 16);
+    if (out_row_bytes > 0) {
+        const int64_t cap = std::max<int64_t>(1 << 16, ((int64_t)64 << 20) / (int64_t)out_row_bytes);
+        target_rows = (int)std::min<int64_t>(target_rows, cap);
+    }
     if (options().pipe_chunk_nnz > 0) { // tests: force many small chunks
         target_nnz = options().pipe_chunk_nnz;
         target_rows = (int)std::min<int64_t>(target_nnz, INT32_MAX);
@@ -255,6 +261,7 @@ struct CsrStream {
     const double *x;
     bool narrow; // the product runs on float32 values
     // host staging (hoststage.cu)
+    bool staging_unavailable = false; // the arena could not be allocated: every copy takes the driver's path
     bool narrow_on_host = false; // float32 values are produced by the host threads, no device narrowing
     bool stage_x = false, stage_j = false;
     size_t x_part = 0; // bytes of a slot reserved for the values (indices follow)
@@ -281,9 +288,9 @@ struct CsrStream {
 
     // Plan + page-locked arena.  dense_pageable: the dense operand wants ring slots too; out_row_bytes > 0:
     // the result is pageable and every chunk's rows (out_row_bytes each) are bounced through an output slot.
-    int plan_host(bool dense_pageable, size_t out_row_bytes)
+    int plan_host(bool dense_pageable, size_t out_row_bytes, size_t result_row_bytes)
     {
-        MXG_TRY(build_plan(m, p, plan));
+        MXG_TRY(build_plan(m, p, plan, result_row_bytes));
         const bool stage = options().host_stage != 0;
         narrow_on_host = narrow && options().host_narrow != 0 && nnz > 0;
         stage_x = nnz > 0 && (narrow_on_host || (stage && !host_is_pinned(x)));
@@ -298,7 +305,17 @@ struct CsrStream {
         const size_t total = (size_t)S * in_slot + (size_t)out_slots * out_slot_bytes;
         if (total > 0) {
             char *base = nullptr;
-            MXG_TRY(pinned_arena(sc.st, total, &base));
+            if (pinned_arena(sc.st, total, &base) != MXG_OK) {
+                // no page-locked memory to be had (ulimit -l, fragmentation): the plain driver copies still work
+                cudaGetLastError();
+                last_error_ref().clear();
+                narrow_on_host = stage_x = stage_j = false;
+                x_part = 0;
+                out_slots = 0;
+                out_slot_bytes = 0;
+                staging_unavailable = true;
+                return MXG_OK;
+            }
             if (in_slot > 0) MXG_TRY(ring.init(sc, base, in_slot, S));
             out_base = base + (size_t)S * in_slot;
         }
@@ -482,7 +499,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     CsrStream cs(sc, m, K, p, j, x, /*narrow=*/dtype == MXG_F32);
     const bool stage = options().host_stage != 0;
     const bool stage_B = stage && K > 0 && !host_is_pinned(B);
-    const bool stage_out = stage && !host_is_pinned(Out);
+    bool stage_out = stage && !host_is_pinned(Out);
     // dense operand first: every chunk needs all of it.  Device copy is rows-contiguous [K][ld_b].
     const size_t ld_b = round_up(nz, vec);
     char *d_B = nullptr, *d_Out = nullptr, *d_tmp = nullptr;
@@ -501,8 +518,9 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     // a page-locked operand starts to fly before the host pass over the indptr, a pageable one needs the ring first
     if (!stage_B) MXG_TRY(upload_dense(nullptr));
     const double t_plan = trace.now();
-    MXG_TRY(cs.plan_host(stage_B, stage_out ? nz * s : 0));
+    MXG_TRY(cs.plan_host(stage_B, stage_out ? nz * s : 0, nz * s));
     trace.plan_ms = trace.now() - t_plan;
+    if (cs.staging_unavailable) stage_out = false;
     if (stage_B) MXG_TRY(upload_dense(&cs.ring));
     MXG_TRY(chain(sc, st->h2d, st->stream));
     if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS)
@@ -579,13 +597,14 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
     CsrStream cs(sc, m, K, p, j, x, /*narrow=*/false);
     const bool stage = options().host_stage != 0;
     const bool stage_y = stage && K > 0 && !host_is_pinned(y);
-    const bool stage_out = stage && !host_is_pinned(out);
+    bool stage_out = stage && !host_is_pinned(out);
     char *d_y = nullptr, *d_out = nullptr;
     MXG_TRY(sc.alloc((void **)&d_y, (size_t)K * ys));
     MXG_TRY(sc.alloc((void **)&d_out, (size_t)m * os));
     MXG_TRY(chain(sc, st->stream, st->h2d));
     if (!stage_y) MXG_TRY(upload_lines(nullptr, d_y, (size_t)K * ys, y, (size_t)K * ys, (size_t)K * ys, 1, st->h2d));
-    MXG_TRY(cs.plan_host(stage_y, stage_out ? os : 0));
+    MXG_TRY(cs.plan_host(stage_y, stage_out ? os : 0, os));
+    if (cs.staging_unavailable) stage_out = false;
     // the vector as lines of <= 4 MiB so that it fits the ring slots whatever K is
     if (stage_y) {
         const size_t line = (size_t)4 << 20, total = (size_t)K * ys;

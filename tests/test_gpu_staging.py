@@ -22,7 +22,7 @@ def rx():
 @pytest.fixture()
 def options():
     from matrixextra_b200 import _lib
-    names = ("pipe_chunk_nnz", "piece", "host_narrow", "host_stage", "host_threads", "pipe_slots")
+    names = ("pipe_chunk_nnz", "piece", "host_narrow", "host_stage", "host_threads", "pipe_slots", "host_arena_max_mb")
     old = {k: _lib.get_option(k) for k in names}
     yield _lib
     for k, v in old.items():
@@ -219,3 +219,23 @@ def test_one_shot_staged_copies_upload_crossprod_and_csr2csc(rx, port, options):
             assert np.array_equal(p2, S.indptr) and np.array_equal(i2, S.indices) and np.array_equal(x2, S.data)
         assert np.array_equal(got64, ref["g64"]) and np.array_equal(got32, ref["g32"]), (stage, narrow)
         assert np.array_equal(p2, q2) and np.array_equal(i2, k2) and np.array_equal(x2, y2)
+
+
+def test_without_page_locked_memory_the_driver_path_takes_over(rx, port, options):
+    """host_arena_max_mb caps the page-locked arena; when a call would need more (or cudaHostAlloc fails) every copy
+    falls back to the driver's own bounce and the values are narrowed on the device: same bits, no error."""
+    from matrixextra_b200._lib import MXG_F32
+    m, K, n = 20_000, 3_000, 48
+    p, j, x = _big_random_csr(m, K, 20, seed=41)
+    rng = np.random.default_rng(41)
+    X = np.asfortranarray(rng.standard_normal((n, K)).astype(np.float32))
+    y = rng.standard_normal(K)
+    Y = np.asfortranarray(rng.standard_normal((m, 8)).astype(np.float32))
+    ref_mm = rx.tcrossprod_dense_csr_float32(X, p, j, x, 4, K)
+    ref_mv = rx.matmul_csr_dvec_numeric(p, j, x, y, 4)
+    ref_cp = rx.crossprod_csr_dense(p, j, x, K, Y, MXG_F32)
+    assert rel_err(ref_mm, port.tcrossprod_dense_csr_float32(X, p, j, x, 1, K)) <= FP32_TOL
+    options.set_option("host_arena_max_mb", 1)  # every arena request (>= 3 slots of >= 1 MiB) is refused
+    assert np.array_equal(rx.tcrossprod_dense_csr_float32(X, p, j, x, 4, K), ref_mm)
+    assert np.array_equal(rx.matmul_csr_dvec_numeric(p, j, x, y, 4), ref_mv)
+    assert np.array_equal(rx.crossprod_csr_dense(p, j, x, K, Y, MXG_F32), ref_cp)
