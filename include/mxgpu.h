@@ -70,11 +70,19 @@ int mxg_device_count(int *count);
 /* Device used by subsequent calls from this thread (default: the current CUDA device). */
 int mxg_set_device(int device);
 
-/* Tuning knobs, all optional ("auto" when never set). Names: "piece" (nnz per long-row piece),
- * "spmm_lpr" (lanes per row of B), "spmm_rpw" (rows per warp), "spmm_panel_mb" (column-panel size of the
- * dense operand in MiB, 0 = off), "spmm_panel_cols" (forced panel width in columns), "spmv_lpr", "spmv_tex" (numeric SpMV gathers y through the texture path, default 1), "svec_smem" (sparse-vector
- * product keeps the presence bitmap in shared memory when it fits, default 1), "h2d_chunk_mb", "pipeline" (level-1 calls: 1 = streamed row chunks, 0 = whole-matrix
- * upload first), "pipe_chunk_nnz" (stored entries per streamed chunk, 0 = auto).  Unknown names return MXG_ERR_ARG. */
+/* Tuning knobs, all optional ("auto" when never set).  Unknown names return MXG_ERR_ARG.
+ *   kernels : "piece" (stored entries per long-row piece, 1024), "spmm_lpr" (lanes per row of B), "spmm_cpl" (vectors
+ *             per lane: 0 = auto, two when a row of B exceeds 128 bytes), "spmm_rpw" (rows per warp), "spmm_panel_mb" /
+ *             "spmm_panel_cols" (column panels of the dense operand, off), "spmv_lpr", "spmv_tex" (numeric SpMV gathers y
+ *             through the texture path, 1), "svec_smem" (sparse-vector product keeps the presence bitmap in shared memory
+ *             when it fits, 1), "radix_bits" (largest digit of the CSR->CSC radix passes, 4..10, default 8);
+ *   level-1 calls : "pipeline" (1 = streamed row chunks, 0 = whole-matrix upload first), "pipe_chunk_nnz" (stored
+ *             entries per chunk, 0 = auto), "pipe_slots" (ring slots, 4), "h2d_chunk_mb";
+ *   host staging (csrc/hoststage.cu) : "host_threads" (threads that narrow / bounce host memory; the Rcpp exports'
+ *             `nthreads`; 0 = all logical CPUs up to 16), "host_narrow" (float32 products narrow the float64 values on
+ *             the host before the copy, 1), "host_stage" (pageable caller memory goes through the page-locked ring, 1),
+ *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
+ *             copies are used). */
 int mxg_set_option(const char *name, long value);
 int mxg_get_option(const char *name, long *value);
 
