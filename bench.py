@@ -56,9 +56,9 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
 # `ncu --set full` captures of exactly these workloads (profiles/README.md); None where no capture exists.
 NCU_TRAFFIC = {
-    "cfg3": (15.562139e9 + 0.517222e9, "profiles/r01_v5_spmm_f32_k64_cfg3.ncu.txt"),
-    "k64f64": (39.131198e9 + 1.028578e9, "profiles/r01_v5_spmm_f64_k64.ncu.txt"),
-    "cfg2": (1.220707e9 + 0.019601e9, "profiles/r01_v5_spmv_f64_cfg2.ncu.txt"),
+    "cfg3": (15.561478e9 + 0.517096e9, "profiles/r01_v6_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": (39.124454e9 + 1.027757e9, "profiles/r01_v6_spmm_f64_k64.ncu.txt"),
+    "cfg2": (1.220725e9 + 0.019018e9, "profiles/r01_v6_spmv_f64_cfg2.ncu.txt"),
 }
 
 
