@@ -78,14 +78,16 @@ int launch_transpose_dense(int elem_size, size_t rows, size_t cols, const void *
 }
 
 // ================================ K4: CSR -> CSC ===================================================
-// one warp per row writes the row id over the row's entries
+// a team of LPR lanes per row writes the row id over the row's entries (LPR by the mean row length: a whole warp
+// on 20-entry rows leaves a third of the lanes idle and issues one store instruction per row)
+template <int LPR>
 __global__ void __launch_bounds__(256) k_expand_rows(int m, const int32_t *__restrict__ p, int32_t base, int32_t *__restrict__ rowid)
 {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < m; r += warps) {
-        const int a = p[r] - base, b = p[r + 1] - base;
-        for (int e = a + lane; e < b; e += 32) rowid[e] = r;
+    const int l = threadIdx.x % LPR;
+    const int teams = (int)(((size_t)gridDim.x * blockDim.x) / LPR);
+    for (int r = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR); r < m; r += teams) {
+        const int a = __ldg(p + r) - base, b = __ldg(p + r + 1) - base;
+        for (int e = a + l; e < b; e += LPR) __stcs(rowid + e, r);
     }
 }
 
@@ -310,9 +312,17 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     // row ids per entry
     int32_t *d_rowid = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_rowid, sizeof(int32_t) * n, stream));
-    int gr = ceil_div_i(m, 8);
-    if (gr > 148 * 32) gr = 148 * 32;
-    MXG_LAUNCH(k_expand_rows, gr, 256, 0, stream, m, d_p, base, d_rowid);
+    {
+        const double mean = (double)nnz / (double)m;
+        // power-law rows: the median is about half the mean, so teams of (mean / 2) lanes rounded down to a power of two
+        const int lpr = mean >= 64.0 ? 32 : (mean >= 32.0 ? 16 : (mean >= 16.0 ? 8 : 4));
+        int gr = ceil_div_i((long long)m * lpr, 256);
+        if (gr > 148 * 32) gr = 148 * 32;
+        if (lpr == 32) MXG_LAUNCH(k_expand_rows<32>, gr, 256, 0, stream, m, d_p, base, d_rowid);
+        else if (lpr == 16) MXG_LAUNCH(k_expand_rows<16>, gr, 256, 0, stream, m, d_p, base, d_rowid);
+        else if (lpr == 8) MXG_LAUNCH(k_expand_rows<8>, gr, 256, 0, stream, m, d_p, base, d_rowid);
+        else MXG_LAUNCH(k_expand_rows<4>, gr, 256, 0, stream, m, d_p, base, d_rowid);
+    }
 
     // LSD radix passes over the column key, records = (key, row, values)
     int bits = 0;
