@@ -178,6 +178,11 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
         const size_t e = w0 + (size_t)s * 32 + lane;
         const bool valid = e < n;
         key[s] = valid ? __ldg(io.keys_in + e) : 0;
+        if (valid) { // the payload is read after two barriers: have it on its way to L2 meanwhile (no registers held)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(io.rows_in + e));
+            if (H64) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.x64_in + e));
+            if (H32) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.x32_in + e));
+        }
         // invalid lanes get a digit no real lane can have (bit RS_MAX_BITS set) so they never match a real one
         const int d = valid ? ((key[s] >> shift) & mask) : RS_BINS;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
