@@ -156,8 +156,6 @@ void narrow_block(const double *s, float *d, size_t n)
 
 } // namespace
 
-int host_threads();
-
 // Threads for a region that moves `bytes`: one per MiB up to the pool size.  Small regions stay on one or two
 // cores on purpose: lines of a slot that sit in many cores' caches make the DMA that follows snoop all of them
 // (measured on the B200 box: a 2.5 MB download into a slot last read by 16 threads takes 0.41 ms, by one thread
