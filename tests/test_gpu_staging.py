@@ -239,3 +239,25 @@ def test_without_page_locked_memory_the_driver_path_takes_over(rx, port, options
     assert np.array_equal(rx.tcrossprod_dense_csr_float32(X, p, j, x, 4, K), ref_mm)
     assert np.array_equal(rx.matmul_csr_dvec_numeric(p, j, x, y, 4), ref_mv)
     assert np.array_equal(rx.crossprod_csr_dense(p, j, x, K, Y, MXG_F32), ref_cp)
+
+
+def test_one_shot_staged_copies_wrap_their_ring(rx, options):
+    """Arrays of many 16 MiB blocks: the 4-slot ring of the one-shot staged copies wraps in both directions
+    (upload of 80 MB indices / 160 MB values, host-narrowed upload of 20 M values, download of the CSC arrays)."""
+    import scipy.sparse as sp
+    from matrixextra_b200._lib import MXG_KEEP_F32, MXG_KEEP_F64
+    from matrixextra_b200.device import DeviceCSR
+    m, K = 400_000, 50_000
+    A = DeviceCSR.synth(m, K, 20_000_000, 1, 0, seed=99, keep=MXG_KEEP_F64)
+    p, j, x = A.to_host()  # pageable numpy arrays
+    A.free()
+    assert x.nbytes > 4 * (16 << 20) and j.nbytes > 4 * (16 << 20)
+    for keep in (MXG_KEEP_F64, MXG_KEEP_F32):
+        H = DeviceCSR.upload(m, K, p, j, x, keep=keep)
+        pp, jj, xx = H.to_host()
+        H.free()
+        assert np.array_equal(pp, p) and np.array_equal(jj, j)
+        assert np.array_equal(xx, x if keep == MXG_KEEP_F64 else x.astype(np.float32).astype(np.float64))
+    p2, i2, x2 = rx.csr_to_csc(m, K, p, j, x)
+    S = sp.csr_matrix((x, j, p), shape=(m, K)).tocsc()
+    assert np.array_equal(p2, S.indptr) and np.array_equal(i2, S.indices) and np.array_equal(x2, S.data)
