@@ -394,9 +394,18 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                                         for (int i = 0; i < V; i++) acc[c].v[i] = prev[c].v[i] + acc[c].v[i];
                                     }
                                     st_stream(dst + col[c], acc[c]);
-                                    for (int d = 0; d < g.n_extra; d++)
-                                        st_stream(static_cast<T *>(g.extra[d]) + (size_t)(row0 + r) * g.ldc + col[c], acc[c]);
                                 }
+                        }
+                    }
+                    if (!COLMAJOR && !PANELS) {
+                        // copies for the other GPUs: after the butterfly every sub-team holds the same bits, so the
+                        // destinations are dealt out over the sub-teams and one store instruction of the warp writes
+                        // to 32 / LPR peers at once
+                        for (int d = sub; d < g.n_extra; d += 32 / LPR) {
+                            T *dst = static_cast<T *>(g.extra[d]) + (size_t)(row0 + r) * g.ldc;
+#pragma unroll
+                            for (int c = 0; c < CPL; c++)
+                                if (cok[c]) st_stream(dst + col[c], acc[c]);
                         }
                     }
                 }
