@@ -330,13 +330,34 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    # NVLS multicast variant of the fused all-gather (rows-contiguous results): every row is written once with
+    # multimem.st and replicated by the NVSwitch; used for the timed step when the box offers it and it is faster
+    step_fn, how_fused, ms_probe = step, "peer", {}
+    mres = None
+    if fused and op == "dense_tcsr" and args.allgather != "peer":
+        try:
+            from matrixextra_b200.sharded import McastResult
+            mres = McastResult(int(np.prod(shape_all)) * s, dist, rank, world)
+            mc_block = mres.mc_ptr(rank * m * n * s)
+
+            def step_mc():
+                A.spmm_mcast(dense, mc_block, n, mdt)
+                mres.barrier()
+            for _ in range(3):
+                step_mc()
+                step()
+            ms_probe = {"mcast": timed(step_mc, 5) / 5, "peer": timed(step, 5) / 5}
+            if args.allgather == "mcast" or ms_probe["mcast"] < ms_probe["peer"]:
+                step_fn, how_fused = step_mc, "mcast"
+        except Exception as e:  # noqa: BLE001  (no multicast support: keep the peer-store kernel)
+            ms_probe = {"mcast_unavailable": str(e)[:200]}
     for _ in range(max(args.warmup, 3)):
-        step()
+        step_fn()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ms_total = timed(step, args.steps)
+    ms_total = timed(step_fn, args.steps)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_compute = timed(lambda: step(False), args.steps) if world > 1 else ms_total
@@ -373,7 +394,8 @@ def run_ours(args):
         "dtype": wl["dtype"], "data": "synthetic (device-generated, Philox4x32-10; SURVEY.md 8d)",
         "config": {"workload": wl["desc"], "rows_per_gpu": m, "cols": K, "nnz_per_gpu": nnz, "n": n,
                    "parallelism": (f"row-block shards x{world}, replicated dense operand, all-gather of the output row blocks "
-                                   + ("fused into the product kernel (NVLink peer stores)" if fused else "by NCCL"))
+                                   + (("fused into the product kernel (NVLS multicast stores)" if how_fused == "mcast"
+                                       else "fused into the product kernel (NVLink peer stores)") if fused else "by NCCL"))
                    if world > 1 else "single GPU",
                    "l2_policy": ("operands (CSR %.0f MB + dense %.0f MB + out %.0f MB) " % (nnz * (4 + s) / 1e6, s * K * n / 1e6, s * out_rows * n / 1e6))
                    + ("exceed the 126 MB L2; no flush needed" if nnz * (4 + s) + s * K * n + s * out_rows * n > 2 * 126e6
@@ -399,8 +421,12 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world > 1:
-        result["allgather"] = ({"how": "fused: every finished row is stored into all ranks' results over NVLink by the product "
-                                       "kernel (mxg_dev_spmm_bcast) + device-side flag barrier", "ms_per_step": ms_step,
+        result["allgather"] = ({"how": ("fused, NVLS multicast: every finished row is written once with multimem.st by the "
+                                        "product kernel (mxg_dev_spmm_mcast) and replicated by the NVSwitch into all ranks' "
+                                        "results + symmetric-memory barrier" if how_fused == "mcast" else
+                                        "fused: every finished row is stored into all ranks' results over NVLink by the product "
+                                        "kernel (mxg_dev_spmm_bcast) + device-side flag barrier"),
+                                "variants_ms_per_step": ms_probe, "ms_per_step": ms_step,
                                 "nccl_after_compute_ms_per_step": ms_nccl, "bytes_received_per_gpu": int((world - 1) * out_rows * n * s)}
                                if fused else {"how": "NCCL all_gather_into_tensor after the product", "ms_per_step": ms_step})
 
@@ -649,6 +675,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/nnz (debugging only; invalid as a bench value)")
+    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer"],
+                    help="fused all-gather of row-major results at N > 1: NVLS multicast stores, peer stores, or the faster")
     ap.add_argument("--others", default="cfg2,k64f64,cfg4", help="extra kernel-only configs reported at N=1 ('' to skip)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -235,6 +235,13 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
                        int n_dst, void *const *d_outs, size_t ldc, void *stream);
 int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream);
 
+/* The same fused product + all-gather through NVLS MULTICAST: mc_out is this block's first row inside a multicast
+ * mapping of the full result (cuMulticast* / torch.distributed._symmetric_memory: one virtual address bound to the
+ * result buffers of every GPU of the box).  Every finished row is written once with multimem.st and the NVSwitch
+ * replicates it into all G buffers, the local one included, so a row block leaves its GPU once instead of G-1 times.
+ * Rows-contiguous results only; the caller closes the step with a barrier across the GPUs. */
+int mxg_dev_spmm_mcast(mxg_csr_t A, int dtype, int n, const void *d_B, size_t ldb, void *mc_out, size_t ldc, void *stream);
+
 /* Device memory that can be shared with the other processes of the box, and its handles (cudaIpc*). */
 int mxg_dev_alloc(size_t bytes, void **d_ptr);
 int mxg_dev_free(void *d_ptr);

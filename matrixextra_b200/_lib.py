@@ -60,6 +60,7 @@ _SIGNATURES = {
     "mxg_dev_spmv": [_vp, _i32, _vp, _vp, _vp],
     "mxg_dev_spmm_bcast": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
     "mxg_dev_spmv_bcast": [_vp, _i32, _vp, _i32, _vp, _vp],
+    "mxg_dev_spmm_mcast": [_vp, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_alloc": [_sz, C.POINTER(_vp)],
     "mxg_dev_free": [_vp],
     "mxg_ipc_export": [_vp, _vp],

@@ -512,6 +512,15 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
     return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, static_cast<cudaStream_t>(stream));
 }
 
+int mxg_dev_spmm_mcast(mxg_csr_t A, int dtype, int n, const void *d_B, size_t ldb, void *mc_out, size_t ldc, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmm_mcast: NULL handle");
+    if (!mc_out) return fail(MXG_ERR_ARG, "dev_spmm_mcast: NULL multicast address");
+    void *outs[1] = {mc_out};
+    return launch_spmm_multi(A, dtype, MXG_ROWS_CONTIGUOUS, n, d_B, ldb, 1, outs, ldc, static_cast<cudaStream_t>(stream), 1);
+}
+
 int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream)
 {
     MXG_TRY(ensure_device_ready());

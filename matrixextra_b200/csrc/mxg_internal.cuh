@@ -157,8 +157,9 @@ int ensure_partial(mxg_csr_s *h, size_t bytes);
 int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
                 void *d_Out, size_t ldc, cudaStream_t stream);
 // the same product written to n_dst result buffers (local and / or peer-mapped), all with leading dimension ldc
+// mcast != 0: d_outs[0] is an NVLS multicast address, rows are written with multimem.st (row-major, one destination)
 int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
-                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream);
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast = 0);
 // spmv.cu
 int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream);
 int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream);

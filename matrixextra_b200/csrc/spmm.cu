@@ -109,6 +109,32 @@ __device__ __forceinline__ void st_stream(double *p, const Pack<double, 2> &v)
 __device__ __forceinline__ void st_stream(float *p, const Pack<float, 1> &v) { __stcs(p, v.v[0]); }
 __device__ __forceinline__ void st_stream(double *p, const Pack<double, 1> &v) { __stcs(p, v.v[0]); }
 
+// NVLS multicast stores: one store to a multicast address (cuMulticast / torch symmetric memory) is replicated by
+// the NVSwitch into the buffers of ALL GPUs bound to it, so a row block leaves its GPU once instead of G-1 times
+__device__ __forceinline__ void st_mcast(float *p, const Pack<float, 4> &v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.v[0]), "f"(v.v[1]), "f"(v.v[2]),
+                 "f"(v.v[3])
+                 : "memory");
+}
+__device__ __forceinline__ void st_mcast(double *p, const Pack<double, 2> &v)
+{
+    // 16 bytes are 16 bytes: the switch replicates bits, so a double pair travels as four 32-bit lanes
+    const float a = __int_as_float(__double2loint(v.v[0])), b = __int_as_float(__double2hiint(v.v[0]));
+    const float c = __int_as_float(__double2loint(v.v[1])), d = __int_as_float(__double2hiint(v.v[1]));
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_mcast(float *p, const Pack<float, 1> &v)
+{
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v.v[0]) : "memory");
+}
+__device__ __forceinline__ void st_mcast(double *p, const Pack<double, 1> &v)
+{
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v.v[0]) : "memory");
+}
+__device__ __forceinline__ void st_mcast_scalar(float *p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_mcast_scalar(double *p, double v) { asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
@@ -200,6 +226,7 @@ struct SpmmArgs {
     // leading dimension): the all-gather of the row blocks happens store by store, inside the product
     void *extra[MXG_MAX_DST - 1];
     int n_extra;
+    int mcast; // Out is a multicast address: rows are written with multimem.st and land on every GPU (row-major only)
     int rpw; // consecutive rows per warp (<= 31; column-major output uses SPMM_CM_RPW)
     int piece;
     int n_pieces;
@@ -393,7 +420,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 #pragma unroll
                                         for (int i = 0; i < V; i++) acc[c].v[i] = prev[c].v[i] + acc[c].v[i];
                                     }
-                                    st_stream(dst + col[c], acc[c]);
+                                    if (!PANELS && g.mcast) st_mcast(dst + col[c], acc[c]);
+                                    else st_stream(dst + col[c], acc[c]);
                                 }
                         }
                     }
@@ -422,6 +450,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
         }
     }
 
+    if (!COLMAJOR && !PANELS && g.mcast) __threadfence_system(); // multicast rows are on their way before the step's barrier
     if (COLMAJOR) {
         __syncthreads();
         const int tile_row0 = rb * BR;
@@ -475,7 +504,7 @@ __global__ void __launch_bounds__(128) k_spmm_fixup(int n, const int32_t *__rest
                                                     const int32_t *__restrict__ long_first,
                                                     const int32_t *__restrict__ long_np,
                                                     const T *__restrict__ partial, const DstList out, size_t ldc,
-                                                    const int *__restrict__ abort)
+                                                    const int *__restrict__ abort, int mcast)
 {
     if (abort != nullptr && *abort != 0) return;
     const int row = long_rows[blockIdx.x];
@@ -485,8 +514,11 @@ __global__ void __launch_bounds__(128) k_spmm_fixup(int n, const int32_t *__rest
         T s = T(0);
         for (int k = 0; k < np; k++) s += partial[(size_t)(first + k) * n + c];
         const size_t at = COLMAJOR ? (size_t)row + (size_t)c * ldc : (size_t)row * ldc + c;
-        for (int d = 0; d < out.n; d++) static_cast<T *>(out.dst[d])[at] = s;
+        if (mcast) st_mcast_scalar(static_cast<T *>(out.dst[0]) + at, s);
+        else
+            for (int d = 0; d < out.n; d++) static_cast<T *>(out.dst[d])[at] = s;
     }
+    if (mcast) __threadfence_system();
 }
 
 // Output rows of a matrix without stored entries (or with m rows but n == 0) still have to be zero.
@@ -609,7 +641,7 @@ static int plan_panels(mxg_csr_s *A, size_t b_bytes, cudaStream_t stream, SpmmAr
 
 template <typename T>
 static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, const T *d_B, size_t ldb,
-                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream)
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     const bool colmajor = out_layout == MXG_COLS_CONTIGUOUS;
@@ -663,6 +695,7 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.Out = d_Out;
     args.ldc = ldc;
     args.n_extra = n_dst - 1;
+    args.mcast = mcast;
     for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.piece = A->piece;
     args.n_pieces = A->n_pieces;
@@ -696,10 +729,10 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
         for (int d = 0; d < MXG_MAX_DST; d++) out.dst[d] = d < n_dst ? d_outs[d] : nullptr;
         if (colmajor)
             MXG_LAUNCH((k_spmm_fixup<T, true>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort);
+                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort, mcast);
         else
             MXG_LAUNCH((k_spmm_fixup<T, false>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort);
+                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort, mcast);
     }
     return MXG_OK;
 }
@@ -708,12 +741,15 @@ int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void
                 void *d_Out, size_t ldc, cudaStream_t stream)
 {
     void *outs[1] = {d_Out};
-    return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, 1, outs, ldc, stream);
+    return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, 1, outs, ldc, stream, 0);
 }
 
 int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
-                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream)
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast)
 {
+    if (mcast && (n_dst != 1 || out_layout != MXG_ROWS_CONTIGUOUS))
+        return fail(MXG_ERR_UNSUPPORTED, "spmm: multicast stores take one rows-contiguous destination");
+    if (mcast && A->nnz == 0) return fail(MXG_ERR_UNSUPPORTED, "spmm: multicast product of a matrix without stored entries");
     if (n_dst < 1 || n_dst > MXG_MAX_DST || !d_outs) return fail(MXG_ERR_ARG, "spmm: 1 .. %d destinations", MXG_MAX_DST);
     if (n < 0) return fail(MXG_ERR_ARG, "spmm: negative n");
     if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS)
@@ -724,11 +760,11 @@ int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, cons
     if (out_layout == MXG_COLS_CONTIGUOUS && ldc < (size_t)A->m) return fail(MXG_ERR_ARG, "spmm: ldc < m");
     if (dtype == MXG_F64) {
         if (!A->d_x64 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "spmm: handle holds no float64 values");
-        return spmm_typed<double>(A, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb, n_dst, d_outs, ldc, stream);
+        return spmm_typed<double>(A, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb, n_dst, d_outs, ldc, stream, mcast);
     }
     if (dtype == MXG_F32) {
         if (!A->d_x32 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "spmm: handle holds no float32 values");
-        return spmm_typed<float>(A, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb, n_dst, d_outs, ldc, stream);
+        return spmm_typed<float>(A, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb, n_dst, d_outs, ldc, stream, mcast);
     }
     return fail(MXG_ERR_ARG, "spmm: bad dtype %d", dtype);
 }

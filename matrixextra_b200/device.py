@@ -107,6 +107,12 @@ class DeviceCSR:
         _lib.call("mxg_dev_spmm_bcast", self._h, int(dtype), int(out_layout), MXG_ROWS_CONTIGUOUS, int(n), _dptr(B_t),
                   int(ldb), len(dst_ptrs), arr, int(ldc), _stream_ptr(stream))
 
+    def spmm_mcast(self, B_t, mc_ptr, n, dtype, ldb=None, ldc=None, stream=None):
+        """Fused product + all-gather through NVLS multicast: ``mc_ptr`` is the raw multicast address of this block's
+        first row (rows-contiguous); every row is stored once and replicated by the switch into all GPUs' results."""
+        _lib.call("mxg_dev_spmm_mcast", self._h, int(dtype), int(n), _dptr(B_t), int(ldb or n), C.c_void_p(int(mc_ptr)),
+                  int(ldc or n), _stream_ptr(stream))
+
     def spmv_bcast(self, y_t, dst_ptrs, ytype=MXG_Y_NUMERIC, stream=None):
         arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
         _lib.call("mxg_dev_spmv_bcast", self._h, int(ytype), _dptr(y_t), len(dst_ptrs), arr, _stream_ptr(stream))

@@ -191,3 +191,32 @@ def cuda_compute(dtype, stream=None) -> Callable:
         return out
 
     return run
+
+
+class McastResult:
+    """The full result of a row-sharded product in NVLS MULTICAST memory (torch symmetric memory does the plumbing:
+    one allocation per rank, exchanged handles, a multicast mapping over all of them).  A rank's product kernel
+    writes each finished row ONCE to the multicast address (``DeviceCSR.spmm_mcast``) and the NVSwitch replicates it
+    into every GPU's buffer, the local one included; ``barrier()`` is symmetric memory's stream-ordered device
+    barrier.  Raises if the box has no multicast support (then ``PeerResult`` is the way)."""
+
+    def __init__(self, payload_bytes: int, dist, rank: int, world: int):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = rank, world
+        self.payload_bytes = int(payload_bytes)
+        self.buf = symm.empty(self.payload_bytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.mc_base = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if self.mc_base == 0:
+            raise RuntimeError("symmetric memory gave no multicast pointer (no NVLS on this box)")
+
+    def tensor(self, shape, dtype):
+        """torch view of the LOCAL copy of the result."""
+        return self.buf.view(dtype)[: int(__import__("numpy").prod(shape))].view(shape)
+
+    def mc_ptr(self, byte_offset: int) -> int:
+        return self.mc_base + int(byte_offset)
+
+    def barrier(self):
+        self.handle.barrier()

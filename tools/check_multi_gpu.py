@@ -18,7 +18,7 @@ import torch.distributed as dist  # noqa: E402
 from matrixextra_b200 import _lib  # noqa: E402
 from matrixextra_b200._lib import MXG_COLS_CONTIGUOUS, MXG_F32, MXG_F64, MXG_ROWS_CONTIGUOUS  # noqa: E402
 from matrixextra_b200.device import DeviceCSR  # noqa: E402
-from matrixextra_b200.sharded import PeerResult  # noqa: E402
+from matrixextra_b200.sharded import McastResult, PeerResult  # noqa: E402
 
 
 def main():
@@ -59,6 +59,30 @@ def main():
             report[f"{name}_{lname}"] = bool(ok) and not res.failed()
             del full
             res.close(dist)
+    # the same through NVLS multicast (rows-contiguous results): one multimem.st per row, replicated by the switch
+    try:
+        for name, dtype, tdt, n in (("f32_n64", MXG_F32, torch.float32, 64), ("f64_n24", MXG_F64, torch.float64, 24)):
+            s = 4 if tdt == torch.float32 else 8
+            B = torch.randn(K, n, device="cuda", dtype=tdt, generator=gen)
+            mres = McastResult(world * m * n * s, dist, rank, world)
+            full = mres.tensor((world * m * n,), tdt)
+            full.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            for _ in range(2):
+                A.spmm_mcast(B, mres.mc_ptr(rank * m * n * s), n, dtype)
+                mres.barrier()
+            torch.cuda.synchronize()
+            local_out = torch.empty(m * n, device="cuda", dtype=tdt)
+            A.spmm(B, local_out, n, dtype, MXG_ROWS_CONTIGUOUS)
+            gathered = torch.empty(world * m * n, device="cuda", dtype=tdt)
+            dist.all_gather_into_tensor(gathered, local_out)
+            report[f"{name}_rows_mcast"] = bool(torch.equal(full, gathered))
+            del full, mres
+    except RuntimeError as e:  # no multicast on this box
+        report["mcast_unavailable"] = True
+        if rank == 0:
+            print("multicast unavailable:", e, file=sys.stderr)
     y = torch.randn(K, device="cuda", dtype=torch.float64, generator=gen)
     res = PeerResult(world * m * 8, dist, rank, world)
     full = res.tensor((world * m,), torch.float64)
