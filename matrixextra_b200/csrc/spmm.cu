@@ -252,7 +252,11 @@ struct SpmmArgs {
 // in panel q to the output row (read-modify-write from the second panel on; rows without entries in the
 // panel are not touched).  Entries are consumed in stored order panel after panel, so for sorted rows the sum
 // order is unchanged; for unsorted rows the split points still partition the row (see k_panel_segments).
-template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS, int MB = (CPL == 1 ? SPMM_MINB : 4)>
+// MULTI (row-major results only): the launch writes more than the local result — peer copies (g.extra) or an NVLS
+// multicast address (g.mcast).  A separate instantiation so that the single-destination kernel keeps the exact
+// instruction schedule it was tuned with (the shared version cost the fp64 variant 17 %).
+template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS, int MB = (CPL == 1 ? SPMM_MINB : 4),
+          bool MULTI = false>
 __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 {
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
@@ -420,12 +424,12 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 #pragma unroll
                                         for (int i = 0; i < V; i++) acc[c].v[i] = prev[c].v[i] + acc[c].v[i];
                                     }
-                                    if (!PANELS && g.mcast) st_mcast(dst + col[c], acc[c]);
+                                    if (MULTI && g.mcast) st_mcast(dst + col[c], acc[c]);
                                     else st_stream(dst + col[c], acc[c]);
                                 }
                         }
                     }
-                    if (!COLMAJOR && !PANELS) {
+                    if (MULTI && !COLMAJOR && !PANELS) {
                         // copies for the other GPUs: after the butterfly every sub-team holds the same bits, so the
                         // destinations are dealt out over the sub-teams and one store instruction of the warp writes
                         // to 32 / LPR peers at once
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
         }
     }
 
-    if (!COLMAJOR && !PANELS && g.mcast) __threadfence_system(); // multicast rows are on their way before the step's barrier
+    if (MULTI && !COLMAJOR && !PANELS && g.mcast) __threadfence_system(); // multicast rows are on their way before the step's barrier
     if (COLMAJOR) {
         __syncthreads();
         const int tile_row0 = rb * BR;
@@ -541,7 +545,10 @@ static int launch_two(SpmmArgs &args, int row_blocks, cudaStream_t stream)
     constexpr int MB = sizeof(T) == 4 ? 6 : 5;
     constexpr int NB = LPR * V * 2;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
-    MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB>), grid, SPMM_THREADS, 0, stream, args);
+    if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
+        MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB, !COLMAJOR>), grid, SPMM_THREADS, 0, stream, args);
+    else
+        MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB>), grid, SPMM_THREADS, 0, stream, args);
     return MXG_OK;
 }
 
@@ -551,7 +558,11 @@ static int launch_variant(SpmmArgs &args, int row_blocks, cudaStream_t stream)
     constexpr int NB = LPR * V * CPL;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
     if (args.n_panels <= 1) {
-        MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false>), grid, SPMM_THREADS, 0, stream, args);
+        if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
+            MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false, (CPL == 1 ? SPMM_MINB : 4), !COLMAJOR>), grid, SPMM_THREADS, 0,
+                       stream, args);
+        else
+            MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false>), grid, SPMM_THREADS, 0, stream, args);
         return MXG_OK;
     }
     for (int q = 0; q < args.n_panels; q++) {
