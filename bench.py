@@ -56,9 +56,9 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
 # `ncu --set full` captures of exactly these workloads (profiles/README.md); None where no capture exists.
 NCU_TRAFFIC = {
-    "cfg3": (15.561478e9 + 0.517096e9, "profiles/r01_v6_spmm_f32_k64_cfg3.ncu.txt"),
-    "k64f64": (39.124454e9 + 1.027757e9, "profiles/r01_v6_spmm_f64_k64.ncu.txt"),
-    "cfg2": (1.220725e9 + 0.019018e9, "profiles/r01_v6_spmv_f64_cfg2.ncu.txt"),
+    "cfg3": (15.632157e9 + 0.570318e9, "profiles/r01_v6_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": (39.124897e9 + 1.030659e9, "profiles/r01_v6_spmm_f64_k64.ncu.txt"),
+    "cfg2": (1.220678e9 + 0.022964e9, "profiles/r01_v6_spmv_f64_cfg2.ncu.txt"),
 }
 
 
