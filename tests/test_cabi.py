@@ -80,3 +80,17 @@ def test_row_partition_balances_entries():
     assert b[0] == 0 and b[-1] == 3
     b = row_partition(np.array([0, 100, 100, 100], np.int32), 3)
     assert b[0] == 0 and b[-1] == 3 and (np.diff(b) >= 0).all()
+
+
+def test_header_is_plain_c_and_cxx():
+    """include/mxgpu.h is the drop-in boundary: it must compile as C99 (cgo / .Call-style consumers) and as C++11 (the
+    Rcpp glue) with warnings as errors, with nothing but <stddef.h> / <stdint.h> behind it."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "mxgpu.h")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                   check=True, env=env)
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr],
+                   check=True, env=env)
+    text = open(hdr).read()
+    assert "torch" not in text.replace("torch symmetric memory", "").replace("torch.distributed._symmetric_memory", "")
