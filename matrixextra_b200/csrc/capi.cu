@@ -3,6 +3,9 @@
 #include "mxg_internal.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -699,14 +702,23 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, i
     MXG_TRY(current_state(&st));
     const int keep = dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32;
     mxg_csr_s *A = nullptr, *At = nullptr;
+    const char *tr = getenv("MXG_TRACE"); // development aid: host-side phase times on stderr
+    const bool trace = tr && *tr && *tr != '0';
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     MXG_TRY(upload_csr(m, K, p, j, x, keep, st->stream, &A));
+    const double t1 = now();
     int rc = transpose_handle(A, keep, st->stream, &At);
     cudaStreamSynchronize(st->stream);
     free_handle(A);
     if (rc != MXG_OK) return rc;
+    const double t2 = now();
     rc = spmm_host_io(At, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream);
     cudaStreamSynchronize(st->stream);
     free_handle(At);
+    if (trace)
+        fprintf(stderr, "[mxg trace] csrT: upload+stats %.2f ms | transpose+stats %.2f ms | dense upload, product, download %.2f ms\n",
+                t1 - t0, t2 - t1, now() - t2);
     return rc;
 }
 
