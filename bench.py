@@ -489,6 +489,9 @@ def run_ours(args):
             return t, r
 
         t_e2e, res = time_calls(call, k_e2e)
+        import ctypes as _C
+        h2d_lib, d2h_lib = _C.c_size_t(0), _C.c_size_t(0)
+        _lib.call("mxg_last_call_bytes", _C.byref(h2d_lib), _C.byref(d2h_lib))  # the last timed call, copy by copy
         # same call the way R makes it: the result is a freshly allocated (pageable, untouched) matrix
         call(out=None)  # warm-up: the page-locked arena grows by the output slots once
         t_fresh, res = time_calls(lambda: call(out=None), 3)
@@ -496,12 +499,21 @@ def run_ours(args):
         host_narrow = f32 and op != "crossprod" and _lib.get_option("host_narrow") != 0 and _lib.get_option("pipeline") != 0
         if host_narrow:
             h2d -= x_h.nbytes // 2
+        # ... and column ids travel packed (2 / 2.5 / 3 bytes per entry) in the chunks where the link, not the host
+        # threads, is the bottleneck (pipeline.cu upload_chunk): take the library's own count of what it copied
+        host_pack = False
+        if h2d_lib.value > 0:
+            host_pack = h2d_lib.value < h2d - 1024
+            h2d, d2h = h2d_lib.value, d2h_lib.value
         e2e = {"value": 2.0 * nnz_all * n / t_e2e / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "ms_per_step": t_e2e * 1e3,
                "entry_point": "level-1 C ABI (streamed row chunks) via the Rcpp-export mirror; pinned host inputs, "
                               "result into a page-locked host buffer"
                               + ("; float64 values narrowed to float32 by the library's host threads before the copy "
-                                 "(h2d bytes counted after narrowing)" if host_narrow else ""),
+                                 "(h2d bytes counted after narrowing)" if host_narrow else "")
+                              + ("; column ids of the chunks uploaded while the link was the bottleneck packed to 2-3 "
+                                 "bytes per entry by the same threads and rebuilt on the device" if host_pack else "")
+                              + ("; bytes are the library's count of its copies in the last timed call" if h2d_lib.value else ""),
                "host_threads": nth,
                "fresh_pageable_result": {"value": 2.0 * nnz_all * n / t_fresh / 1e9, "ms_per_step": t_fresh * 1e3,
                                          "note": "same call returning a newly allocated pageable matrix, as the Rcpp glue does"}}

@@ -81,6 +81,9 @@ int mxg_set_device(int device);
  *   host staging (csrc/hoststage.cu) : "host_threads" (threads that narrow / bounce host memory; the Rcpp exports'
  *             `nthreads`; 0 = all logical CPUs up to 16), "host_narrow" (float32 products narrow the float64 values on
  *             the host before the copy, 1), "host_stage" (pageable caller memory goes through the page-locked ring, 1),
+ *             "host_pack" (streamed calls of >= 2^20 entries whose host threads are not busy narrowing values or
+ *             bouncing a large result send column ids as 2 / 2.5 / 3 bytes per entry when the matrix has <= 2^16 /
+ *             2^20 / 2^24 columns: packed by the host threads, rebuilt on the device, 1; 2 = always),
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
  *             copies are used). */
 int mxg_set_option(const char *name, long value);
@@ -278,6 +281,25 @@ int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
 int mxg_host_narrow(const double *src, float *dst, size_t n);
 int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
                      int streaming_stores);
+/* mxg_host_pack_indices: the wire format of column ids in a streamed call (option "host_pack"): n uint16 low
+ * halves, padded to 16 bytes, then the high parts — nothing for K <= 2^16, a nibble per entry (entry i in byte i/2,
+ * even entries in the low nibble) for K <= 2^20, a byte per entry for K <= 2^24.  *packed_bytes receives the size
+ * (0 when K > 2^24: such ids travel as int32); packed == NULL only queries it.  *in_range = 0 when an id lies
+ * outside [0, K) (the streamed call then fails with MXG_ERR_INDEX before anything is computed from that chunk).
+ * `packed` must be 16-byte aligned. */
+int mxg_host_pack_indices(const int32_t *j, size_t n, int K, void *packed, size_t *packed_bytes, int *in_range);
+/* mxg_last_call_bytes: bytes the calling thread's most recent streamed product (mxg_spmm_csr_dense / mxg_spmv_csr
+ * with option "pipeline" = 1) copied host -> device and device -> host, counted copy by copy (after host narrowing
+ * and id packing; bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step). */
+int mxg_last_call_bytes(size_t *h2d_bytes, size_t *d2h_bytes);
+/* mxg_host_chunk_plan: how a streamed level-1 call would cut the CSR with this indptr into row chunks (first row of
+ * every chunk in chunk_rows[0 .. *n_chunks], cap = slots available there; chunk_rows may be NULL to query the
+ * counts): about 16 chunks of equal nnz (at most 16 Mi entries / 64 MiB of result rows each, result_row_bytes per
+ * row) that shrink towards the end of the matrix, or chunks of option "pipe_chunk_nnz" entries when that is set.
+ * Also reports the long rows (> option "piece" entries), their pieces and the longest row.  MXG_ERR_INDEX for a
+ * negative or decreasing indptr — the same check the products make. */
+int mxg_host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks,
+                        int *n_long, int *n_pieces, int *max_len);
 
 /* ============ synthetic inputs for bench.py / tests (device-side, counter-based RNG) ============
  * Power-law row lengths, stratified sorted unique columns; see DESIGN.md "Synthetic inputs". */

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "mxg_dev_gather_probe": [_i32, _vp, _sz, C.c_longlong, C.c_uint64, _vp, C.POINTER(C.c_longlong), _vp],
     "mxg_host_narrow": [_vp, _vp, _sz],
     "mxg_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz, _i32],
+    "mxg_host_pack_indices": [_vp, _sz, _i32, _vp, C.POINTER(_sz), C.POINTER(C.c_int)],
+    "mxg_last_call_bytes": [C.POINTER(_sz), C.POINTER(_sz)],
+    "mxg_host_chunk_plan": [_i32, _vp, _sz, _vp, _i32] + [C.POINTER(C.c_int)] * 4,
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],
 }
 _RESTYPES = {"mxg_last_error": C.c_char_p, "mxg_launch_count": C.c_ulonglong, "mxg_csr_error_string": C.c_char_p}

@@ -329,6 +329,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "host_threads")) return &o.host_threads;
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
     if (!strcmp(name, "host_stage")) return &o.host_stage;
+    if (!strcmp(name, "host_pack")) return &o.host_pack;
     if (!strcmp(name, "pipe_slots")) return &o.pipe_slots;
     if (!strcmp(name, "host_arena_max_mb")) return &o.host_arena_max_mb;
     if (!strcmp(name, "spmv_lpr")) return &o.spmv_lpr;
@@ -363,6 +364,32 @@ int mxg_host_narrow(const double *src, float *dst, size_t n)
     if (n > 0 && (!src || !dst)) return fail(MXG_ERR_ARG, "host_narrow: NULL buffer");
     host_narrow_f64_to_f32(src, dst, n);
     return MXG_OK;
+}
+
+int mxg_host_pack_indices(const int32_t *j, size_t n, int K, void *packed, size_t *packed_bytes, int *in_range)
+{
+    const int hb = index_pack_hi_bits(K);
+    if (packed_bytes) *packed_bytes = hb < 0 ? 0 : packed_index_bytes(n, hb);
+    if (!packed) return MXG_OK; // size query
+    if (hb < 0) return fail(MXG_ERR_ARG, "host_pack_indices: K = %d does not pack (ids above 2^24 travel as int32)", K);
+    if (n > 0 && !j) return fail(MXG_ERR_ARG, "host_pack_indices: NULL buffer");
+    if (((uintptr_t)packed & 15) != 0) return fail(MXG_ERR_ARG, "host_pack_indices: destination must be 16-byte aligned");
+    const bool ok = host_pack_indices(j, n, K, hb, packed);
+    if (in_range) *in_range = ok ? 1 : 0;
+    return MXG_OK;
+}
+
+int mxg_last_call_bytes(size_t *h2d_bytes, size_t *d2h_bytes)
+{
+    last_call_bytes(h2d_bytes, d2h_bytes);
+    return MXG_OK;
+}
+
+int mxg_host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks,
+                        int *n_long, int *n_pieces, int *max_len)
+{
+    if (m < 0 || !p) return fail(MXG_ERR_ARG, "chunk_plan: bad arguments");
+    return host_chunk_plan(m, p, result_row_bytes, chunk_rows, cap, n_chunks, n_long, n_pieces, max_len);
 }
 
 int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,

@@ -154,6 +154,54 @@ void narrow_block(const double *s, float *d, size_t n)
     _mm_sfence();
 }
 
+
+// 32-bit column ids -> low halves (uint16 per entry) + high parts (a nibble per entry when hi_bits == 4, a byte
+// when 8, nothing when 0); entry i's nibble is the low one of byte i/2 for even i.  [a, b) with a % 32 == 0;
+// lo and hi 16-byte aligned.  Returns non-zero when an id lies outside [0, K).
+int pack_block(const int32_t *j, size_t a, size_t b, int K, int hi_bits, uint16_t *lo, unsigned char *hi)
+{
+    const __m128i zero = _mm_setzero_si128(), kmax = _mm_set1_epi32(K - 1), low8 = _mm_set1_epi16(0x00ff);
+    __m128i bad = zero;
+    size_t i = a;
+    for (; i + 32 <= b; i += 32) {
+        __m128i v[8], h[8];
+#pragma GCC unroll 8
+        for (int q = 0; q < 8; q++) {
+            v[q] = _mm_loadu_si128(reinterpret_cast<const __m128i *>(j + i) + q);
+            bad = _mm_or_si128(bad, _mm_or_si128(_mm_cmplt_epi32(v[q], zero), _mm_cmpgt_epi32(v[q], kmax)));
+            h[q] = _mm_srli_epi32(v[q], 16);
+            v[q] = _mm_srai_epi32(_mm_slli_epi32(v[q], 16), 16); // sign-extended low half: the signed pack keeps its bits
+        }
+#pragma GCC unroll 4
+        for (int q = 0; q < 4; q++)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(lo + i) + q, _mm_packs_epi32(v[2 * q], v[2 * q + 1]));
+        if (hi_bits == 0) continue;
+        // valid ids have high parts < 256 (< 16): the saturating packs are exact
+        const __m128i b0 = _mm_packus_epi16(_mm_packs_epi32(h[0], h[1]), _mm_packs_epi32(h[2], h[3]));
+        const __m128i b1 = _mm_packus_epi16(_mm_packs_epi32(h[4], h[5]), _mm_packs_epi32(h[6], h[7]));
+        if (hi_bits == 8) {
+            _mm_stream_si128(reinterpret_cast<__m128i *>(hi + i), b0);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(hi + i) + 1, b1);
+        } else {
+            // 16-bit lane = byte[2k] | byte[2k+1] << 8  ->  byte[2k] | byte[2k+1] << 4 in its low byte
+            const __m128i n0 = _mm_and_si128(_mm_or_si128(b0, _mm_srli_epi16(b0, 4)), low8);
+            const __m128i n1 = _mm_and_si128(_mm_or_si128(b1, _mm_srli_epi16(b1, 4)), low8);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(hi + i / 2), _mm_packus_epi16(n0, n1));
+        }
+    }
+    int tail_bad = 0;
+    for (; i < b; i++) {
+        const int32_t c = j[i];
+        tail_bad |= (c < 0 || c >= K);
+        lo[i] = (uint16_t)c;
+        const unsigned h = (unsigned)c >> 16;
+        if (hi_bits == 8) hi[i] = (unsigned char)h;
+        else if (hi_bits == 4) hi[i / 2] = (i & 1) ? (unsigned char)(hi[i / 2] | ((h & 15u) << 4)) : (unsigned char)(h & 15u);
+    }
+    _mm_sfence();
+    return tail_bad | (_mm_movemask_epi8(bad) != 0);
+}
+
 } // namespace
 
 // Threads for a region that moves `bytes`: one per MiB up to the pool size.  Small regions stay on one or two
@@ -177,6 +225,11 @@ int host_threads()
     return (int)std::min<long>(t, 64);
 }
 
+void host_parallel_for(size_t ntasks, size_t bytes_touched, const std::function<void(size_t)> &fn)
+{
+    HostPool::get().run(ntasks, threads_for(bytes_touched), fn);
+}
+
 void host_narrow_f64_to_f32(const double *src, float *dst, size_t n)
 {
     const size_t grain = (size_t)1 << 15; // 256 KiB of doubles per task: small calls still spread over the pool
@@ -184,6 +237,31 @@ void host_narrow_f64_to_f32(const double *src, float *dst, size_t n)
         const size_t a = t * grain, b = std::min(n, a + grain);
         narrow_block(src + a, dst + a, b - a);
     });
+}
+
+// Column ids on the wire (streamed level-1 calls): ids below 2^16 / 2^20 / 2^24 travel as 2 / 2.5 / 3 bytes per
+// entry instead of 4 — [uint16 low halves][high nibbles or bytes], unpacked by k_unpack_indices on the device.
+int index_pack_hi_bits(int K) { return K <= (1 << 16) ? 0 : (K <= (1 << 20) ? 4 : (K <= (1 << 24) ? 8 : -1)); }
+
+size_t packed_index_lo_bytes(size_t n) { return (2 * n + 15) & ~(size_t)15; }
+
+size_t packed_index_bytes(size_t n, int hi_bits)
+{
+    const size_t hi = hi_bits == 0 ? 0 : (hi_bits == 4 ? (n + 1) / 2 : n);
+    return packed_index_lo_bytes(n) + ((hi + 15) & ~(size_t)15);
+}
+
+bool host_pack_indices(const int32_t *j, size_t n, int K, int hi_bits, void *dst)
+{
+    uint16_t *lo = static_cast<uint16_t *>(dst);
+    unsigned char *hi = static_cast<unsigned char *>(dst) + packed_index_lo_bytes(n);
+    const size_t grain = (size_t)1 << 15; // entries per task (a multiple of 32: tasks never share a byte)
+    std::atomic<int> bad{0};
+    HostPool::get().run((n + grain - 1) / grain, threads_for(n * 8), [&](size_t t) {
+        const size_t a = t * grain, b = std::min(n, a + grain);
+        if (pack_block(j, a, b, K, hi_bits, lo, hi)) bad.store(1, std::memory_order_relaxed);
+    });
+    return bad.load() == 0;
 }
 
 void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst)

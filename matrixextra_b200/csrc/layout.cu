@@ -239,6 +239,39 @@ __global__ void __launch_bounds__(256) k_check_indices_flag(size_t nnz, const in
     if ((threadIdx.x & 31) == 0 && bad) atomicOr(flag, 1);
 }
 
+// Streamed path with packed column ids (hoststage.cu: host_pack_indices): rebuild the int32 ids of a chunk and
+// validate them in the same pass (packed ids cannot be negative; the host has already rejected those).
+template <int HI_BITS>
+__global__ void __launch_bounds__(256) k_unpack_indices(size_t n, const uint16_t *__restrict__ lo, const unsigned char *__restrict__ hi,
+                                                        int K, int32_t *__restrict__ out, int *__restrict__ flag)
+{
+    int bad = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        int c = (int)__ldg(lo + e);
+        if (HI_BITS == 8) c |= (int)__ldg(hi + e) << 16;
+        if (HI_BITS == 4) c |= (int)((__ldg(hi + (e >> 1)) >> ((e & 1) * 4)) & 15u) << 16;
+        out[e] = c;
+        bad |= (c >= K);
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicOr(flag, 1);
+}
+
+int unpack_indices_flag(size_t n, const void *d_packed, int hi_bits, int K, int32_t *d_j, int *d_flag, cudaStream_t stream)
+{
+    if (n == 0) return MXG_OK;
+    const uint16_t *lo = static_cast<const uint16_t *>(d_packed);
+    const unsigned char *hi = static_cast<const unsigned char *>(d_packed) + packed_index_lo_bytes(n);
+    int g = ceil_div_i((long long)n, 256 * 8);
+    if (g > 148 * 16) g = 148 * 16;
+    if (hi_bits == 0) MXG_LAUNCH(k_unpack_indices<0>, g, 256, 0, stream, n, lo, hi, K, d_j, d_flag);
+    else if (hi_bits == 4) MXG_LAUNCH(k_unpack_indices<4>, g, 256, 0, stream, n, lo, hi, K, d_j, d_flag);
+    else if (hi_bits == 8) MXG_LAUNCH(k_unpack_indices<8>, g, 256, 0, stream, n, lo, hi, K, d_j, d_flag);
+    else return fail(MXG_ERR_ARG, "unpack_indices: hi_bits %d", hi_bits);
+    return MXG_OK;
+}
+
 int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream)
 {
     if (nnz == 0) return MXG_OK;

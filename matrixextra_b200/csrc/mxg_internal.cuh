@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <string>
 #include <atomic>
+#include <functional>
 
 #include "../../include/mxgpu.h"
 
@@ -61,6 +62,7 @@ struct Options {
     long host_threads = 0;    // host threads of the staging engine (hoststage.cu); 0 = auto (all logical CPUs, <= 16)
     long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry)
     long host_stage = 1;      // bounce pageable caller memory through the page-locked arena with the host threads
+    long host_pack = 1;       // streamed calls: column ids cross PCIe as 2 / 2.5 / 3 bytes (K <= 2^16 / 2^20 / 2^24), packed by the host threads
     long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
     long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
 };
@@ -127,11 +129,22 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
                   const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc);
 int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
                   const void *y, void *out);
+void last_call_bytes(size_t *h2d, size_t *d2h);
+int host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks, int *n_long,
+                    int *n_pieces, int *max_len);
 int check_indices_flag(size_t nnz, const int32_t *d_j, int K, int *d_flag, cudaStream_t stream);
+int unpack_indices_flag(size_t n, const void *d_packed, int hi_bits, int K, int32_t *d_j, int *d_flag, cudaStream_t stream);
 
 // hoststage.cu: worker threads + page-locked arena for pageable caller memory and host-side narrowing
 int host_threads();
+// fn(0 .. ntasks-1) on the calling thread plus pool workers (one per MiB of bytes_touched, up to host_threads())
+void host_parallel_for(size_t ntasks, size_t bytes_touched, const std::function<void(size_t)> &fn);
 void host_narrow_f64_to_f32(const double *src, float *dst, size_t n);
+// column ids as [uint16 low halves][high nibbles / bytes] (2, 2.5 or 3 bytes per entry on the wire)
+int index_pack_hi_bits(int K);                      // 0, 4, 8, or -1 when K > 2^24 (ids travel as int32)
+size_t packed_index_lo_bytes(size_t n);             // offset of the high parts
+size_t packed_index_bytes(size_t n, int hi_bits);
+bool host_pack_indices(const int32_t *j, size_t n, int K, int hi_bits, void *dst); // false: an id outside [0, K)
 // nt_dst: the destination is a ring slot the DMA engine reads next -> cache-bypassing stores
 void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst = false);
 void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, bool nt_dst = false);

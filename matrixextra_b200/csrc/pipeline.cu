@@ -38,6 +38,7 @@ struct Trace {
     bool on = false;
     std::chrono::steady_clock::time_point t0;
     double wait_ms = 0, fill_ms = 0, drain_wait_ms = 0, drain_ms = 0, plan_ms = 0, finish_ms = 0;
+    int packed_chunks = 0;
     Trace()
     {
         const char *e = getenv("MXG_TRACE");
@@ -67,10 +68,10 @@ struct Trace {
             cudaEventElapsedTime(&comp, g[1], g[2]);
             cudaEventElapsedTime(&down, g[2], g[3]);
         }
-        fprintf(stderr, "[mxg trace] %s: %d chunks, total %.2f ms | plan %.2f | slot waits %.2f | host fill %.2f | "
+        fprintf(stderr, "[mxg trace] %s: %d chunks (%d with packed ids), total %.2f ms | plan %.2f | slot waits %.2f | host fill %.2f | "
                         "out waits %.2f | out copies %.2f | finish %.2f | gpu: uploads %.3f, last kernel after last upload %.3f, "
                         "last download %.3f\n",
-                what, chunks, now(), plan_ms, wait_ms, fill_ms, drain_wait_ms, drain_ms, finish_ms, up, comp, down);
+                what, chunks, packed_chunks, now(), plan_ms, wait_ms, fill_ms, drain_wait_ms, drain_ms, finish_ms, up, comp, down);
     }
 };
 
@@ -87,8 +88,9 @@ struct HostPlan {
     size_t max_chunk_rows = 0;
 };
 
-// One pass over the host indptr: chunk boundaries, monotonicity check, long-row tables (the host twin of
-// k_row_stats / k_fill_long_tables in layout.cu; same table format, rows numbered from the chunk start).
+// The host indptr -> chunk boundaries, monotonicity check, long-row tables (the host twin of k_row_stats /
+// k_fill_long_tables in layout.cu; same table format, rows numbered from the chunk start).  The scan over the rows
+// (validity, longest row, long rows) runs on the host threads; boundaries are binary searches in the indptr.
 int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
 {
     plan.piece = (int)std::max<long>(32, options().piece);
@@ -101,33 +103,80 @@ int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
         const int64_t cap = std::max<int64_t>(1 << 16, ((int64_t)64 << 20) / (int64_t)out_row_bytes);
         target_rows = (int)std::min<int64_t>(target_rows, cap);
     }
-    if (options().pipe_chunk_nnz > 0) { // tests: force many small chunks
+    const bool forced = options().pipe_chunk_nnz > 0; // tests: many small chunks of exactly this size
+    if (forced) {
         target_nnz = options().pipe_chunk_nnz;
         target_rows = (int)std::min<int64_t>(target_nnz, INT32_MAX);
     }
+
+    // 1. scan: every task owns a range of rows and reports its long rows in row order
+    struct Part {
+        int bad = 0, max_len = 0;
+        std::vector<int> long_rows;
+    };
+    const size_t grain = (size_t)1 << 16;
+    const size_t ntasks = ((size_t)m + grain - 1) / grain;
+    std::vector<Part> parts(ntasks);
+    const int piece = plan.piece;
+    host_parallel_for(ntasks, (size_t)m * sizeof(int32_t), [&](size_t t) {
+        Part &q = parts[t];
+        const int r0 = (int)(t * grain), r1 = (int)std::min<size_t>((size_t)m, (t + 1) * grain);
+        int bad = 0, mx = 0;
+        for (int r = r0; r < r1; r++) {
+            const int a = p[r], b = p[r + 1];
+            bad |= (a < 0) | (b < a);
+            const int len = b - a;
+            mx = std::max(mx, len);
+            if (len > piece && !bad) q.long_rows.push_back(r);
+        }
+        q.bad = bad;
+        q.max_len = mx;
+    });
+    for (const Part &q : parts) {
+        if (q.bad) return fail(MXG_ERR_INDEX, "CSR indptr is negative or decreasing");
+        plan.max_len = std::max(plan.max_len, q.max_len);
+    }
+
+    // 2. boundaries: a chunk ends at the first row that brings it to the target (entries or rows).  Towards the end
+    // of the matrix the chunks shrink (a third of what is left, down to an eighth of the target): what follows the
+    // last upload — that chunk's kernel and its download — is exposed, so the last chunk should be a small one.
     plan.chunk_row.push_back(0);
+    for (int start = 0; start < m;) {
+        const int64_t first = p[start];
+        int64_t tn = target_nnz;
+        int tr = target_rows;
+        if (!forced) {
+            tn = std::min(tn, std::max<int64_t>(target_nnz / 8, (nnz - first) / 3));
+            tr = (int)std::min<int64_t>(tr, std::max<int64_t>(target_rows / 8, (int64_t)(m - start) / 3));
+        }
+        const int32_t *hit = std::lower_bound(p + start + 1, p + m + 1, first + tn,
+                                              [](int32_t v, int64_t want) { return (int64_t)v < want; });
+        int end = (int)std::min<int64_t>(hit - p, (int64_t)start + tr);
+        end = std::min(std::max(end, start + 1), m);
+        plan.chunk_row.push_back(end);
+        plan.max_chunk_nnz = std::max(plan.max_chunk_nnz, (size_t)((int64_t)p[end] - first));
+        plan.max_chunk_rows = std::max(plan.max_chunk_rows, (size_t)(end - start));
+        start = end;
+    }
+
+    // 3. long-row tables per chunk
     plan.chunk_long_off.push_back(0);
     plan.chunk_piece_off.push_back(0);
-    int chunk_start = 0;
-    int64_t chunk_first = 0;
+    size_t c = 0; // chunk of the current long row
     int pieces_in_chunk = 0;
-    auto close_chunk = [&](int row_end) {
-        plan.chunk_row.push_back(row_end);
+    auto close_chunk = [&]() {
         plan.chunk_long_off.push_back((int)plan.long_rows.size());
         plan.chunk_piece_off.push_back((int)plan.piece_row.size());
         plan.max_chunk_pieces = std::max(plan.max_chunk_pieces, pieces_in_chunk);
-        plan.max_chunk_nnz = std::max(plan.max_chunk_nnz, (size_t)((int64_t)p[row_end] - chunk_first));
-        plan.max_chunk_rows = std::max(plan.max_chunk_rows, (size_t)(row_end - chunk_start));
-        chunk_start = row_end;
-        chunk_first = p[row_end];
         pieces_in_chunk = 0;
+        c++;
     };
-    for (int r = 0; r < m; r++) {
-        const int a = p[r], b = p[r + 1];
-        if (a < 0 || b < a) return fail(MXG_ERR_INDEX, "CSR indptr is negative or decreasing");
-        const int len = b - a;
-        plan.max_len = std::max(plan.max_len, len);
-        if (len > plan.piece) {
+    const size_t C = plan.chunk_row.size() - 1;
+    for (const Part &q : parts)
+        for (int r : q.long_rows) {
+            while (r >= plan.chunk_row[c + 1]) close_chunk();
+            const int chunk_start = plan.chunk_row[c];
+            const int len = p[r + 1] - p[r];
             const int np = (len + plan.piece - 1) / plan.piece;
             plan.long_rows.push_back(r - chunk_start);
             plan.long_first.push_back(pieces_in_chunk);
@@ -138,9 +187,7 @@ int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
             }
             pieces_in_chunk += np;
         }
-        if ((int64_t)b - chunk_first >= target_nnz || r + 1 - chunk_start >= target_rows) close_chunk(r + 1);
-    }
-    if (chunk_start < m) close_chunk(m);
+    while (c < C) close_chunk();
     return MXG_OK;
 }
 
@@ -184,12 +231,24 @@ int chain(Scratch &sc, cudaStream_t earlier, cudaStream_t later)
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// bytes the most recent streamed call of this thread moved over PCIe (mxg_last_call_bytes; bench.py reports them)
+thread_local size_t g_h2d_bytes = 0, g_d2h_bytes = 0;
+
+cudaError_t copy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    (kind == cudaMemcpyHostToDevice ? g_h2d_bytes : g_d2h_bytes) += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, stream);
+}
+
 int copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
               cudaStream_t stream)
 {
     if (width == 0 || height == 0) return MXG_OK;
-    if (dpitch == width && spitch == width) MXG_CUDA_TRY(cudaMemcpyAsync(dst, src, width * height, kind, stream));
-    else MXG_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, stream));
+    if (dpitch == width && spitch == width) MXG_CUDA_TRY(copy_async(dst, src, width * height, kind, stream));
+    else {
+        (kind == cudaMemcpyHostToDevice ? g_h2d_bytes : g_d2h_bytes) += width * height;
+        MXG_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, stream));
+    }
     return MXG_OK;
 }
 
@@ -264,6 +323,12 @@ struct CsrStream {
     bool staging_unavailable = false; // the arena could not be allocated: every copy takes the driver's path
     bool narrow_on_host = false; // float32 values are produced by the host threads, no device narrowing
     bool stage_x = false, stage_j = false;
+    // column ids packed by the host threads (2 / 2.5 / 3 bytes per entry) and unpacked on the device: decided per
+    // chunk (pack_mode 1: while the link is the bottleneck; 2: always)
+    bool pack_j = false;
+    int pack_mode = 0, hi_bits = -1;
+    std::vector<char> chunk_packed; // [C]
+    int pack_buf_last[3] = {-1, -1, -1}; // the last packed chunk that used d_pack[b]
     size_t x_part = 0; // bytes of a slot reserved for the values (indices follow)
     InRing ring;       // slots for chunk uploads (also used for the dense operand before the first chunk)
     char *out_base = nullptr; // ring of output slots (one per chunk, c % out_slots)
@@ -274,11 +339,12 @@ struct CsrStream {
     float *d_x32 = nullptr;
     static constexpr int NSTAGE = 3;
     double *d_stage[NSTAGE] = {nullptr, nullptr, nullptr};
+    char *d_pack[NSTAGE] = {nullptr, nullptr, nullptr};
     int32_t *d_tables = nullptr;
     int *d_flag = nullptr;
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
-    std::vector<cudaEvent_t> ev_h2d, ev_conv;
+    std::vector<cudaEvent_t> ev_h2d, ev_conv, ev_unpack;
 
     CsrStream(Scratch &s, int m_, int K_, const int32_t *p_, const int32_t *j_, const double *x_, bool narrow_)
         : sc(s), m(m_), K(K_), nnz(p_[m_]), p(p_), j(j_), x(x_), narrow(narrow_)
@@ -294,10 +360,20 @@ struct CsrStream {
         const bool stage = options().host_stage != 0;
         narrow_on_host = narrow && options().host_narrow != 0 && nnz > 0;
         stage_x = nnz > 0 && (narrow_on_host || (stage && !host_is_pinned(x)));
-        stage_j = nnz > 0 && stage && !host_is_pinned(j);
+        // Packed column ids pay while the call is PCIe-bound and the host threads have time to spare; a packed chunk
+        // costs them more memory traffic (read 4, write 2-3 bytes per entry), so when they are also narrowing values
+        // or bouncing a result they can become the bottleneck instead.  upload_chunk() therefore decides chunk by
+        // chunk from the state of the upload stream (profiles/r01_v7_e2e_packed_ids.jsonl).  Only for long calls and
+        // a full pool; host_pack = 2 packs every chunk whatever the size (tests).
+        hi_bits = index_pack_hi_bits(K);
+        pack_mode = (int)options().host_pack;
+        pack_j = stage && hi_bits >= 0 && nnz > 0 &&
+                 (pack_mode == 2 || (pack_mode == 1 && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
+        stage_j = nnz > 0 && stage && !host_is_pinned(j); // unpacked ids are bounced through the slot
         auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
         x_part = stage_x ? up(plan.max_chunk_nnz * (narrow_on_host ? sizeof(float) : sizeof(double))) : 0;
-        size_t in_slot = x_part + (stage_j ? up(plan.max_chunk_nnz * sizeof(int32_t)) : 0);
+        size_t in_slot = x_part + std::max(pack_j ? up(packed_index_bytes(plan.max_chunk_nnz, hi_bits)) : 0,
+                                           stage_j ? up(plan.max_chunk_nnz * sizeof(int32_t)) : 0);
         if (dense_pageable && stage) in_slot = std::max(in_slot, (size_t)16 << 20);
         const int S = (int)std::min<long>(std::max<long>(options().pipe_slots, 3), 8);
         out_slots = out_row_bytes > 0 && stage ? S : 0;
@@ -309,7 +385,7 @@ struct CsrStream {
                 // no page-locked memory to be had (ulimit -l, fragmentation): the plain driver copies still work
                 cudaGetLastError();
                 last_error_ref().clear();
-                narrow_on_host = stage_x = stage_j = false;
+                narrow_on_host = stage_x = stage_j = pack_j = false;
                 x_part = 0;
                 out_slots = 0;
                 out_slot_bytes = 0;
@@ -335,7 +411,7 @@ struct CsrStream {
         MXG_TRY(sc.alloc((void **)&d_flag, sizeof(int)));
         MXG_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st->stream));
         MXG_TRY(chain(sc, st->stream, st->h2d));
-        MXG_CUDA_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, st->h2d));
+        MXG_CUDA_TRY(copy_async(d_p, p, sizeof(int32_t) * ((size_t)m + 1), cudaMemcpyHostToDevice, st->h2d));
         const size_t nl = plan.long_rows.size(), np = plan.piece_row.size();
         if (nl > 0) {
             MXG_TRY(sc.alloc((void **)&d_tables, sizeof(int32_t) * (3 * nl + 2 * np)));
@@ -345,7 +421,7 @@ struct CsrStream {
             const std::vector<int32_t> *src[5] = {&plan.long_rows, &plan.long_first, &plan.long_np, &plan.piece_row, &plan.piece_k};
             size_t off = 0;
             for (int t = 0; t < 5; t++) {
-                MXG_CUDA_TRY(cudaMemcpyAsync(d_tables + off, src[t]->data(), sizeof(int32_t) * src[t]->size(),
+                MXG_CUDA_TRY(copy_async(d_tables + off, src[t]->data(), sizeof(int32_t) * src[t]->size(),
                                              cudaMemcpyHostToDevice, st->h2d));
                 off += src[t]->size();
             }
@@ -355,11 +431,19 @@ struct CsrStream {
             for (int b = 0; b < NSTAGE && b < chunks(); b++) MXG_TRY(sc.alloc((void **)&d_stage[b], sizeof(double) * stage_n));
             MXG_TRY(chain(sc, st->stream, st->h2d));
         }
+        if (pack_j) {
+            for (int b = 0; b < NSTAGE && b < chunks(); b++)
+                MXG_TRY(sc.alloc((void **)&d_pack[b], packed_index_bytes(plan.max_chunk_nnz, hi_bits)));
+            MXG_TRY(chain(sc, st->stream, st->h2d));
+        }
         ev_h2d.resize((size_t)chunks());
         ev_conv.resize((size_t)chunks());
+        ev_unpack.resize((size_t)chunks());
+        chunk_packed.assign((size_t)chunks(), 0);
         for (int c = 0; c < chunks(); c++) {
             MXG_TRY(sc.event(&ev_h2d[(size_t)c]));
             if (narrow && !narrow_on_host) MXG_TRY(sc.event(&ev_conv[(size_t)c]));
+            if (pack_j) MXG_TRY(sc.event(&ev_unpack[(size_t)c]));
         }
         return MXG_OK;
     }
@@ -372,14 +456,20 @@ struct CsrStream {
         const size_t len = (size_t)(e1 - e0);
         if (len > 0) {
             char *slot = nullptr;
-            if (stage_x || stage_j) MXG_TRY(ring.acquire(&slot));
+            // Pack this chunk's ids?  Yes while uploads are queueing up (the chunk before the previous one has not
+            // arrived yet: the link is behind the host); no when the link is about to run dry (the host is behind).
+            // The first two chunks queue behind the dense operand.
+            const bool pk = pack_j && (pack_mode == 2 || c < 2 || cudaEventQuery(ev_h2d[(size_t)(c - 2)]) == cudaErrorNotReady);
+            cudaGetLastError(); // cudaErrorNotReady is an answer, not an error
+            chunk_packed[(size_t)c] = pk;
+            if (stage_x || stage_j || pk) MXG_TRY(ring.acquire(&slot));
             // values: float32 made on the host -> d_x32; float64 -> d_x64, or -> device staging + narrowing kernel
             const void *xsrc = x + e0;
             const double tf = g_trace ? g_trace->now() : 0;
             if (narrow_on_host) {
                 host_narrow_f64_to_f32(x + e0, reinterpret_cast<float *>(slot), len);
                 if (g_trace) g_trace->fill_ms += g_trace->now() - tf;
-                MXG_CUDA_TRY(cudaMemcpyAsync(d_x32 + e0, slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
+                MXG_CUDA_TRY(copy_async(d_x32 + e0, slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
             } else {
                 if (stage_x) {
                     host_copy(slot, x + e0, sizeof(double) * len, /*nt_dst=*/true);
@@ -389,19 +479,32 @@ struct CsrStream {
                 if (narrow) {
                     // the device staging buffer is free again once the narrowing of chunk c - NSTAGE has run
                     if (c >= NSTAGE) MXG_CUDA_TRY(cudaStreamWaitEvent(st->h2d, ev_conv[(size_t)(c - NSTAGE)], 0));
-                    MXG_CUDA_TRY(cudaMemcpyAsync(d_stage[c % NSTAGE], xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                    MXG_CUDA_TRY(copy_async(d_stage[c % NSTAGE], xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
                 } else {
-                    MXG_CUDA_TRY(cudaMemcpyAsync(d_x64 + e0, xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                    MXG_CUDA_TRY(copy_async(d_x64 + e0, xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
                 }
             }
             const void *jsrc = j + e0;
-            if (stage_j) {
+            if (pk) {
+                const double tj = g_trace ? g_trace->now() : 0;
+                if (!host_pack_indices(j + e0, len, K, hi_bits, slot + x_part))
+                    return fail(MXG_ERR_INDEX, "CSR column index outside [0, %d)", K);
+                if (g_trace) {
+                    g_trace->fill_ms += g_trace->now() - tj;
+                    g_trace->packed_chunks++;
+                }
+                // the device staging buffer is free again once the chunk that used it last has been unpacked
+                const int b = c % NSTAGE;
+                if (pack_buf_last[b] >= 0) MXG_CUDA_TRY(cudaStreamWaitEvent(st->h2d, ev_unpack[(size_t)pack_buf_last[b]], 0));
+                pack_buf_last[b] = c;
+                MXG_CUDA_TRY(copy_async(d_pack[b], slot + x_part, packed_index_bytes(len, hi_bits), cudaMemcpyHostToDevice, st->h2d));
+            } else if (stage_j) {
                 const double tj = g_trace ? g_trace->now() : 0;
                 host_copy(slot + x_part, j + e0, sizeof(int32_t) * len, /*nt_dst=*/true);
                 jsrc = slot + x_part;
                 if (g_trace) g_trace->fill_ms += g_trace->now() - tj;
             }
-            MXG_CUDA_TRY(cudaMemcpyAsync(d_j + e0, jsrc, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
+            if (!pk) MXG_CUDA_TRY(copy_async(d_j + e0, jsrc, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
             if (slot) MXG_TRY(ring.release(st->h2d));
         }
         MXG_CUDA_TRY(cudaEventRecord(ev_h2d[(size_t)c], st->h2d));
@@ -423,7 +526,12 @@ struct CsrStream {
             }
             MXG_CUDA_TRY(cudaEventRecord(ev_conv[(size_t)c], st->stream));
         }
-        MXG_TRY(check_indices_flag(len, d_j + e0, K, d_flag, st->stream));
+        if (chunk_packed[(size_t)c]) {
+            MXG_TRY(unpack_indices_flag(len, d_pack[c % NSTAGE], hi_bits, K, d_j + e0, d_flag, st->stream));
+            MXG_CUDA_TRY(cudaEventRecord(ev_unpack[(size_t)c], st->stream));
+        } else {
+            MXG_TRY(check_indices_flag(len, d_j + e0, K, d_flag, st->stream));
+        }
         const size_t nl = plan.long_rows.size(), np = plan.piece_row.size();
         const int l0 = plan.chunk_long_off[(size_t)c], l1 = plan.chunk_long_off[(size_t)c + 1];
         const int q0 = plan.chunk_piece_off[(size_t)c], q1 = plan.chunk_piece_off[(size_t)c + 1];
@@ -461,7 +569,7 @@ struct CsrStream {
     {
         DeviceState *st = sc.st;
         int flag = 0;
-        MXG_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st->stream));
+        MXG_CUDA_TRY(copy_async(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st->stream));
         MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
         MXG_CUDA_TRY(cudaStreamSynchronize(st->d2h));
         MXG_CUDA_TRY(cudaStreamSynchronize(st->h2d));
@@ -471,6 +579,30 @@ struct CsrStream {
 };
 
 } // namespace
+
+void last_call_bytes(size_t *h2d, size_t *d2h)
+{
+    if (h2d) *h2d = g_h2d_bytes;
+    if (d2h) *d2h = g_d2h_bytes;
+}
+
+// the chunk plan of a streamed call, for inspection (mxg_host_chunk_plan; no device involved)
+int host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks, int *n_long,
+                    int *n_pieces, int *max_len)
+{
+    HostPlan plan;
+    MXG_TRY(build_plan(m, p, plan, result_row_bytes));
+    const int C = (int)plan.chunk_row.size() - 1;
+    if (n_chunks) *n_chunks = C;
+    if (n_long) *n_long = (int)plan.long_rows.size();
+    if (n_pieces) *n_pieces = (int)plan.piece_row.size();
+    if (max_len) *max_len = plan.max_len;
+    if (chunk_rows) {
+        if (cap < C + 1) return fail(MXG_ERR_ARG, "chunk_plan: %d boundaries do not fit %d slots", C + 1, cap);
+        for (int c = 0; c <= C; c++) chunk_rows[c] = plan.chunk_row[(size_t)c];
+    }
+    return MXG_OK;
+}
 
 int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
                   const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc)
@@ -490,6 +622,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     const int64_t nnz = p[m];
     if (nnz > 0 && (!j || !x)) return fail(MXG_ERR_ARG, "csr: indices / values is NULL");
 
+    g_h2d_bytes = g_d2h_bytes = 0;
     Trace trace;
     struct TraceScope {
         explicit TraceScope(Trace *t) { g_trace = t->on ? t : nullptr; }
@@ -593,6 +726,7 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
     const size_t ys = ytype == MXG_Y_NUMERIC ? 8 : 4;
     const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
 
+    g_h2d_bytes = g_d2h_bytes = 0;
     Scratch sc(st);
     CsrStream cs(sc, m, K, p, j, x, /*narrow=*/false);
     const bool stage = options().host_stage != 0;
@@ -628,7 +762,7 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
         MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
         if (nr == 0) return MXG_OK;
         char *dst = stage_out ? cs.out_slot(c) : static_cast<char *>(out) + r0 * os;
-        MXG_CUDA_TRY(cudaMemcpyAsync(dst, d_out + r0 * os, nr * os, cudaMemcpyDeviceToHost, st->d2h));
+        MXG_CUDA_TRY(copy_async(dst, d_out + r0 * os, nr * os, cudaMemcpyDeviceToHost, st->d2h));
         if (stage_out) MXG_CUDA_TRY(cudaEventRecord(ev_out[(size_t)c], st->d2h));
         return MXG_OK;
     };

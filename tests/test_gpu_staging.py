@@ -3,6 +3,7 @@ pageable caller memory bounced through the page-locked ring by the host threads,
 host.  Whatever route the bytes take — pageable or page-locked operands, host or device narrowing, staging on or
 off, one thread or many, few ring slots and many chunks — the result must be the SAME BITS, and within the
 north_star tolerance of the CPU oracle (src/matmul.cpp:118-185, 381-483)."""
+import ctypes as C
 import itertools
 
 import numpy as np
@@ -22,7 +23,7 @@ def rx():
 @pytest.fixture()
 def options():
     from matrixextra_b200 import _lib
-    names = ("pipe_chunk_nnz", "piece", "host_narrow", "host_stage", "host_threads", "pipe_slots", "host_arena_max_mb")
+    names = ("pipe_chunk_nnz", "piece", "host_narrow", "host_stage", "host_threads", "pipe_slots", "host_arena_max_mb", "host_pack")
     old = {k: _lib.get_option(k) for k in names}
     yield _lib
     for k, v in old.items():
@@ -58,8 +59,9 @@ def test_every_staging_route_gives_the_same_bits(rx, port, options, dtype):
     pX = _pinned_f((n, K), dtype)
     pX[...] = X
     ref_rm = ref_cm = None
-    routes = itertools.product((0, 1), (0, 1), (1, 5), (False, True), (3, 8))
-    for narrow, stage, threads, pinned, slots in routes:
+    routes = itertools.product((0, 1), (0, 1), (1, 5), (False, True), (3, 8), (0, 2))
+    for narrow, stage, threads, pinned, slots, pack in routes:
+        options.set_option("host_pack", pack)  # 2: column ids packed on the host whatever the size (K = 1500: 2 bytes each)
         options.set_option("host_narrow", narrow)
         options.set_option("host_stage", stage)
         options.set_option("pipe_slots", slots)
@@ -71,7 +73,7 @@ def test_every_staging_route_gives_the_same_bits(rx, port, options, dtype):
         if ref_rm is None:
             ref_rm, ref_cm = got_rm.copy(), got_cm.copy()
             assert rel_err(ref_rm, want_rm) <= tol and rel_err(ref_cm, want_cm) <= tol
-        route = dict(narrow=narrow, stage=stage, threads=threads, pinned=pinned, slots=slots)
+        route = dict(narrow=narrow, stage=stage, threads=threads, pinned=pinned, slots=slots, pack=pack)
         assert np.array_equal(got_rm, ref_rm), route
         assert np.array_equal(got_cm, ref_cm), route
 
@@ -261,3 +263,58 @@ def test_one_shot_staged_copies_wrap_their_ring(rx, options):
     p2, i2, x2 = rx.csr_to_csc(m, K, p, j, x)
     S = sp.csr_matrix((x, j, p), shape=(m, K)).tocsc()
     assert np.array_equal(p2, S.indptr) and np.array_equal(i2, S.indices) and np.array_equal(x2, S.data)
+
+
+@pytest.mark.parametrize("K", [40_000, 70_000, 1_000_000, 1_100_000, 16_777_216, 16_777_217])
+def test_packed_column_ids_every_width(rx, port, options, K):
+    """Column ids cross PCIe as 2 / 2.5 / 3 bytes per entry (host_pack, csrc/hoststage.cu + k_unpack_indices) or as
+    int32 above 2^24 columns: same bits as the unpacked route for SpMM (float32, host-narrowed values sharing the
+    slot) and SpMV (float64), odd chunk starts, ids at both ends of the range."""
+    m, n = 3000, 4
+    rng = np.random.default_rng(K % 977)
+    rows = [np.unique(rng.integers(0, K, size=l)) for l in rng.integers(0, 9, size=m)]  # sorted, unique
+    rows[0] = np.union1d(rows[0], [0])
+    rows[-1] = np.union1d(rows[-1], [K - 1])
+    p = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum([len(r) for r in rows], out=p[1:])
+    j = np.concatenate(rows).astype(np.int32)
+    x = rng.uniform(-1, 1, size=p[-1])
+    v = rng.standard_normal(K)
+    X = np.asfortranarray(rng.standard_normal((n, 1)).astype(np.float32) * np.ones((1, K), dtype=np.float32))
+    X[:, ::7] *= -0.5
+    options.set_option("pipe_chunk_nnz", 777)
+    got, moved = {}, {}
+    for pack in (0, 2):
+        options.set_option("host_pack", pack)
+        got[pack] = (rx.tcrossprod_dense_csr_float32(X, p, j, x, 4, K), rx.matmul_csr_dvec_numeric(p, _pinned(j), _pinned(x), v, 4))
+        h2d, d2h = C.c_size_t(0), C.c_size_t(0)
+        options.call("mxg_last_call_bytes", C.byref(h2d), C.byref(d2h))  # of the SpMV call
+        moved[pack] = (h2d.value, d2h.value)
+    assert np.array_equal(got[0][0], got[2][0]) and np.array_equal(got[0][1], got[2][1])
+    nnz = int(p[-1])
+    raw = 4 * (m + 1) + 12 * nnz + 8 * K
+    assert raw <= moved[0][0] <= raw + 4096 and moved[0][1] == moved[2][1] == 8 * m + 4  # + the validation flag
+    if K <= 1 << 24:  # 2, 2.5 or 3 bytes per id, every chunk padded to 2 x 16 bytes
+        per_id = 2 if K <= 1 << 16 else (2.5 if K <= 1 << 20 else 3)
+        assert moved[0][0] - (4 - per_id) * nnz <= moved[2][0] <= moved[0][0] - (4 - per_id) * nnz + 33 * (nnz // 777 + m // 777 + 4)
+    else:
+        assert moved[2][0] == moved[0][0]
+    assert rel_err(got[2][0], port.tcrossprod_dense_csr_float32(X, p, j, x, 1, K)) <= FP32_TOL
+    assert rel_err(got[2][1], port.matmul_csr_dvec_numeric(p, j, x, v, 1)) <= FP64_TOL
+
+
+@pytest.mark.parametrize("bad", [-1, "K", "K+70000"])
+def test_packed_column_ids_out_of_range_is_an_error(rx, options, bad):
+    """The packed route keeps the streamed call's validation: a negative id is caught by the host threads while
+    packing, one at or beyond K by the device when the chunk is unpacked; both fail like the unpacked route."""
+    from matrixextra_b200._lib import MxgError
+    m, K, n = 500, 70_000, 4
+    p, j, x = powerlaw_csr(m, K, 6, seed=3, cap=60)
+    j = j.copy()
+    j[len(j) // 2] = {-1: -1, "K": K, "K+70000": K + 70_000}[bad]
+    X = np.asfortranarray(np.ones((n, K), dtype=np.float32))
+    options.set_option("pipe_chunk_nnz", 500)
+    for pack in (0, 2):
+        options.set_option("host_pack", pack)
+        with pytest.raises(MxgError, match="column index outside"):
+            rx.tcrossprod_dense_csr_float32(X, p, j, x, 2, K)

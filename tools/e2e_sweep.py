@@ -40,6 +40,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="cfg3,k64f64,cfg2")
     ap.add_argument("--quick", action="store_true", help="default options only")
+    ap.add_argument("--slots", action="store_true", help="only: ring slots 4 / 6 / 8 x packed ids off / on")
+    ap.add_argument("--pack", action="store_true", help="only: packed column ids on / off (option host_pack), twice each")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     emit(cpus=os.cpu_count())
@@ -88,6 +90,18 @@ def main():
                 ms = timeit(f)
                 emit(workload=name, case=cname, tag=tag, opts=opts, ms=ms, gflops=flops / ms / 1e6)
 
+        if args.slots:
+            for rep in range(2):
+                for slots in (4, 6, 8):
+                    for pack in (0, 1):
+                        run("slots_x_pack", pipe_slots=slots, host_pack=pack)
+            continue
+        if args.pack:
+            for rep in range(2):
+                run("pack_off", host_pack=0)
+                run("pack_on", host_pack=1)
+                run("pack_forced", host_pack=2)
+            continue
         run("default")
         if args.quick:
             continue
