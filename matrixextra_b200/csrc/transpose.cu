@@ -100,6 +100,7 @@ constexpr int RS_MAX_BITS = 10;                   // widest digit the kernels su
 constexpr int RS_BINS = 1 << RS_MAX_BITS;
 constexpr int RS_HIST_THREADS = 256;
 constexpr int RS_DPT = RS_BINS / RS_THREADS;      // digits per thread in the tile-local scan (2)
+constexpr int RS_MIN_CTAS = 3;                   // register budget: 65536 / (3 * 512) = 42 per thread
 typedef unsigned short rs_cnt_t;                  // per-warp digit counters (<= RS_WARP_ITEMS) live in 16 bits
 
 // a) digit histogram of every tile, written digit-major: hist[d * ntiles + tile], d < nbins = 1 << nbits
@@ -136,15 +137,18 @@ struct RadixIO {
     int32_t *col_count; // last pass only: entries per column (-> p2); nullptr otherwise
 };
 
-constexpr size_t radix_smem_bytes(bool h64, bool h32)
+// shared memory of a scatter CTA: the tile's records + tables sized by the digit of the pass (128 bins: 69 KB with
+// float64 values, three CTAs per SM; 1024 bins: 104 KB, two)
+__host__ __device__ constexpr int radix_stride(int nbins) { return nbins < 2 ? 2 : nbins; }
+constexpr size_t radix_smem_bytes(bool h64, bool h32, int nbins)
 {
-    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(rs_cnt_t) * RS_WARPS * RS_BINS +
-           sizeof(int) * 2 * RS_BINS;
+    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(rs_cnt_t) * RS_WARPS * radix_stride(nbins) +
+           sizeof(int) * 2 * radix_stride(nbins);
 }
 
 // c) stable scatter.  offs = exclusive scan of hist (digit-major): first destination of (digit, tile).
 template <bool H64, bool H32>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const RadixIO io, int shift, int nbins,
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_radix_scatter(size_t n, const RadixIO io, int shift, int nbins,
                                                                  const int32_t *__restrict__ offs, int ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -152,9 +156,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
     int *s_key = reinterpret_cast<int *>(smem_raw + (H64 ? (size_t)RS_TILE * 8 : 0));       // [RS_TILE]
     int *s_row = s_key + RS_TILE;                                                            // [RS_TILE]
     float *s_x32 = reinterpret_cast<float *>(s_row + RS_TILE);                               // [RS_TILE] if H32
-    int *dig_off = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));           // [RS_BINS] tile-local digit starts
-    int *gdelta = dig_off + RS_BINS;                                                         // [RS_BINS] global - local
-    rs_cnt_t *wcnt = reinterpret_cast<rs_cnt_t *>(gdelta + RS_BINS);                         // [RS_WARPS][RS_BINS]
+    const int stride = radix_stride(nbins);                                                  // table rows are nbins wide
+    int *dig_off = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));           // [stride] tile-local digit starts
+    int *gdelta = dig_off + stride;                                                          // [stride] global - local
+    rs_cnt_t *wcnt = reinterpret_cast<rs_cnt_t *>(gdelta + stride);                          // [RS_WARPS][stride]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mask = nbins - 1;
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
         // pass can produce are cleared
         unsigned *z = reinterpret_cast<unsigned *>(wcnt);
         const int words = nbins > 1 ? nbins / 2 : 1;
-        for (int i = threadIdx.x; i < RS_WARPS * words; i += RS_THREADS) z[(i / words) * (RS_BINS / 2) + (i % words)] = 0u;
+        for (int i = threadIdx.x; i < RS_WARPS * words; i += RS_THREADS) z[i] = 0u; // words == stride / 2: rows are contiguous
     }
     __syncthreads();
 
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
     int key[RS_STEPS];
     int rank[RS_STEPS]; // rank of the entry among same-digit entries of this warp, in entry order
     const unsigned lt_mask = (1u << lane) - 1u;
-    rs_cnt_t *my_cnt = wcnt + warp * RS_BINS;
+    rs_cnt_t *my_cnt = wcnt + warp * stride;
 #pragma unroll
     for (int s = 0; s < RS_STEPS; s++) {
         const size_t e = w0 + (size_t)s * 32 + lane;
@@ -207,8 +212,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_radix_scatter(size_t n, const
             unsigned acc = 0;
 #pragma unroll
             for (int w = 0; w < RS_WARPS; w++) {
-                const unsigned c = wc32[w * (RS_BINS / 2) + threadIdx.x];
-                wc32[w * (RS_BINS / 2) + threadIdx.x] = acc;
+                const unsigned c = wc32[w * (stride / 2) + threadIdx.x];
+                wc32[w * (stride / 2) + threadIdx.x] = acc;
                 acc += c;
             }
             run[0] = (int)(acc & 0xffffu);
@@ -281,10 +286,11 @@ template <bool H64, bool H32>
 static int launch_radix_scatter(size_t n, const RadixIO &io, int shift, int nbins, const int32_t *offs, int ntiles,
                                 cudaStream_t stream)
 {
-    constexpr size_t smem = radix_smem_bytes(H64, H32);
+    const size_t smem = radix_smem_bytes(H64, H32, nbins);
     static bool configured = false;
     if (!configured) {
-        MXG_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<H64, H32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MXG_CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<H64, H32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)radix_smem_bytes(H64, H32, RS_BINS)));
         configured = true;
     }
     MXG_LAUNCH((k_radix_scatter<H64, H32>), ntiles, RS_THREADS, smem, stream, n, io, shift, nbins, offs, ntiles);
