@@ -167,12 +167,21 @@ def cpu_dense_operand(wl, rows, rng):
     raise ValueError(wl["op"])
 
 
+def host_cores():
+    """Host threads the reference may use: every CPU this process is allowed on.  Not omp_get_max_threads():
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would time a single-threaded reference."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(wl, p, j, x, budget_s=12.0):
     """Time the reference's CPU implementation on a bounded row sample of the SAME matrix."""
     from oracle.cpu_oracle import best_cpu_baseline
     cpu = best_cpu_baseline()
     cpu.copy_result = False
-    nthreads = cpu.max_threads
+    nthreads = host_cores()  # passed to the reference's `num_threads(nthreads)` clause
     m = p.size - 1
     rng = np.random.default_rng(99)
     # probe on ~1/32 of the rows, then size the sample for the time budget
@@ -635,7 +644,7 @@ def run_reference(args):
     wl = dict(WORKLOADS[args.workload])
     cpu = best_cpu_baseline()
     cpu.copy_result = False
-    nthreads = cpu.max_threads
+    nthreads = host_cores()  # passed to the reference's `num_threads(nthreads)` clause
     # bounded sample of the same workload: the first rows of the same synthetic matrix when a GPU is there to
     # generate it, else a host-generated matrix with the same row-length law
     m_s = max(1, wl["m"] // 8)
