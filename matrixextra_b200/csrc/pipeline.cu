@@ -324,7 +324,7 @@ struct CsrStream {
     bool narrow_on_host = false; // float32 values are produced by the host threads, no device narrowing
     bool stage_x = false, stage_j = false;
     // column ids packed by the host threads (2 / 2.5 / 3 bytes per entry) and unpacked on the device: decided per
-    // chunk (pack_mode 1: while the link is the bottleneck; 2: always)
+    // chunk (pack_mode 1: while the link is the bottleneck; 2: always; 3: two chunks out of three)
     bool pack_j = false;
     int pack_mode = 0, hi_bits = -1;
     std::vector<char> chunk_packed; // [C]
@@ -368,7 +368,7 @@ struct CsrStream {
         hi_bits = index_pack_hi_bits(K);
         pack_mode = (int)options().host_pack;
         pack_j = stage && hi_bits >= 0 && nnz > 0 &&
-                 (pack_mode == 2 || (pack_mode == 1 && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
+                 (pack_mode == 2 || pack_mode == 3 || (pack_mode == 1 && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
         stage_j = nnz > 0 && stage && !host_is_pinned(j); // unpacked ids are bounced through the slot
         auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
         x_part = stage_x ? up(plan.max_chunk_nnz * (narrow_on_host ? sizeof(float) : sizeof(double))) : 0;
@@ -459,7 +459,9 @@ struct CsrStream {
             // Pack this chunk's ids?  Yes while uploads are queueing up (the chunk before the previous one has not
             // arrived yet: the link is behind the host); no when the link is about to run dry (the host is behind).
             // The first two chunks queue behind the dense operand.
-            const bool pk = pack_j && (pack_mode == 2 || c < 2 || cudaEventQuery(ev_h2d[(size_t)(c - 2)]) == cudaErrorNotReady);
+            // (pack_mode 3, tests: a fixed mix — two chunks out of three)
+            const bool pk = pack_j && (pack_mode == 2 || (pack_mode == 3 ? c % 3 != 1
+                                                         : (c < 2 || cudaEventQuery(ev_h2d[(size_t)(c - 2)]) == cudaErrorNotReady)));
             cudaGetLastError(); // cudaErrorNotReady is an answer, not an error
             chunk_packed[(size_t)c] = pk;
             if (stage_x || stage_j || pk) MXG_TRY(ring.acquire(&slot));

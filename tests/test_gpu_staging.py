@@ -284,21 +284,24 @@ def test_packed_column_ids_every_width(rx, port, options, K):
     X[:, ::7] *= -0.5
     options.set_option("pipe_chunk_nnz", 777)
     got, moved = {}, {}
-    for pack in (0, 2):
+    for pack in (0, 2, 3, 1):  # off, every chunk, a fixed mix of packed and raw chunks, decided from the upload stream
         options.set_option("host_pack", pack)
         got[pack] = (rx.tcrossprod_dense_csr_float32(X, p, j, x, 4, K), rx.matmul_csr_dvec_numeric(p, _pinned(j), _pinned(x), v, 4))
         h2d, d2h = C.c_size_t(0), C.c_size_t(0)
         options.call("mxg_last_call_bytes", C.byref(h2d), C.byref(d2h))  # of the SpMV call
         moved[pack] = (h2d.value, d2h.value)
-    assert np.array_equal(got[0][0], got[2][0]) and np.array_equal(got[0][1], got[2][1])
+    for pack in (2, 3, 1):
+        assert np.array_equal(got[0][0], got[pack][0]) and np.array_equal(got[0][1], got[pack][1]), pack
     nnz = int(p[-1])
     raw = 4 * (m + 1) + 12 * nnz + 8 * K
     assert raw <= moved[0][0] <= raw + 4096 and moved[0][1] == moved[2][1] == 8 * m + 4  # + the validation flag
     if K <= 1 << 24:  # 2, 2.5 or 3 bytes per id, every chunk padded to 2 x 16 bytes
         per_id = 2 if K <= 1 << 16 else (2.5 if K <= 1 << 20 else 3)
         assert moved[0][0] - (4 - per_id) * nnz <= moved[2][0] <= moved[0][0] - (4 - per_id) * nnz + 33 * (nnz // 777 + m // 777 + 4)
+        assert moved[2][0] < moved[3][0] < moved[0][0]
     else:
-        assert moved[2][0] == moved[0][0]
+        assert moved[2][0] == moved[3][0] == moved[0][0]
+    assert moved[1][0] == moved[0][0]  # the automatic mode leaves a call of this size alone
     assert rel_err(got[2][0], port.tcrossprod_dense_csr_float32(X, p, j, x, 1, K)) <= FP32_TOL
     assert rel_err(got[2][1], port.matmul_csr_dvec_numeric(p, j, x, v, 1)) <= FP64_TOL
 
@@ -318,3 +321,33 @@ def test_packed_column_ids_out_of_range_is_an_error(rx, options, bad):
         options.set_option("host_pack", pack)
         with pytest.raises(MxgError, match="column index outside"):
             rx.tcrossprod_dense_csr_float32(X, p, j, x, 2, K)
+
+
+def test_packed_column_ids_automatic_mode_on_a_long_call(rx, options):
+    """A call long enough for the automatic mode (>= 2^20 entries, >= 8 host threads): chunks are packed or not
+    depending on how far the upload stream lags behind the host threads — whatever the mix, same bits."""
+    from matrixextra_b200._lib import MXG_KEEP_F64
+    from matrixextra_b200.device import DeviceCSR
+    m, K, n = 200_000, 300_000, 16
+    A = DeviceCSR.synth(m, K, 6_000_000, 1, 1, seed=123, keep=MXG_KEEP_F64)
+    p, j, x = A.to_host()
+    A.free()
+    rng = np.random.default_rng(123)
+    v = rng.standard_normal(K)
+    X = np.asfortranarray(rng.standard_normal((n, K)).astype(np.float32))
+    pj, px = _pinned(j), _pinned(x)
+    options.set_option("pipe_chunk_nnz", 250_000)  # ~24 chunks
+    got, moved = {}, {}
+    for pack in (0, 1, 1):
+        options.set_option("host_pack", pack)
+        mv = rx.matmul_csr_dvec_numeric(p, pj, px, v, 16)
+        h2d = C.c_size_t(0)
+        options.call("mxg_last_call_bytes", C.byref(h2d), None)
+        mm = rx.tcrossprod_dense_csr_float32(X, p, pj, px, 16, K)
+        if pack in got:
+            assert np.array_equal(mv, got[pack][0]) and np.array_equal(mm, got[pack][1])
+        got[pack], moved[pack] = (mv, mm), h2d.value
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    import os
+    if (os.cpu_count() or 1) >= 8:
+        assert moved[1] < moved[0]  # at least the first two chunks (queued behind the vector) go packed
