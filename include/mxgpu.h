@@ -81,10 +81,11 @@ int mxg_set_device(int device);
  *   host staging (csrc/hoststage.cu) : "host_threads" (threads that narrow / bounce host memory; the Rcpp exports'
  *             `nthreads`; 0 = all logical CPUs up to 16), "host_narrow" (float32 products narrow the float64 values on
  *             the host before the copy, 1), "host_stage" (pageable caller memory goes through the page-locked ring, 1),
- *             "host_pack" (streamed calls of >= 2^20 entries whose host threads are not busy narrowing values or
- *             bouncing a large result send column ids as 2 / 2.5 / 3 bytes per entry when the matrix has <= 2^16 /
+ *             "host_pack" (streamed calls of >= 2^20 entries whose host threads are not narrowing values send, while
+ *             the upload stream lags behind them, column ids as 2 / 2.5 / 3 bytes per entry when the matrix has <= 2^16 /
  *             2^20 / 2^24 columns: packed by the host threads, rebuilt on the device, 1; 2 = always, 3 = two chunks
- *             out of three: test modes),
+ *             out of three: test modes), "host_pack_lag" (a chunk is packed while the upload of the chunk this many
+ *             places before it is still pending, 2),
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
  *             copies are used). */
 int mxg_set_option(const char *name, long value);

@@ -63,6 +63,7 @@ struct Options {
     long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry)
     long host_stage = 1;      // bounce pageable caller memory through the page-locked arena with the host threads
     long host_pack = 1;       // streamed calls: column ids cross PCIe as 2 / 2.5 / 3 bytes (K <= 2^16 / 2^20 / 2^24), packed by the host threads
+    long host_pack_lag = 2;   // a chunk's ids are packed while the upload of the chunk this many places before it is pending
     long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
     long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
 };

@@ -364,11 +364,15 @@ struct CsrStream {
         // costs them more memory traffic (read 4, write 2-3 bytes per entry), so when they are also narrowing values
         // or bouncing a result they can become the bottleneck instead.  upload_chunk() therefore decides chunk by
         // chunk from the state of the upload stream (profiles/r01_v7_e2e_packed_ids.jsonl).  Only for long calls and
-        // a full pool; host_pack = 2 packs every chunk whatever the size (tests).
+        // a full pool, and not when the same threads narrow the values of a float32 product: there the fills are
+        // already within a third of the link time, packing makes them the critical path, and the outcome depends on
+        // the box (measured: -3 % on hosts that narrow 100 M values in 11.8 ms, +3..6 % on one that takes 16.5 ms).
+        // host_pack = 2 packs every chunk whatever the size (tests).
         hi_bits = index_pack_hi_bits(K);
         pack_mode = (int)options().host_pack;
         pack_j = stage && hi_bits >= 0 && nnz > 0 &&
-                 (pack_mode == 2 || pack_mode == 3 || (pack_mode == 1 && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
+                 (pack_mode == 2 || pack_mode == 3 ||
+                  (pack_mode == 1 && !narrow_on_host && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
         stage_j = nnz > 0 && stage && !host_is_pinned(j); // unpacked ids are bounced through the slot
         auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
         x_part = stage_x ? up(plan.max_chunk_nnz * (narrow_on_host ? sizeof(float) : sizeof(double))) : 0;
@@ -460,8 +464,9 @@ struct CsrStream {
             // arrived yet: the link is behind the host); no when the link is about to run dry (the host is behind).
             // The first two chunks queue behind the dense operand.
             // (pack_mode 3, tests: a fixed mix — two chunks out of three)
+            const int lag = (int)std::min<long>(std::max<long>(options().host_pack_lag, 1), 8);
             const bool pk = pack_j && (pack_mode == 2 || (pack_mode == 3 ? c % 3 != 1
-                                                         : (c < 2 || cudaEventQuery(ev_h2d[(size_t)(c - 2)]) == cudaErrorNotReady)));
+                                                         : (c < lag || cudaEventQuery(ev_h2d[(size_t)(c - lag)]) == cudaErrorNotReady)));
             cudaGetLastError(); // cudaErrorNotReady is an answer, not an error
             chunk_packed[(size_t)c] = pk;
             if (stage_x || stage_j || pk) MXG_TRY(ring.acquire(&slot));

@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--workloads", default="cfg3,k64f64,cfg2")
     ap.add_argument("--quick", action="store_true", help="default options only")
     ap.add_argument("--slots", action="store_true", help="only: ring slots 4 / 6 / 8 x packed ids off / on")
+    ap.add_argument("--lag", action="store_true", help="only: packed ids off, then on with upload-lag thresholds 2 / 3 / 4")
     ap.add_argument("--pack", action="store_true", help="only: packed column ids on / off (option host_pack), twice each")
     args = ap.parse_args()
     torch.cuda.set_device(0)
@@ -95,6 +96,12 @@ def main():
                 for slots in (4, 6, 8):
                     for pack in (0, 1):
                         run("slots_x_pack", pipe_slots=slots, host_pack=pack)
+            continue
+        if args.lag:
+            for rep in range(3):
+                run("lag", host_pack=0)
+                for lag in (2, 3, 4):
+                    run("lag", host_pack=1, host_pack_lag=lag)
             continue
         if args.pack:
             for rep in range(2):
