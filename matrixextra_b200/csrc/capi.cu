@@ -178,11 +178,15 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
     const size_t s = dtype == MXG_F64 ? 8 : 4;
     const size_t vec = 16 / s;
     const size_t ld = round_up(n, vec);
+    if (K > 0 && n > 0) { // argument errors before anything is allocated
+        if (b_layout != MXG_ROWS_CONTIGUOUS && b_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "dense operand: bad layout %d", b_layout);
+        if (b_layout == MXG_ROWS_CONTIGUOUS && ldb < n) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
+        if (b_layout == MXG_COLS_CONTIGUOUS && ldb < K) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
+    }
     void *d_B = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_B, std::max<size_t>(K * ld * s, 16), stream));
     if (K > 0 && n > 0) {
         if (b_layout == MXG_ROWS_CONTIGUOUS) {
-            if (ldb < n) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
             if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
             if (ld == n && ldb == n) {
                 DeviceState *st = nullptr;
@@ -191,8 +195,7 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
             } else {
                 MXG_CUDA_TRY(cudaMemcpy2DAsync(d_B, ld * s, B, ldb * s, n * s, K, cudaMemcpyHostToDevice, stream));
             }
-        } else if (b_layout == MXG_COLS_CONTIGUOUS) {
-            if (ldb < K) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
+        } else {
             void *d_tmp = nullptr;
             MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, K * n * s, stream));
             if (ldb == K) {
@@ -206,8 +209,6 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
             // d_tmp is n rows of K contiguous -> d_B is K rows of n contiguous
             MXG_TRY(launch_transpose_dense((int)s, n, K, d_tmp, K, d_B, ld, stream));
             MXG_CUDA_TRY(cudaFreeAsync(d_tmp, stream));
-        } else {
-            return fail(MXG_ERR_ARG, "dense operand: bad layout %d", b_layout);
         }
     }
     *d_out = d_B;
@@ -216,8 +217,10 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
 }
 
 // shared tail of the two level-1 SpMM entry points: A is on the device, B/Out are host buffers
+// d_B_early / b_ready: the dense operand was put on its way by the caller (another stream); b_ready marks its arrival
 static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
-                        void *Out, size_t ldc, cudaStream_t stream)
+                        void *Out, size_t ldc, cudaStream_t stream, void *d_B_early = nullptr, size_t ld_b_early = 0,
+                        cudaEvent_t b_ready = nullptr)
 {
     const size_t s = dtype == MXG_F64 ? 8 : 4;
     const size_t vec = 16 / s;
@@ -225,9 +228,10 @@ static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, i
     if (rows == 0 || n == 0) return MXG_OK;
     if (!B && K > 0) return fail(MXG_ERR_ARG, "dense operand is NULL");
     if (!Out) return fail(MXG_ERR_ARG, "output is NULL");
-    void *d_B = nullptr, *d_Out = nullptr;
-    size_t ld_b = 0;
-    MXG_TRY(upload_dense_rows(dtype, b_layout, K, (size_t)n, B, ldb, stream, &d_B, &ld_b));
+    void *d_B = d_B_early, *d_Out = nullptr;
+    size_t ld_b = ld_b_early;
+    if (d_B) MXG_CUDA_TRY(cudaStreamWaitEvent(stream, b_ready, 0));
+    else MXG_TRY(upload_dense_rows(dtype, b_layout, K, (size_t)n, B, ldb, stream, &d_B, &ld_b));
     size_t ld_o;
     if (out_layout == MXG_ROWS_CONTIGUOUS) {
         if (ldc < (size_t)n) return fail(MXG_ERR_ARG, "output: ldc < n");
@@ -736,13 +740,36 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, i
     const double t0 = now();
     MXG_TRY(upload_csr(m, K, p, j, x, keep, st->stream, &A));
     const double t1 = now();
-    int rc = transpose_handle(A, keep, st->stream, &At);
+    // A page-locked dense operand (m rows: the columns of t(A)) starts to cross PCIe on the upload stream now, while
+    // the CSR is transposed on the compute stream; a pageable one needs the host threads and waits its turn below.
+    void *d_B = nullptr;
+    size_t ld_b = 0;
+    cudaEvent_t b_ready = nullptr;
+    int rc = MXG_OK;
+    if (m > 0 && K > 0 && n > 0 && B && Out && host_is_pinned(B)) {
+        rc = upload_dense_rows(dtype, b_layout, (size_t)m, (size_t)n, B, ldb, st->h2d, &d_B, &ld_b);
+        if (rc == MXG_OK && cudaEventCreateWithFlags(&b_ready, cudaEventDisableTiming) != cudaSuccess) rc = fail(MXG_ERR_CUDA, "csrT: event");
+        if (rc == MXG_OK && cudaEventRecord(b_ready, st->h2d) != cudaSuccess) rc = fail(MXG_ERR_CUDA, "csrT: event record");
+    }
+    auto drop_early = [&]() {
+        cudaStreamSynchronize(st->h2d);
+        if (d_B) cudaFreeAsync(d_B, st->stream);
+        if (b_ready) cudaEventDestroy(b_ready);
+        d_B = nullptr;
+        b_ready = nullptr;
+    };
+    if (rc == MXG_OK) rc = transpose_handle(A, keep, st->stream, &At);
     cudaStreamSynchronize(st->stream);
     free_handle(A);
-    if (rc != MXG_OK) return rc;
+    if (rc != MXG_OK) {
+        drop_early();
+        return rc;
+    }
     const double t2 = now();
-    rc = spmm_host_io(At, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream);
+    rc = spmm_host_io(At, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream, d_B, ld_b, b_ready);
     cudaStreamSynchronize(st->stream);
+    if (rc != MXG_OK && d_B) drop_early(); // spmm_host_io frees the operand on success only
+    else if (b_ready) cudaEventDestroy(b_ready);
     free_handle(At);
     if (trace)
         fprintf(stderr, "[mxg trace] csrT: upload+stats %.2f ms | transpose+stats %.2f ms | dense upload, product, download %.2f ms\n",
