@@ -217,7 +217,8 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
 }
 
 // shared tail of the two level-1 SpMM entry points: A is on the device, B/Out are host buffers
-// d_B_early / b_ready: the dense operand was put on its way by the caller (another stream); b_ready marks its arrival
+// d_B_early / b_ready: the dense operand was put on its way by the caller (another stream); b_ready marks its arrival.
+// The operand's device copy is released here on every path, early or not.
 static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
                         void *Out, size_t ldc, cudaStream_t stream, void *d_B_early = nullptr, size_t ld_b_early = 0,
                         cudaEvent_t b_ready = nullptr)
@@ -225,40 +226,35 @@ static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, i
     const size_t s = dtype == MXG_F64 ? 8 : 4;
     const size_t vec = 16 / s;
     const size_t rows = (size_t)A->m, K = (size_t)A->K;
-    if (rows == 0 || n == 0) return MXG_OK;
-    if (!B && K > 0) return fail(MXG_ERR_ARG, "dense operand is NULL");
-    if (!Out) return fail(MXG_ERR_ARG, "output is NULL");
     void *d_B = d_B_early, *d_Out = nullptr;
     size_t ld_b = ld_b_early;
-    if (d_B) MXG_CUDA_TRY(cudaStreamWaitEvent(stream, b_ready, 0));
-    else MXG_TRY(upload_dense_rows(dtype, b_layout, K, (size_t)n, B, ldb, stream, &d_B, &ld_b));
-    size_t ld_o;
-    if (out_layout == MXG_ROWS_CONTIGUOUS) {
-        if (ldc < (size_t)n) return fail(MXG_ERR_ARG, "output: ldc < n");
-        ld_o = round_up((size_t)n, vec);
-        MXG_CUDA_TRY(cudaMallocAsync(&d_Out, rows * ld_o * s, stream));
-    } else if (out_layout == MXG_COLS_CONTIGUOUS) {
-        if (ldc < rows) return fail(MXG_ERR_ARG, "output: ldc < m");
-        ld_o = rows;
-        MXG_CUDA_TRY(cudaMallocAsync(&d_Out, rows * (size_t)n * s, stream));
-    } else {
-        return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
-    }
-    MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, stream));
-    {
+    auto body = [&]() -> int {
+        if (rows == 0 || n == 0) return MXG_OK;
+        if (!B && K > 0) return fail(MXG_ERR_ARG, "dense operand is NULL");
+        if (!Out) return fail(MXG_ERR_ARG, "output is NULL");
+        if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
+        const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
+        if (rm && ldc < (size_t)n) return fail(MXG_ERR_ARG, "output: ldc < n");
+        if (!rm && ldc < rows) return fail(MXG_ERR_ARG, "output: ldc < m");
+        if (d_B) MXG_CUDA_TRY(cudaStreamWaitEvent(stream, b_ready, 0));
+        else MXG_TRY(upload_dense_rows(dtype, b_layout, K, (size_t)n, B, ldb, stream, &d_B, &ld_b));
+        const size_t ld_o = rm ? round_up((size_t)n, vec) : rows;
+        MXG_CUDA_TRY(cudaMallocAsync(&d_Out, rm ? rows * ld_o * s : rows * (size_t)n * s, stream));
+        MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, stream));
         DeviceState *st = nullptr;
         MXG_TRY(current_state(&st));
-        const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
         const size_t width = rm ? (size_t)n * s : rows * s, height = rm ? rows : (size_t)n;
         if (ldc * s == width && ld_o * s == width) // tight on both sides: one staged block copy
             MXG_TRY(staged_d2h(st, Out, d_Out, width * height, stream));
         else
             MXG_CUDA_TRY(cudaMemcpy2DAsync(Out, ldc * s, d_Out, ld_o * s, width, height, cudaMemcpyDeviceToHost, stream));
-    }
-    MXG_CUDA_TRY(cudaFreeAsync(d_B, stream));
-    MXG_CUDA_TRY(cudaFreeAsync(d_Out, stream));
-    MXG_CUDA_TRY(cudaStreamSynchronize(stream));
-    return MXG_OK;
+        return MXG_OK;
+    };
+    int rc = body();
+    if (d_B) cudaFreeAsync(d_B, stream);
+    if (d_Out) cudaFreeAsync(d_Out, stream);
+    if (cudaStreamSynchronize(stream) != cudaSuccess && rc == MXG_OK) rc = fail(MXG_ERR_CUDA, "spmm: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
 }
 
 static int transpose_handle(const mxg_csr_s *A, int keep, cudaStream_t stream, mxg_csr_s **out)
@@ -768,8 +764,7 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, i
     const double t2 = now();
     rc = spmm_host_io(At, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, st->stream, d_B, ld_b, b_ready);
     cudaStreamSynchronize(st->stream);
-    if (rc != MXG_OK && d_B) drop_early(); // spmm_host_io frees the operand on success only
-    else if (b_ready) cudaEventDestroy(b_ready);
+    if (b_ready) cudaEventDestroy(b_ready); // (spmm_host_io has released the operand)
     free_handle(At);
     if (trace)
         fprintf(stderr, "[mxg trace] csrT: upload+stats %.2f ms | transpose+stats %.2f ms | dense upload, product, download %.2f ms\n",
