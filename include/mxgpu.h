@@ -70,6 +70,18 @@ int mxg_device_count(int *count);
 /* Device used by subsequent calls from this thread (default: the current CUDA device). */
 int mxg_set_device(int device);
 
+/* Number of GPUs a host-buffer (level-1) product is spread over (default 1).  With n > 1, mxg_spmm_csr_dense and
+ * mxg_spmv_csr cut the CSR into n nnz-balanced row blocks (mxg_row_partition) and run one streamed pipeline per
+ * device from n host threads of the calling process: every device uploads only its block over its own PCIe link
+ * and downloads its rows straight into the caller's result (no all-gather: the result is wanted on the host); the
+ * dense operand crosses PCIe once, a slice per device, and is completed over NVLink peer copies.  This is the
+ * in-process counterpart of the reference's one OpenMP team over the rows (src/matmul.cpp:132-136,
+ * R/matmul.R:175-180) — an R session is one process.  Devices used: the calling thread's current device and the
+ * n - 1 that follow it.  Calls with fewer than option "multi_min_nnz" stored entries stay on one device.
+ * Results are bit-identical to n = 1.  The Rcpp glue reads MATRIXEXTRA_GPUS once and calls this. */
+int mxg_set_devices(int n);
+int mxg_get_devices(int *n);
+
 /* Tuning knobs, all optional ("auto" when never set).  Unknown names return MXG_ERR_ARG.
  *   kernels : "piece" (stored entries per long-row piece, 1024), "spmm_lpr" (lanes per row of B), "spmm_cpl" (vectors
  *             per lane: 0 = auto, two when a row of B exceeds 128 bytes), "spmm_rpw" (rows per warp), "spmm_panel_mb" /
@@ -87,7 +99,11 @@ int mxg_set_device(int device);
  *             out of three: test modes), "host_pack_lag" (a chunk is packed while the upload of the chunk this many
  *             places before it is still pending, 2),
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
- *             copies are used). */
+ *             copies are used);
+ *   several devices : "multi_min_nnz" (level-1 calls below this many stored entries stay on one device, 4 Mi),
+ *             "multi_dense_share" (1 = each device uploads one slice of the dense operand and pulls the rest over NVLink,
+ *             0 = every device uploads all of it);
+ *   residency : "cache_mb" (level-1 operand cache, MiB of device memory, 0 = off: see mxg_cache_clear). */
 int mxg_set_option(const char *name, long value);
 int mxg_get_option(const char *name, long *value);
 
@@ -183,6 +199,18 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout,
                         const void *B, size_t ldb,
                         void *Out, size_t ldc);
 
+/* ---- level-1 operand cache (option "cache_mb" > 0, off by default) -------------------------------
+ * The callers of the reference multiply ONE sparse matrix many times (vignettes/Introducing_MatrixExtra.Rmd:454-476:
+ * `X %*% coefs` inside optim), and every .Call hands over the same R vectors.  With the cache on, the device copy
+ * of the CSR that a level-1 product has streamed in is kept, keyed on the three host addresses, the sizes and a
+ * sampled fingerprint of the contents (both ends + ~1000 positions of each array), LRU within cache_mb; the next
+ * product on the same arrays moves only the dense operand and the result.  Dense operands are kept the same way,
+ * crossprod keeps the device-built CSC with its matrix.  Opt-in because R objects can be modified in place
+ * (MatrixExtra.inplace_sort): a change that touches none of the sampled positions is not noticed — call
+ * mxg_cache_clear() after modifying a matrix in place, or use explicit handles (below), which have no such caveat. */
+int mxg_cache_clear(void);
+int mxg_cache_stats(unsigned long long *hits, unsigned long long *misses, size_t *bytes, int *entries);
+
 /* ============ level 2: device-resident handles (repeated multiplies, benchmarks, sharding) ===== */
 
 /* Upload a host CSR once (validates indices, converts values, computes row statistics). */
@@ -196,6 +224,17 @@ int mxg_csr_wrap_device(int m, int K, const int32_t *d_p, const int32_t *d_j,
                         void *stream, mxg_csr_t *handle);
 
 int mxg_csr_free(mxg_csr_t handle);
+
+/* Products of a device-resident handle with HOST operands: the same semantics as mxg_spmm_csr_dense /
+ * mxg_spmm_csrT_dense / mxg_spmv_csr, but the CSR does not cross PCIe again — only the dense operand goes up and
+ * the result comes down, in row chunks that leave while later rows are computed (mxg_last_call_bytes counts them).
+ * What the glue's as_gpu_csr() objects call (rglue/handle_gpu_glue.cpp).  _t_: Out(K x n) = t(A) . B(m x n); the
+ * CSC is built on the device at the first such product and kept with the handle.  Synchronous. */
+int mxg_csr_spmm_host(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,
+                      const void *B, size_t ldb, void *Out, size_t ldc);
+int mxg_csr_spmm_t_host(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n,
+                        const void *B, size_t ldb, void *Out, size_t ldc);
+int mxg_csr_spmv_host(mxg_csr_t A, int ytype, const void *y, void *out);
 
 /* m, K, nnz, number of long rows, number of long-row pieces, longest row */
 int mxg_csr_info(mxg_csr_t handle, int64_t info[6]);
@@ -313,6 +352,12 @@ int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model
  * roof (DRAM when the table is far larger than L2, L2->SM when it fits) that bounds K1/K2.  d_sink: 1 float. */
 int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
                          float *d_sink, long long *gathers_done, void *stream);
+
+/* Measurement probe for K3: the handle's column ids streamed 16 bytes per thread with the row structure taken away.
+ * mode 0: ids only; 1: + an 8-byte gather of d_y[j] per entry (plain loads); 2: the same through the texture path;
+ * 3: ids + float64 values + texture gathers + FMA (12 streamed bytes and one gather per entry, what the SpMV must
+ * do at the very least).  d_sink: 1 double.  The time of mode 3 is the floor the SpMV kernel is measured against. */
+int mxg_dev_spmv_probe(mxg_csr_t A, int mode, const double *d_y, double *d_sink, void *stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,13 @@ _vp, _i32, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 _SIGNATURES = {
     "mxg_device_count": [C.POINTER(C.c_int)],
     "mxg_set_device": [_i32],
+    "mxg_set_devices": [_i32],
+    "mxg_get_devices": [C.POINTER(C.c_int)],
+    "mxg_cache_clear": [],
+    "mxg_cache_stats": [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.POINTER(_sz), C.POINTER(C.c_int)],
+    "mxg_csr_spmm_host": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz],
+    "mxg_csr_spmm_t_host": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz],
+    "mxg_csr_spmv_host": [_vp, _i32, _vp, _vp],
     "mxg_set_option": [C.c_char_p, C.c_long],
     "mxg_get_option": [C.c_char_p, C.POINTER(C.c_long)],
     "mxg_trim": [],
@@ -77,6 +84,7 @@ _SIGNATURES = {
     "mxg_host_pack_indices": [_vp, _sz, _i32, _vp, C.POINTER(_sz), C.POINTER(C.c_int)],
     "mxg_last_call_bytes": [C.POINTER(_sz), C.POINTER(_sz)],
     "mxg_host_chunk_plan": [_i32, _vp, _sz, _vp, _i32] + [C.POINTER(C.c_int)] * 4,
+    "mxg_dev_spmv_probe": [_vp, _i32, _vp, _vp, _vp],
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],
 }
 _RESTYPES = {"mxg_last_error": C.c_char_p, "mxg_launch_count": C.c_ulonglong, "mxg_csr_error_string": C.c_char_p}

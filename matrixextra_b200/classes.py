@@ -141,3 +141,28 @@ def check_valid_matrix(x) -> None:
         raise ValueError("Matrix is invalid ('p' doesn't match with dimension).")
     if x.p[0] != 0 or x.p[outer] != idx.size:
         raise ValueError("Matrix is invalid ('p' has bad start/end.)")
+
+
+class gpuRsparse:
+    """A dgRMatrix kept in HBM (the S4 class `gpuRsparse` of rglue/matmul_gpu_methods.R): made once
+    with ``as_gpu(x)``, multiplied many times — every product moves only the dense operand and the result.
+    ``float32=True`` also keeps float32 values so that products with ``float32`` operands are available."""
+
+    def __init__(self, x: "dgRMatrix", float64: bool = True, float32: bool = False):
+        from . import rcpp_exports as rx
+        check_valid_matrix(x)
+        self.Dim = tuple(x.Dim)
+        self.Dimnames = x.Dimnames
+        self.ptr = rx.as_gpu_csr(x.p, x.j, x.x, x.Dim[1], float64, float32)
+
+    @property
+    def shape(self):
+        return self.Dim
+
+    def free(self):
+        from . import rcpp_exports as rx
+        rx.gpu_csr_free(self.ptr)
+
+
+def as_gpu(x: "dgRMatrix", float64: bool = True, float32: bool = False) -> gpuRsparse:
+    return gpuRsparse(x, float64, float32)

@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace mxg {
@@ -30,6 +33,7 @@ int current_state(DeviceState **out)
         MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
         MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.h2d, cudaStreamNonBlocking));
         MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.d2h, cudaStreamNonBlocking));
+        MXG_CUDA_TRY(cudaStreamCreateWithFlags(&st.p2p, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long keep_all = ~0ULL; // keep freed blocks cached between calls (mxg_trim releases them)
@@ -69,6 +73,8 @@ static int free_handle(mxg_csr_s *h)
     rel(h->d_piece_k);
     rel(h->d_partial);
     rel(h->d_seg);
+    delete h->host_chunks;
+    if (h->cached_t) free_handle(h->cached_t);
     delete h;
     return MXG_OK;
 }
@@ -257,6 +263,12 @@ static int spmm_host_io(mxg_csr_s *A, int dtype, int out_layout, int b_layout, i
     return rc;
 }
 
+int csr_handle_free(mxg_csr_s *h) { return free_handle(h); }
+
+// every host-buffer (level-1) entry point runs under this lock: they share the per-device streams, the page-locked
+// arena and the operand cache, and the reference's callers are a single R thread anyway (SURVEY.md 8 b)
+static std::recursive_mutex g_level1_mu;
+
 static int transpose_handle(const mxg_csr_s *A, int keep, cudaStream_t stream, mxg_csr_s **out)
 {
     const bool w64 = (keep & MXG_KEEP_F64) && A->d_x64, w32 = (keep & MXG_KEEP_F32) && A->d_x32;
@@ -293,6 +305,47 @@ static int transpose_handle(const mxg_csr_s *A, int keep, cudaStream_t stream, m
     return MXG_OK;
 }
 
+// the CSC of a handle (as the CSR handle of t(A)), built on first use and kept with it
+static int handle_transposed(mxg_csr_s *A, int keep, cudaStream_t stream)
+{
+    if (A->cached_t) {
+        const bool ok = (!(keep & MXG_KEEP_F64) || A->cached_t->d_x64) && (!(keep & MXG_KEEP_F32) || A->cached_t->d_x32);
+        if (ok || A->nnz == 0) return MXG_OK;
+        free_handle(A->cached_t);
+        A->cached_t = nullptr;
+    }
+    int have = 0;
+    if (A->d_x64) have |= MXG_KEEP_F64;
+    if (A->d_x32) have |= MXG_KEEP_F32;
+    if ((keep & have) != keep && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "handle lacks the values of this type");
+    MXG_TRY(transpose_handle(A, have, stream, &A->cached_t));
+    MXG_CUDA_TRY(cudaStreamSynchronize(stream));
+    return MXG_OK;
+}
+
+// warm product on a cached (or explicit) handle; with the cache on, the dense operand's device copy is kept too
+static int cached_spmm(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
+                       void *Out, size_t ldc)
+{
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    const size_t K = (size_t)A->K, nz = (size_t)n;
+    if (!cache_enabled() || K == 0 || n <= 0 || !B) return handle_spmm_host(st, A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc);
+    // host bytes the operand spans (a strided operand is fingerprinted over its whole span)
+    const size_t lines = b_layout == MXG_ROWS_CONTIGUOUS ? K : nz, width = b_layout == MXG_ROWS_CONTIGUOUS ? nz : K;
+    if (ldb < width) return fail(MXG_ERR_ARG, "dense operand: leading dimension too small");
+    const size_t host_bytes = ((lines - 1) * ldb + width) * s;
+    void *d_B = cache_find_dense(B, dtype, b_layout, K, nz, ldb, host_bytes);
+    if (d_B) return handle_spmm_host(st, A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, d_B, nullptr);
+    void *kept = nullptr;
+    const int rc = handle_spmm_host(st, A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc, nullptr, &kept);
+    if (kept) {
+        const size_t ld_b = (nz + 16 / s - 1) / (16 / s) * (16 / s);
+        if (rc == MXG_OK) cache_insert_dense(B, dtype, b_layout, K, nz, ldb, host_bytes, kept, std::max<size_t>(K * ld_b * s, 16), st->stream);
+        else cudaFreeAsync(kept, st->stream);
+    }
+    return rc;
+}
+
 } // namespace mxg
 
 using namespace mxg;
@@ -313,6 +366,66 @@ int mxg_set_device(int device)
 {
     MXG_CUDA_TRY(cudaSetDevice(device));
     return MXG_OK;
+}
+
+int mxg_set_devices(int n)
+{
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
+    return set_devices(n);
+}
+
+int mxg_get_devices(int *n)
+{
+    if (!n) return fail(MXG_ERR_ARG, "get_devices: NULL argument");
+    *n = multi_devices();
+    return MXG_OK;
+}
+
+int mxg_cache_clear(void)
+{
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
+    return cache_clear();
+}
+
+int mxg_cache_stats(unsigned long long *hits, unsigned long long *misses, size_t *bytes, int *entries)
+{
+    cache_stats(hits, misses, bytes, entries);
+    return MXG_OK;
+}
+
+/* ---- explicit handles with host operands: the CSR stays in HBM, a product moves B up and Out down ---- */
+
+int mxg_csr_spmm_host(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb, void *Out, size_t ldc)
+{
+    if (!A) return fail(MXG_ERR_ARG, "csr_spmm_host: NULL handle");
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
+    if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    return handle_spmm_host(st, A, dtype, out_layout, b_layout, n, B, ldb, Out, ldc);
+}
+
+int mxg_csr_spmm_t_host(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb, void *Out, size_t ldc)
+{
+    if (!A) return fail(MXG_ERR_ARG, "csr_spmm_t_host: NULL handle");
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
+    if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    MXG_TRY(handle_transposed(A, dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32, st->stream));
+    return handle_spmm_host(st, A->cached_t, dtype, out_layout, b_layout, n, B, ldb, Out, ldc);
+}
+
+int mxg_csr_spmv_host(mxg_csr_t A, int ytype, const void *y, void *out)
+{
+    if (!A) return fail(MXG_ERR_ARG, "csr_spmv_host: NULL handle");
+    if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    return handle_spmv_host(st, A, ytype, y, out);
 }
 
 static long *option_slot(const char *name)
@@ -339,6 +452,9 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "h2d_chunk_mb")) return &o.h2d_chunk_mb;
     if (!strcmp(name, "pipeline")) return &o.pipeline;
     if (!strcmp(name, "pipe_chunk_nnz")) return &o.pipe_chunk_nnz;
+    if (!strcmp(name, "multi_min_nnz")) return &o.multi_min_nnz;
+    if (!strcmp(name, "multi_dense_share")) return &o.multi_dense_share;
+    if (!strcmp(name, "cache_mb")) return &o.cache_mb;
     return nullptr;
 }
 
@@ -407,6 +523,8 @@ int mxg_trim(void)
     int dev = 0;
     MXG_CUDA_TRY(cudaGetDevice(&dev));
     MXG_CUDA_TRY(cudaDeviceSynchronize());
+    cache_clear();
+    texture_cache_clear();
     cudaMemPool_t pool;
     MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
     MXG_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
@@ -638,20 +756,7 @@ int mxg_dev_transpose_dense(int elem_size, size_t rows, size_t cols, const void 
 int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts)
 {
     if (m < 0 || parts <= 0 || !p || !row_starts) return fail(MXG_ERR_ARG, "row_partition: bad arguments");
-    const int64_t base = p[0], nnz = (int64_t)p[m] - base;
-    row_starts[0] = 0;
-    for (int g = 1; g < parts; g++) {
-        // first row whose start offset reaches g/parts of the entries
-        const int64_t target = base + (nnz * g) / parts;
-        const int32_t *it = std::lower_bound(p, p + m + 1, (int32_t)std::min<int64_t>(target, INT32_MAX));
-        int r = (int)(it - p);
-        if (r > m) r = m;
-        if (nnz == 0) r = (int)(((int64_t)m * g) / parts);
-        if (r < row_starts[g - 1]) r = row_starts[g - 1];
-        row_starts[g] = r;
-    }
-    row_starts[parts] = m;
-    return MXG_OK;
+    return row_partition(m, p, parts, row_starts);
 }
 
 int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
@@ -665,6 +770,13 @@ int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long l
         *gathers_done = teams * std::max<long long>(8, (gathers / teams + 7) / 8 * 8);
     }
     return MXG_OK;
+}
+
+int mxg_dev_spmv_probe(mxg_csr_t A, int mode, const double *d_y, double *d_sink, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A || !d_sink) return fail(MXG_ERR_ARG, "spmv_probe: NULL argument");
+    return spmv_probe(A, mode, d_y, d_sink, static_cast<cudaStream_t>(stream));
 }
 
 int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model, uint64_t seed, int keep,
@@ -708,8 +820,24 @@ int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout, int m, int K, in
     if (n < 0) return fail(MXG_ERR_ARG, "negative n");
     if (m < 0 || K < 0) return fail(MXG_ERR_ARG, "csr: negative dimension");
     if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     DeviceState *st;
     MXG_TRY(current_state(&st));
+    // several devices (mxg_set_devices): nnz-balanced row blocks, one host thread and one streamed pipeline per device
+    if (options().pipeline != 0 && multi_wanted(m, p) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
+        return multi_spmm(dtype, out_layout, b_layout, m, K, n, p, j, x, B, ldb, Out, ldc);
+    // operand cache (option cache_mb): the device CSR of these host arrays is kept between calls
+    if (p[0] == 0 && options().pipeline != 0 && cache_enabled() && m > 0 && n > 0 && p[m] > 0 && j && x) {
+        const int need = dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32;
+        mxg_csr_s *hit = cache_find_csr(m, K, p, j, x, need);
+        if (!hit) { // cold: the streamed call, which hands its device arrays over instead of releasing them
+            mxg_csr_s *kept = nullptr;
+            MXG_TRY(pipeline_spmm(st, dtype, out_layout, b_layout, m, K, n, p, j, x, B, ldb, Out, ldc, nullptr, 0, &kept));
+            cache_insert_csr(m, K, p, j, x, kept);
+            return MXG_OK;
+        }
+        return cached_spmm(st, hit, dtype, out_layout, b_layout, n, B, ldb, Out, ldc);
+    }
     // every valid R matrix has p[0] == 0 (R/utils.R:349-410): streamed, chunk-overlapped path
     if (p[0] == 0 && options().pipeline != 0)
         return pipeline_spmm(st, dtype, out_layout, b_layout, m, K, n, p, j, x, B, ldb, Out, ldc);
@@ -726,9 +854,24 @@ int mxg_spmm_csrT_dense(int dtype, int out_layout, int b_layout, int m, int K, i
 {
     if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
     if (n < 0) return fail(MXG_ERR_ARG, "negative n");
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     DeviceState *st;
     MXG_TRY(current_state(&st));
     const int keep = dtype == MXG_F64 ? MXG_KEEP_F64 : MXG_KEEP_F32;
+    if (cache_enabled() && p && m > 0 && K > 0 && n > 0 && p[0] == 0 && p[m] > 0 && j && x) {
+        // operand cache: the matrix AND its device-built CSC stay resident; a repeated crossprod only moves Y and the result
+        mxg_csr_s *hit = cache_find_csr(m, K, p, j, x, keep);
+        if (!hit) {
+            MXG_TRY(upload_csr(m, K, p, j, x, keep, st->stream, &hit));
+            cache_insert_csr(m, K, p, j, x, hit);
+            hit = cache_find_csr(m, K, p, j, x, keep); // NULL when it did not fit the budget (and was released)
+        }
+        if (hit) {
+            MXG_TRY(handle_transposed(hit, keep, st->stream));
+            cache_account_csr(hit);
+            return cached_spmm(st, hit->cached_t, dtype, out_layout, b_layout, n, B, ldb, Out, ldc);
+        }
+    }
     mxg_csr_s *A = nullptr, *At = nullptr;
     const char *tr = getenv("MXG_TRACE"); // development aid: host-side phase times on stderr
     const bool trace = tr && *tr && *tr != '0';
@@ -777,8 +920,19 @@ int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, co
     if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
     if (m < 0 || K < 0) return fail(MXG_ERR_ARG, "csr: negative dimension");
     if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     DeviceState *st;
     MXG_TRY(current_state(&st));
+    if (options().pipeline != 0 && multi_wanted(m, p) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
+        return multi_spmv(ytype, m, K, p, j, x, y, out);
+    if (p[0] == 0 && options().pipeline != 0 && cache_enabled() && m > 0 && p[m] > 0 && j && x) {
+        mxg_csr_s *hit = cache_find_csr(m, K, p, j, x, MXG_KEEP_F64);
+        if (hit) return handle_spmv_host(st, hit, ytype, y, out);
+        mxg_csr_s *kept = nullptr;
+        MXG_TRY(pipeline_spmv(st, ytype, m, K, p, j, x, y, out, &kept));
+        cache_insert_csr(m, K, p, j, x, kept);
+        return MXG_OK;
+    }
     if (p[0] == 0 && options().pipeline != 0) return pipeline_spmv(st, ytype, m, K, p, j, x, y, out);
     mxg_csr_s *A = nullptr;
     MXG_TRY(upload_csr(m, K, p, j, x, MXG_KEEP_F64, st->stream, &A));

@@ -6,7 +6,10 @@
 #include <stddef.h>
 #include <string>
 #include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
+#include <vector>
 
 #include "../../include/mxgpu.h"
 
@@ -66,6 +69,9 @@ struct Options {
     long host_pack_lag = 2;   // a chunk's ids are packed while the upload of the chunk this many places before it is pending
     long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
     long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
+    long multi_min_nnz = 4 << 20;  // mxg_set_devices(n > 1): level-1 calls with fewer stored entries stay on one device
+    long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
+    long cache_mb = 0;             // level-1 operand cache (device-resident CSR + dense operands keyed on the host arrays); 0 = off
 };
 Options &options();
 
@@ -108,6 +114,11 @@ struct mxg_csr_s {
     // device flag set by the index validation of the streamed (level-1) path: kernels that see it non-zero
     // return at once instead of gathering through an out-of-range column id
     const int *d_abort = nullptr;
+
+    // host-side extras of handles that serve host-buffer products (pipeline.cu: handle_spmm_host): the row chunks
+    // the result leaves the device in, and the cached CSC (as the CSR handle of t(A)) for crossprod-type products
+    std::vector<int32_t> *host_chunks = nullptr;
+    mxg_csr_s *cached_t = nullptr;
 };
 
 namespace mxg {
@@ -119,17 +130,82 @@ struct DeviceState {
     cudaStream_t stream = nullptr; // kernels (and everything of the non-pipelined calls)
     cudaStream_t h2d = nullptr;
     cudaStream_t d2h = nullptr;
+    cudaStream_t p2p = nullptr; // pulls of the other devices' dense-operand slices over NVLink (multi-device calls)
     // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
     void *pin_base = nullptr;
     size_t pin_bytes = 0;
 };
 int current_state(DeviceState **out);
 
+// Multi-device level-1 products (mxg_set_devices(n > 1); capi.cu: one host thread per device, each running the
+// streamed pipeline on its nnz-balanced row block).  The dense operand is replicated: every device uploads ONE
+// slice of its rows over its own PCIe link and pulls the other slices from its peers over NVLink.
+struct DenseShare {
+    int G = 1;
+    int device[MXG_MAX_DST] = {};
+    void *d_B[MXG_MAX_DST] = {};
+    cudaEvent_t slice_ready[MXG_MAX_DST] = {};
+    // host barrier between the device threads; a thread that has returned counts as arrived at every phase
+    std::mutex mu;
+    std::condition_variable cv;
+    int phase_of[MXG_MAX_DST] = {}; // barriers rank g has entered
+    bool gone[MXG_MAX_DST] = {};
+    bool failed = false;
+    bool wait(int phase, int g) // false: a participant has failed, the slices are not all there
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        phase_of[g] = phase + 1;
+        cv.notify_all();
+        cv.wait(lk, [&] {
+            for (int q = 0; q < G; q++)
+                if (!gone[q] && phase_of[q] <= phase) return false;
+            return true;
+        });
+        return !failed;
+    }
+    void leave(int g, bool ok)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        gone[g] = true;
+        if (!ok) failed = true;
+        cv.notify_all();
+    }
+};
+
 // pipeline.cu: streamed level-1 products (host CSR with p[0] == 0)
+// share / share_rank: this call is one device of a multi-device product (NULL otherwise)
+// keep: when non-NULL and the call succeeds, the device CSR is not released but returned as an owned handle
 int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
-                  const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc);
+                  const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc,
+                  DenseShare *share = nullptr, int share_rank = 0, mxg_csr_s **keep = nullptr);
+// host dense operand in, host result out, CSR already device-resident (the warm path of SURVEY.md 8 f1)
+int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
+                     void *Out, size_t ldc, const void *d_B_resident = nullptr, void **d_B_keep = nullptr);
+int handle_spmv_host(DeviceState *st, mxg_csr_s *A, int ytype, const void *y, void *out);
+void set_last_call_bytes(size_t h2d, size_t d2h);
+
+// capi.cu
+int csr_handle_free(mxg_csr_s *h);
+
+// residency.cu: devices of a level-1 call, level-1 operand cache
+int multi_devices();
+int set_devices(int n);
+int row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
+bool multi_wanted(int m, const int32_t *p);
+int multi_spmm(int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p, const int32_t *j,
+               const double *x, const void *B, size_t ldb, void *Out, size_t ldc);
+int multi_spmv(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *y, void *out);
+bool cache_enabled();
+mxg_csr_s *cache_find_csr(int m, int K, const int32_t *p, const int32_t *j, const double *x, int need);
+void cache_insert_csr(int m, int K, const int32_t *p, const int32_t *j, const double *x, mxg_csr_s *h);
+void cache_account_csr(mxg_csr_s *h);
+void *cache_find_dense(const void *ptr, int dtype, int layout, size_t K, size_t n, size_t ldb, size_t host_bytes);
+void cache_insert_dense(const void *ptr, int dtype, int layout, size_t K, size_t n, size_t ldb, size_t host_bytes, void *d_B,
+                        size_t dev_bytes, cudaStream_t stream);
+int cache_clear();
+void cache_stats(unsigned long long *hits, unsigned long long *misses, size_t *bytes, int *entries);
 int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
-                  const void *y, void *out);
+                  const void *y, void *out, mxg_csr_s **keep = nullptr);
 void last_call_bytes(size_t *h2d, size_t *d2h);
 int host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks, int *n_long,
                     int *n_pieces, int *max_len);
@@ -174,9 +250,15 @@ int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void
 // mcast != 0: d_outs[0] is an NVLS multicast address, rows are written with multimem.st (row-major, one destination)
 int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,
                       int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast = 0);
+// one slice of the product: rows [r0, r1) of a handle without their long rows (pieces == 0), or only the long rows
+// (pieces != 0: piece kernels + fix-up, whatever r0 / r1).  d_Out is the FULL result's origin in both cases.
+int launch_spmm_rows(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb, void *d_Out,
+                     size_t ldc, int r0, int r1, int pieces, cudaStream_t stream);
 // spmv.cu
 int launch_spmv(const mxg_csr_s *A, int ytype, const void *d_y, void *d_out, cudaStream_t stream);
 int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream);
+int spmv_probe(const mxg_csr_s *A, int mode, const double *d_y, double *d_sink, cudaStream_t stream);
+void texture_cache_clear(); // cached texture objects over dense vectors (mxg_trim)
 // CSR x sparse vector (indices base 1, K = columns covered by the presence bitmap), double result
 int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
                      double *d_out, cudaStream_t stream);

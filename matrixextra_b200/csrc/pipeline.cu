@@ -94,7 +94,7 @@ struct HostPlan {
 int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
 {
     plan.piece = (int)std::max<long>(32, options().piece);
-    const int64_t nnz = p[m];
+    const int64_t nnz = (int64_t)p[m] - (int64_t)p[0]; // a row block of a larger matrix keeps its absolute offsets
     // ~16 chunks, but never more than 16 Mi entries or 64 MiB of result rows per chunk: the ring slots of the
     // page-locked arena are sized by the largest chunk (a 2-billion-entry call must not pin gigabytes)
     int64_t target_nnz = std::min<int64_t>(std::max<int64_t>(nnz / 16, (int64_t)1 << 20), (int64_t)16 << 20);
@@ -146,7 +146,7 @@ int build_plan(int m, const int32_t *p, HostPlan &plan, size_t out_row_bytes)
         int64_t tn = target_nnz;
         int tr = target_rows;
         if (!forced) {
-            tn = std::min(tn, std::max<int64_t>(target_nnz / 8, (nnz - first) / 3));
+            tn = std::min(tn, std::max<int64_t>(target_nnz / 8, ((int64_t)p[m] - first) / 3));
             tr = (int)std::min<int64_t>(tr, std::max<int64_t>(target_rows / 8, (int64_t)(m - start) / 3));
         }
         const int32_t *hit = std::lower_bound(p + start + 1, p + m + 1, first + tn,
@@ -316,6 +316,7 @@ struct CsrStream {
     HostPlan plan;
     int m, K;
     int64_t nnz;
+    int64_t base; // p[0]: host arrays are indexed with the absolute offsets of p, device arrays start at this entry
     const int32_t *p, *j;
     const double *x;
     bool narrow; // the product runs on float32 values
@@ -347,7 +348,7 @@ struct CsrStream {
     std::vector<cudaEvent_t> ev_h2d, ev_conv, ev_unpack;
 
     CsrStream(Scratch &s, int m_, int K_, const int32_t *p_, const int32_t *j_, const double *x_, bool narrow_)
-        : sc(s), m(m_), K(K_), nnz(p_[m_]), p(p_), j(j_), x(x_), narrow(narrow_)
+        : sc(s), m(m_), K(K_), nnz((int64_t)p_[m_] - (int64_t)p_[0]), base(p_[0]), p(p_), j(j_), x(x_), narrow(narrow_)
     {
     }
     int chunks() const { return (int)plan.chunk_row.size() - 1; }
@@ -476,7 +477,7 @@ struct CsrStream {
             if (narrow_on_host) {
                 host_narrow_f64_to_f32(x + e0, reinterpret_cast<float *>(slot), len);
                 if (g_trace) g_trace->fill_ms += g_trace->now() - tf;
-                MXG_CUDA_TRY(copy_async(d_x32 + e0, slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
+                MXG_CUDA_TRY(copy_async(d_x32 + (e0 - base), slot, sizeof(float) * len, cudaMemcpyHostToDevice, st->h2d));
             } else {
                 if (stage_x) {
                     host_copy(slot, x + e0, sizeof(double) * len, /*nt_dst=*/true);
@@ -488,7 +489,7 @@ struct CsrStream {
                     if (c >= NSTAGE) MXG_CUDA_TRY(cudaStreamWaitEvent(st->h2d, ev_conv[(size_t)(c - NSTAGE)], 0));
                     MXG_CUDA_TRY(copy_async(d_stage[c % NSTAGE], xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
                 } else {
-                    MXG_CUDA_TRY(copy_async(d_x64 + e0, xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
+                    MXG_CUDA_TRY(copy_async(d_x64 + (e0 - base), xsrc, sizeof(double) * len, cudaMemcpyHostToDevice, st->h2d));
                 }
             }
             const void *jsrc = j + e0;
@@ -511,7 +512,7 @@ struct CsrStream {
                 jsrc = slot + x_part;
                 if (g_trace) g_trace->fill_ms += g_trace->now() - tj;
             }
-            if (!pk) MXG_CUDA_TRY(copy_async(d_j + e0, jsrc, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
+            if (!pk) MXG_CUDA_TRY(copy_async(d_j + (e0 - base), jsrc, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st->h2d));
             if (slot) MXG_TRY(ring.release(st->h2d));
         }
         MXG_CUDA_TRY(cudaEventRecord(ev_h2d[(size_t)c], st->h2d));
@@ -529,15 +530,15 @@ struct CsrStream {
         if (narrow && !narrow_on_host) {
             if (len > 0) {
                 // chunk starts are not always even: narrow element-wise from the staging buffer's start
-                MXG_TRY(convert_f64_to_f32(d_stage[c % NSTAGE], d_x32 + e0, len, st->stream));
+                MXG_TRY(convert_f64_to_f32(d_stage[c % NSTAGE], d_x32 + (e0 - base), len, st->stream));
             }
             MXG_CUDA_TRY(cudaEventRecord(ev_conv[(size_t)c], st->stream));
         }
         if (chunk_packed[(size_t)c]) {
-            MXG_TRY(unpack_indices_flag(len, d_pack[c % NSTAGE], hi_bits, K, d_j + e0, d_flag, st->stream));
+            MXG_TRY(unpack_indices_flag(len, d_pack[c % NSTAGE], hi_bits, K, d_j + (e0 - base), d_flag, st->stream));
             MXG_CUDA_TRY(cudaEventRecord(ev_unpack[(size_t)c], st->stream));
         } else {
-            MXG_TRY(check_indices_flag(len, d_j + e0, K, d_flag, st->stream));
+            MXG_TRY(check_indices_flag(len, d_j + (e0 - base), K, d_flag, st->stream));
         }
         const size_t nl = plan.long_rows.size(), np = plan.piece_row.size();
         const int l0 = plan.chunk_long_off[(size_t)c], l1 = plan.chunk_long_off[(size_t)c + 1];
@@ -548,10 +549,10 @@ struct CsrStream {
         h.K = K;
         h.nnz = e1 - e0;
         h.base = (int32_t)e0;
-        h.d_p = d_p + r0; // offsets stay absolute: the kernels index d_j / d_x with them directly
-        h.d_j = d_j;
-        h.d_x64 = d_x64;
-        h.d_x32 = d_x32;
+        h.d_p = d_p + r0; // offsets stay absolute: the kernels index d_j / d_x with them directly, so the array
+        h.d_j = d_j - base; // origins handed to them are those of entry 0 (never dereferenced below entry `base`)
+        h.d_x64 = d_x64 ? d_x64 - base : nullptr;
+        h.d_x32 = d_x32 ? d_x32 - base : nullptr;
         h.owns = false;
         h.stream = st->stream;
         h.piece = plan.piece;
@@ -568,6 +569,34 @@ struct CsrStream {
         h.d_partial = d_partial;
         h.partial_bytes = partial_bytes;
         h.d_abort = d_flag;
+        return MXG_OK;
+    }
+
+    // The device CSR of a finished, valid call becomes an owned handle instead of being released (level-1 cache).
+    int detach_handle(mxg_csr_s **out)
+    {
+        mxg_csr_s *h = new mxg_csr_s();
+        h->m = m;
+        h->K = K;
+        h->nnz = nnz;
+        h->base = 0;
+        h->d_p = d_p;
+        h->d_j = d_j;
+        h->d_x64 = d_x64;
+        h->d_x32 = d_x32;
+        h->owns = true;
+        h->stream = sc.st->stream;
+        cudaGetDevice(&h->device);
+        for (const void *q : {(const void *)d_p, (const void *)d_j, (const void *)d_x64, (const void *)d_x32})
+            if (q) sc.bufs.erase(std::remove(sc.bufs.begin(), sc.bufs.end(), const_cast<void *>(q)), sc.bufs.end());
+        const int rc = csr_build_stats(h, /*validate=*/0, sc.st->stream);
+        if (rc != MXG_OK) {
+            for (const void *q : {(const void *)d_p, (const void *)d_j, (const void *)d_x64, (const void *)d_x32})
+                if (q) cudaFreeAsync(const_cast<void *>(q), sc.st->stream);
+            delete h;
+            return rc;
+        }
+        *out = h;
         return MXG_OK;
     }
 
@@ -593,6 +622,12 @@ void last_call_bytes(size_t *h2d, size_t *d2h)
     if (d2h) *d2h = g_d2h_bytes;
 }
 
+void set_last_call_bytes(size_t h2d, size_t d2h)
+{
+    g_h2d_bytes = h2d;
+    g_d2h_bytes = d2h;
+}
+
 // the chunk plan of a streamed call, for inspection (mxg_host_chunk_plan; no device involved)
 int host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *chunk_rows, int cap, int *n_chunks, int *n_long,
                     int *n_pieces, int *max_len)
@@ -612,7 +647,8 @@ int host_chunk_plan(int m, const int32_t *p, size_t result_row_bytes, int32_t *c
 }
 
 int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p,
-                  const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc)
+                  const int32_t *j, const double *x, const void *B, size_t ldb, void *Out, size_t ldc, DenseShare *share,
+                  int share_rank, mxg_csr_s **keep)
 {
     const size_t s = dtype == MXG_F64 ? 8 : 4;
     const size_t vec = 16 / s;
@@ -626,8 +662,11 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     if (b_layout == MXG_COLS_CONTIGUOUS && ldb < Kz) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
     if (out_layout == MXG_ROWS_CONTIGUOUS && ldc < nz) return fail(MXG_ERR_ARG, "output: ldc < n");
     if (out_layout == MXG_COLS_CONTIGUOUS && ldc < rows) return fail(MXG_ERR_ARG, "output: ldc < m");
-    const int64_t nnz = p[m];
+    const int64_t nnz = (int64_t)p[m] - (int64_t)p[0];
     if (nnz > 0 && (!j || !x)) return fail(MXG_ERR_ARG, "csr: indices / values is NULL");
+    if (keep && p[0] != 0) return fail(MXG_ERR_ARG, "pipeline: a kept handle needs p[0] == 0");
+    // one device of a multi-device call: only a rows-contiguous operand is cut into slices
+    if (share && (b_layout != MXG_ROWS_CONTIGUOUS || K < share->G)) return fail(MXG_ERR_ARG, "pipeline: dense operand cannot be shared");
 
     g_h2d_bytes = g_d2h_bytes = 0;
     Trace trace;
@@ -650,8 +689,19 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     if (K > 0 && ld_b != nz) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, Kz * ld_b * s, st->stream));
     MXG_TRY(chain(sc, st->stream, st->h2d));
     trace.mark(0, st->h2d);
+    // rows [k0, k1) of the dense operand cross this device's PCIe link (all of them unless the call is shared)
+    auto slice = [&](int q, size_t &k0, size_t &k1) {
+        k0 = Kz * (size_t)q / (size_t)share->G;
+        k1 = Kz * (size_t)(q + 1) / (size_t)share->G;
+    };
     auto upload_dense = [&](InRing *ring) -> int {
         if (K == 0) return MXG_OK;
+        if (share) {
+            size_t k0, k1;
+            slice(share_rank, k0, k1);
+            return upload_lines(ring, d_B + k0 * ld_b * s, ld_b * s, static_cast<const char *>(B) + k0 * ldb * s, ldb * s, nz * s,
+                                k1 - k0, st->h2d);
+        }
         if (b_layout == MXG_ROWS_CONTIGUOUS) return upload_lines(ring, d_B, ld_b * s, B, ldb * s, nz * s, Kz, st->h2d);
         return upload_lines(ring, d_tmp, Kz * s, B, ldb * s, Kz * s, nz, st->h2d);
     };
@@ -662,6 +712,23 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     trace.plan_ms = trace.now() - t_plan;
     if (cs.staging_unavailable) stage_out = false;
     if (stage_B) MXG_TRY(upload_dense(&cs.ring));
+    if (share) {
+        // publish this device's copy and the event behind its slice, then pull the peers' slices over NVLink on a
+        // stream of their own (the CSR chunks keep the PCIe upload stream busy meanwhile)
+        MXG_CUDA_TRY(cudaEventRecord(share->slice_ready[share_rank], st->h2d));
+        share->d_B[share_rank] = d_B;
+        if (!share->wait(0, share_rank)) return fail(MXG_ERR_CUDA, "multi-device product: another device failed");
+        for (int dq = 1; dq < share->G; dq++) {
+            const int q = (share_rank + dq) % share->G; // every device starts with a different peer
+            size_t k0, k1;
+            slice(q, k0, k1);
+            MXG_CUDA_TRY(cudaStreamWaitEvent(st->p2p, share->slice_ready[q], 0));
+            MXG_CUDA_TRY(cudaMemcpyPeerAsync(d_B + k0 * ld_b * s, share->device[share_rank],
+                                             static_cast<char *>(share->d_B[q]) + k0 * ld_b * s, share->device[q],
+                                             (k1 - k0) * ld_b * s, st->p2p));
+        }
+        MXG_TRY(chain(sc, st->p2p, st->stream));
+    }
     MXG_TRY(chain(sc, st->h2d, st->stream));
     if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS)
         MXG_TRY(launch_transpose_dense((int)s, nz, Kz, d_tmp, Kz, d_B, ld_b, st->stream)); // [n][K] -> [K][ld_b]
@@ -716,19 +783,22 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
         if (c >= 2) MXG_TRY(drain(c - 2));
     }
     const double t_fin = trace.now();
-    const int rc = cs.finish();
+    int rc = cs.finish();
     trace.finish_ms = trace.now() - t_fin;
     trace.report("spmm", C);
+    // nobody may release its copy of the dense operand while a peer is still pulling slices out of it
+    if (share && !share->wait(1, share_rank) && rc == MXG_OK) rc = fail(MXG_ERR_CUDA, "multi-device product: another device failed");
+    if (rc == MXG_OK && keep) rc = cs.detach_handle(keep);
     return rc;
 }
 
 int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x,
-                  const void *y, void *out)
+                  const void *y, void *out, mxg_csr_s **keep)
 {
     if (m == 0) return MXG_OK;
     if (!out) return fail(MXG_ERR_ARG, "output is NULL");
     if (K > 0 && !y) return fail(MXG_ERR_ARG, "vector is NULL");
-    const int64_t nnz = p[m];
+    const int64_t nnz = (int64_t)p[m] - (int64_t)p[0];
     if (nnz > 0 && (!j || !x)) return fail(MXG_ERR_ARG, "csr: indices / values is NULL");
     const size_t ys = ytype == MXG_Y_NUMERIC ? 8 : 4;
     const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
@@ -786,7 +856,181 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
         if (c >= 1 && c <= C) MXG_TRY(process(c - 1));
         if (c >= 2) MXG_TRY(drain(c - 2));
     }
-    return cs.finish();
+    int rc = cs.finish();
+    if (rc == MXG_OK && keep && p[0] == 0) rc = cs.detach_handle(keep);
+    return rc;
+}
+
+// ================================================================================================
+// Warm path: the CSR is already device-resident (an explicit handle from mxg_csr_upload, or an
+// entry of the level-1 operand cache), so a product only moves the dense operand up and the result down.
+// The result leaves in row chunks: chunk c is downloaded (and, for a pageable result, copied out of its
+// page-locked slot by the host threads) while chunk c + 1 is computed.  Long rows (pieces + fix-up) run first.
+// ================================================================================================
+namespace {
+
+// row chunks of a handle (about 16 of equal nnz, tapered like the streamed plan), computed once per handle
+int handle_chunks(mxg_csr_s *A, cudaStream_t stream)
+{
+    if (A->host_chunks) return MXG_OK;
+    std::vector<int32_t> hp((size_t)A->m + 1);
+    MXG_CUDA_TRY(cudaMemcpyAsync(hp.data(), A->d_p, sizeof(int32_t) * hp.size(), cudaMemcpyDeviceToHost, stream));
+    MXG_CUDA_TRY(cudaStreamSynchronize(stream));
+    HostPlan plan;
+    MXG_TRY(build_plan(A->m, hp.data(), plan, 0));
+    A->host_chunks = new std::vector<int32_t>(plan.chunk_row.begin(), plan.chunk_row.end());
+    return MXG_OK;
+}
+
+} // namespace
+
+int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
+                     void *Out, size_t ldc, const void *d_B_resident, void **d_B_keep)
+{
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    const size_t vec = 16 / s;
+    const int m = A->m, K = A->K;
+    const size_t rows = (size_t)m, Kz = (size_t)K, nz = (size_t)n;
+    if (d_B_keep) *d_B_keep = nullptr;
+    if (m == 0 || n == 0) return MXG_OK;
+    if (!Out) return fail(MXG_ERR_ARG, "output is NULL");
+    if (!B && K > 0 && !d_B_resident) return fail(MXG_ERR_ARG, "dense operand is NULL");
+    if (b_layout != MXG_ROWS_CONTIGUOUS && b_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "dense operand: bad layout %d", b_layout);
+    if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
+    if (b_layout == MXG_ROWS_CONTIGUOUS && ldb < nz) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
+    if (b_layout == MXG_COLS_CONTIGUOUS && ldb < Kz) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
+    if (out_layout == MXG_ROWS_CONTIGUOUS && ldc < nz) return fail(MXG_ERR_ARG, "output: ldc < n");
+    if (out_layout == MXG_COLS_CONTIGUOUS && ldc < rows) return fail(MXG_ERR_ARG, "output: ldc < m");
+    if (dtype == MXG_F64 && !A->d_x64 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "handle holds no float64 values");
+    if (dtype == MXG_F32 && !A->d_x32 && A->nnz > 0) return fail(MXG_ERR_UNSUPPORTED, "handle holds no float32 values");
+
+    g_h2d_bytes = g_d2h_bytes = 0;
+    MXG_TRY(handle_chunks(A, st->stream));
+    const std::vector<int32_t> &cr = *A->host_chunks;
+    // chunks of at most 64 MiB of result rows (the output slots of the page-locked arena are sized by the largest)
+    std::vector<int32_t> chunk_row;
+    const size_t cap_rows = std::max<size_t>(1 << 12, ((size_t)64 << 20) / (nz * s));
+    chunk_row.push_back(0);
+    for (size_t c = 0; c + 1 < cr.size(); c++) {
+        const size_t r0 = (size_t)cr[c], r1 = (size_t)cr[c + 1];
+        const size_t parts = (r1 - r0 + cap_rows - 1) / cap_rows;
+        for (size_t q = 1; q <= parts; q++) chunk_row.push_back((int32_t)(r0 + (r1 - r0) * q / parts));
+    }
+    const int C = (int)chunk_row.size() - 1;
+    size_t max_rows = 0;
+    for (int c = 0; c < C; c++) max_rows = std::max(max_rows, (size_t)(chunk_row[(size_t)c + 1] - chunk_row[(size_t)c]));
+
+    Scratch sc(st);
+    const bool stage = options().host_stage != 0;
+    const bool have_B = d_B_resident != nullptr;
+    const bool stage_B = stage && K > 0 && !have_B && !host_is_pinned(B);
+    bool stage_out = stage && !host_is_pinned(Out);
+    const size_t ld_b = round_up(nz, vec);
+    const size_t ld_o = out_layout == MXG_ROWS_CONTIGUOUS ? round_up(nz, vec) : rows;
+    const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
+    char *d_B = const_cast<char *>(static_cast<const char *>(d_B_resident)), *d_Out = nullptr, *d_tmp = nullptr;
+    if (!have_B) {
+        if (d_B_keep) { // the caller keeps the device copy (operand cache): not a temporary of this call
+            MXG_CUDA_TRY(cudaMallocAsync((void **)&d_B, std::max<size_t>(Kz * ld_b * s, 16), st->stream));
+            *d_B_keep = d_B;
+        } else {
+            MXG_TRY(sc.alloc((void **)&d_B, Kz * ld_b * s));
+        }
+    }
+    MXG_TRY(sc.alloc((void **)&d_Out, rm ? rows * ld_o * s : rows * nz * s));
+    // page-locked arena: input slots for a pageable dense operand, output slots for a pageable result
+    auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
+    const int S = (int)std::min<long>(std::max<long>(options().pipe_slots, 3), 8);
+    const size_t in_slot = stage_B ? (size_t)16 << 20 : 0;
+    size_t out_slot_bytes = stage_out ? up(max_rows * nz * s) : 0;
+    InRing ring;
+    char *out_base = nullptr;
+    if (in_slot + out_slot_bytes > 0) {
+        char *base = nullptr;
+        if (pinned_arena(st, (size_t)S * (in_slot + out_slot_bytes), &base) != MXG_OK) {
+            cudaGetLastError();
+            last_error_ref().clear();
+            stage_out = false; // the driver's own copies still work
+        } else {
+            if (in_slot) MXG_TRY(ring.init(sc, base, in_slot, S));
+            out_base = base + (size_t)S * in_slot;
+        }
+    }
+    if (!have_B && K > 0) {
+        if (b_layout == MXG_COLS_CONTIGUOUS) MXG_TRY(sc.alloc((void **)&d_tmp, Kz * nz * s));
+        if (ld_b != nz) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, Kz * ld_b * s, st->stream));
+        MXG_TRY(chain(sc, st->stream, st->h2d));
+        InRing *rg = ring.enabled() ? &ring : nullptr;
+        if (b_layout == MXG_ROWS_CONTIGUOUS) MXG_TRY(upload_lines(rg, d_B, ld_b * s, B, ldb * s, nz * s, Kz, st->h2d));
+        else MXG_TRY(upload_lines(rg, d_tmp, Kz * s, B, ldb * s, Kz * s, nz, st->h2d));
+        MXG_TRY(chain(sc, st->h2d, st->stream));
+        if (b_layout == MXG_COLS_CONTIGUOUS) MXG_TRY(launch_transpose_dense((int)s, nz, Kz, d_tmp, Kz, d_B, ld_b, st->stream));
+    }
+    std::vector<cudaEvent_t> ev_done((size_t)C), ev_out((size_t)(stage_out ? C : 0));
+    for (int c = 0; c < C; c++) MXG_TRY(sc.event(&ev_done[(size_t)c]));
+    for (size_t c = 0; c < ev_out.size(); c++) MXG_TRY(sc.event(&ev_out[c]));
+    auto out_slot = [&](int c) { return out_base + (size_t)(c % S) * out_slot_bytes; };
+
+    // a matrix without stored entries: one zero fill of the whole result (src/matmul.cpp:128-129), chunks only copy
+    if (A->nnz == 0) MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, st->stream));
+    else if (A->n_pieces > 0) MXG_TRY(launch_spmm_rows(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, 0, 0, /*pieces=*/1, st->stream));
+    auto process = [&](int c) -> int {
+        const size_t r0 = (size_t)chunk_row[(size_t)c], nr = (size_t)chunk_row[(size_t)c + 1] - r0;
+        if (A->nnz > 0)
+            MXG_TRY(launch_spmm_rows(A, dtype, out_layout, n, d_B, ld_b, d_Out, ld_o, (int)r0, (int)(r0 + nr), /*pieces=*/0, st->stream));
+        MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)c], st->stream));
+        MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)c], 0));
+        char *d_o = d_Out + (rm ? r0 * ld_o * s : r0 * s);
+        const size_t width = rm ? nz * s : nr * s, height = rm ? nr : nz;
+        if (stage_out) {
+            MXG_TRY(copy_rows(out_slot(c), width, d_o, ld_o * s, width, height, cudaMemcpyDeviceToHost, st->d2h));
+            MXG_CUDA_TRY(cudaEventRecord(ev_out[(size_t)c], st->d2h));
+        } else {
+            char *h_o = static_cast<char *>(Out) + (rm ? r0 * ldc * s : r0 * s);
+            MXG_TRY(copy_rows(h_o, ldc * s, d_o, ld_o * s, width, height, cudaMemcpyDeviceToHost, st->d2h));
+        }
+        return MXG_OK;
+    };
+    auto drain = [&](int c) -> int {
+        if (!stage_out) return MXG_OK;
+        const size_t r0 = (size_t)chunk_row[(size_t)c], nr = (size_t)chunk_row[(size_t)c + 1] - r0;
+        const size_t width = rm ? nz * s : nr * s, height = rm ? nr : nz;
+        MXG_CUDA_TRY(cudaEventSynchronize(ev_out[(size_t)c]));
+        char *h_o = static_cast<char *>(Out) + (rm ? r0 * ldc * s : r0 * s);
+        host_copy_2d(h_o, ldc * s, out_slot(c), width, width, height);
+        return MXG_OK;
+    };
+    // output slot c % S is free again once chunk c - S has been drained: keep S - 1 downloads in flight
+    for (int c = 0; c < C + S - 1; c++) {
+        if (c >= S - 1) MXG_TRY(drain(c - (S - 1)));
+        if (c < C) MXG_TRY(process(c));
+    }
+    MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    MXG_CUDA_TRY(cudaStreamSynchronize(st->d2h));
+    return MXG_OK;
+}
+
+int handle_spmv_host(DeviceState *st, mxg_csr_s *A, int ytype, const void *y, void *out)
+{
+    const int m = A->m, K = A->K;
+    if (m == 0) return MXG_OK;
+    if (!out) return fail(MXG_ERR_ARG, "output is NULL");
+    if (K > 0 && !y) return fail(MXG_ERR_ARG, "vector is NULL");
+    const size_t ys = ytype == MXG_Y_NUMERIC ? 8 : 4;
+    const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
+    g_h2d_bytes = g_d2h_bytes = 0;
+    Scratch sc(st);
+    char *d_y = nullptr, *d_out = nullptr;
+    MXG_TRY(sc.alloc((void **)&d_y, (size_t)K * ys));
+    MXG_TRY(sc.alloc((void **)&d_out, (size_t)m * os));
+    cudaStream_t q = st->stream;
+    g_h2d_bytes += (size_t)K * ys;
+    g_d2h_bytes += (size_t)m * os;
+    MXG_TRY(staged_h2d(st, d_y, y, (size_t)K * ys, q));
+    MXG_TRY(launch_spmv(A, ytype, d_y, d_out, q));
+    MXG_TRY(staged_d2h(st, out, d_out, (size_t)m * os, q));
+    MXG_CUDA_TRY(cudaStreamSynchronize(q));
+    return MXG_OK;
 }
 
 } // namespace mxg

@@ -652,8 +652,9 @@ static int plan_panels(mxg_csr_s *A, size_t b_bytes, cudaStream_t stream, SpmmAr
 
 template <typename T>
 static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, const T *d_B, size_t ldb,
-                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast)
+                      int n_dst, void *const *d_outs, size_t ldc, cudaStream_t stream, int mcast, int part = 0)
 {
+    // part 0: the whole product; 1: short rows only (row CTAs); 2: long rows only (piece CTAs + fix-up)
     constexpr int VEC = 16 / (int)sizeof(T);
     const bool colmajor = out_layout == MXG_COLS_CONTIGUOUS;
     const size_t out_rows = (size_t)A->m;
@@ -709,7 +710,8 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.mcast = mcast;
     for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.piece = A->piece;
-    args.n_pieces = A->n_pieces;
+    args.n_pieces = part == 1 ? 0 : A->n_pieces;
+    if (part == 2) args.m = 0; // no row CTAs
     args.piece_row = A->d_piece_row;
     args.piece_k = A->d_piece_k;
     args.partial = nullptr;
@@ -718,8 +720,8 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.panel = 0;
     args.n_panels = 1;
     args.panel_width = A->K > 0 ? A->K : 1;
-    if (n_dst == 1) MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
-    if (A->n_pieces > 0) {
+    if (n_dst == 1 && part == 0) MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
+    if (args.n_pieces > 0) {
         MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * (size_t)n * sizeof(T)));
         args.partial = A->d_partial;
     }
@@ -734,7 +736,7 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     }
     MXG_TRY(rc);
 
-    if (A->n_long > 0) {
+    if (A->n_long > 0 && part != 1) {
         DstList out;
         out.n = n_dst;
         for (int d = 0; d < MXG_MAX_DST; d++) out.dst[d] = d < n_dst ? d_outs[d] : nullptr;
@@ -753,6 +755,34 @@ int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void
 {
     void *outs[1] = {d_Out};
     return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, 1, outs, ldc, stream, 0);
+}
+
+// Rows [r0, r1) of the product without their long rows, or the long rows alone: how the warm host-buffer path
+// (pipeline.cu: handle_spmm_host) lets result chunks leave the device while later rows are still being computed.
+int launch_spmm_rows(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb, void *d_Out,
+                     size_t ldc, int r0, int r1, int pieces, cudaStream_t stream)
+{
+    if (n <= 0 || A->nnz == 0) return fail(MXG_ERR_ARG, "spmm_rows: empty product");
+    if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "spmm: bad out_layout %d", out_layout);
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "spmm: bad dtype %d", dtype);
+    if ((dtype == MXG_F64 && !A->d_x64) || (dtype == MXG_F32 && !A->d_x32)) return fail(MXG_ERR_UNSUPPORTED, "spmm: handle lacks the values of this type");
+    if (pieces) { // the handle itself: piece tables and the partial-sum workspace belong to it
+        if (A->n_pieces == 0) return MXG_OK;
+        void *outs[1] = {d_Out};
+        if (dtype == MXG_F64)
+            return spmm_typed<double>(A, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb, 1, outs, ldc, stream, 0, 2);
+        return spmm_typed<float>(A, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb, 1, outs, ldc, stream, 0, 2);
+    }
+    if (r0 < 0 || r1 > A->m || r0 > r1) return fail(MXG_ERR_ARG, "spmm_rows: bad row range");
+    if (r0 == r1) return MXG_OK;
+    mxg_csr_s v = *A; // a view: same arrays, a window of the rows (offsets in d_p are absolute)
+    v.m = r1 - r0;
+    v.d_p = A->d_p + r0;
+    void *outs[1] = {static_cast<char *>(d_Out) + (out_layout == MXG_ROWS_CONTIGUOUS ? (size_t)r0 * ldc * s : (size_t)r0 * s)};
+    if (dtype == MXG_F64)
+        return spmm_typed<double>(&v, A->d_x64, out_layout, n, static_cast<const double *>(d_B), ldb, 1, outs, ldc, stream, 0, 1);
+    return spmm_typed<float>(&v, A->d_x32, out_layout, n, static_cast<const float *>(d_B), ldb, 1, outs, ldc, stream, 0, 1);
 }
 
 int launch_spmm_multi(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,

@@ -14,6 +14,8 @@
 
 #include <limits.h>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace mxg {
 
@@ -237,6 +239,126 @@ __global__ void __launch_bounds__(128) k_spmv_fixup(int n_long, const int32_t *_
     store_result<YTYPE>(out, extra, long_rows[i], s, na);
 }
 
+// Texture objects over the dense vector y.  A kernel argument carries only the 64-bit handle of the object, so the
+// object has to outlive every launch that fetches through it: objects are cached per (device, address, size) and
+// each carries an event recorded behind its most recent launch.  A repeated y (power iteration, L-BFGS) re-uses its
+// object; an entry is destroyed only when it is evicted AND its event has completed (the oldest one is waited for
+// when all 16 are in flight).  mxg_trim() empties the cache.
+namespace {
+struct TexEntry {
+    int device = -1;
+    const void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaTextureObject_t tex = 0;
+    cudaEvent_t last_use = nullptr;
+    bool used = false; // last_use has been recorded
+    int leases = 0;    // launches being enqueued through it right now
+    unsigned long long stamp = 0;
+};
+std::mutex g_tex_mu;
+std::vector<TexEntry> g_tex;
+unsigned long long g_tex_clock = 0;
+constexpr size_t TEX_CACHE = 16;
+
+void tex_destroy(TexEntry &e)
+{
+    if (e.used) cudaEventSynchronize(e.last_use);
+    if (e.tex) cudaDestroyTextureObject(e.tex);
+    if (e.last_use) cudaEventDestroy(e.last_use);
+    e = TexEntry();
+}
+} // namespace
+
+void texture_cache_clear()
+{
+    std::lock_guard<std::mutex> lk(g_tex_mu);
+    for (TexEntry &e : g_tex) tex_destroy(e);
+    g_tex.clear();
+}
+
+struct TexLease {
+    cudaTextureObject_t tex = 0;
+    int slot = -1;
+    int acquire(const void *d_y, size_t bytes)
+    {
+        int dev = 0;
+        MXG_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(g_tex_mu);
+        for (size_t i = 0; i < g_tex.size(); i++) {
+            TexEntry &e = g_tex[i];
+            if (e.tex && e.device == dev && e.ptr == d_y && e.bytes == bytes) {
+                e.leases++;
+                e.stamp = ++g_tex_clock;
+                tex = e.tex;
+                slot = (int)i;
+                return MXG_OK;
+            }
+        }
+        // a free slot, else the least recently used entry nobody is launching through (finished ones first)
+        int pick = -1;
+        for (size_t i = 0; i < g_tex.size() && pick < 0; i++)
+            if (!g_tex[i].tex) pick = (int)i;
+        if (pick < 0 && g_tex.size() < TEX_CACHE) {
+            g_tex.emplace_back();
+            pick = (int)g_tex.size() - 1;
+        }
+        if (pick < 0) {
+            int oldest = -1, oldest_done = -1;
+            for (size_t i = 0; i < g_tex.size(); i++) {
+                TexEntry &e = g_tex[i];
+                if (e.leases > 0) continue;
+                if (oldest < 0 || e.stamp < g_tex[(size_t)oldest].stamp) oldest = (int)i;
+                const bool done = !e.used || cudaEventQuery(e.last_use) == cudaSuccess;
+                if (done && (oldest_done < 0 || e.stamp < g_tex[(size_t)oldest_done].stamp)) oldest_done = (int)i;
+            }
+            cudaGetLastError(); // cudaErrorNotReady is an answer, not an error
+            pick = oldest_done >= 0 ? oldest_done : oldest;
+            if (pick < 0) return MXG_OK; // every entry is mid-launch on other threads: this product uses plain loads
+            tex_destroy(g_tex[(size_t)pick]); // waits for its last launch when that is still running
+        }
+        TexEntry &e = g_tex[(size_t)pick];
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = const_cast<void *>(d_y);
+        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindSigned);
+        rd.res.linear.sizeInBytes = bytes;
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        MXG_CUDA_TRY(cudaCreateTextureObject(&e.tex, &rd, &td, nullptr));
+        if (cudaEventCreateWithFlags(&e.last_use, cudaEventDisableTiming) != cudaSuccess) {
+            cudaDestroyTextureObject(e.tex);
+            e = TexEntry();
+            return fail(MXG_ERR_CUDA, "spmv: cudaEventCreate failed");
+        }
+        e.device = dev;
+        e.ptr = d_y;
+        e.bytes = bytes;
+        e.leases = 1;
+        e.stamp = ++g_tex_clock;
+        tex = e.tex;
+        slot = pick;
+        return MXG_OK;
+    }
+    // after the launch (or instead of it, on an error path): mark the object busy until `stream` gets here
+    int release(cudaStream_t stream)
+    {
+        if (slot < 0) return MXG_OK;
+        std::lock_guard<std::mutex> lk(g_tex_mu);
+        TexEntry &e = g_tex[(size_t)slot];
+        slot = -1;
+        e.leases--;
+        MXG_CUDA_TRY(cudaEventRecord(e.last_use, stream));
+        e.used = true;
+        return MXG_OK;
+    }
+    ~TexLease()
+    {
+        if (slot < 0) return; // released
+        std::lock_guard<std::mutex> lk(g_tex_mu);
+        g_tex[(size_t)slot].leases--; // error path before any launch: nothing is in flight through this lease
+    }
+};
+
 template <int YTYPE, typename XT>
 static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int n_dst, void *const *d_outs, cudaStream_t stream)
 {
@@ -277,17 +399,10 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int
     }
     args.rows_per_team = 4;
     args.tex = 0;
-    cudaTextureObject_t tex = 0;
+    TexLease lease;
     if (YTYPE == MXG_Y_NUMERIC && options().spmv_tex != 0 && A->K > 0 && A->K <= (1 << 27) && (((uintptr_t)d_y & 255) == 0)) {
-        cudaResourceDesc rd = {};
-        rd.resType = cudaResourceTypeLinear;
-        rd.res.linear.devPtr = const_cast<void *>(d_y);
-        rd.res.linear.desc = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindSigned);
-        rd.res.linear.sizeInBytes = (size_t)A->K * 8;
-        cudaTextureDesc td = {};
-        td.readMode = cudaReadModeElementType;
-        MXG_CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
-        args.tex = tex;
+        MXG_TRY(lease.acquire(d_y, (size_t)A->K * 8));
+        args.tex = lease.tex;
     }
 #define MXG_SPMV(L)                                                                              \
     if (lpr == L) {                                                                              \
@@ -300,7 +415,7 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int
         return fail(MXG_ERR_ARG, "spmv: unsupported team size %d", lpr);
     }
 #undef MXG_SPMV
-    if (tex) cudaDestroyTextureObject(tex); // the launch holds its own copy of the descriptor handle
+    MXG_TRY(lease.release(stream)); // the object stays alive (cached) until the kernel that fetches through it has run
     if (A->n_long > 0) {
         MXG_LAUNCH((k_spmv_fixup<YTYPE>), ceil_div_i(A->n_long, 128), 128, 0, stream, A->n_long, A->d_long_rows,
                    A->d_long_first, A->d_long_np, args.partial, args.partial_na,
@@ -335,6 +450,80 @@ int launch_spmv_multi(const mxg_csr_s *A, int ytype, const void *d_y, int n_dst,
     case MXG_Y_FLOAT32: return spmv_values<MXG_Y_FLOAT32>(A, d_y, n_dst, d_outs, stream);
     default: return fail(MXG_ERR_ARG, "spmv: bad ytype %d", ytype);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Measurement probe (mxg_dev_spmv_probe): the access pattern of K3 with the row structure taken away.  Every
+// thread streams 4 consecutive column ids of the handle per step (one 16-byte load, U steps in flight) and,
+// depending on `mode`, gathers y[j] for each of them — no indptr, no per-row reduction, no result vector.
+//   mode 0: ids only (the streaming floor of the 4-byte index array)
+//   mode 1: ids + 8-byte gathers of y through plain loads          mode 2: ... through the texture path
+//   mode 3: ids + values (12 streamed bytes per entry) + gathers through the texture path + FMA
+// The time of mode 2 / 3 is what one L1 wavefront + one 32-byte L2 sector per stored entry costs on this matrix:
+// the floor K3 is measured against.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_spmv_probe(size_t nnz4, const int4 *__restrict__ j4, const double2 *__restrict__ x2,
+                                                    const double *__restrict__ y, cudaTextureObject_t tex, double *sink)
+{
+    constexpr int U = 2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz4; e += stride * U) {
+        int4 jj[U];
+        double2 xa[U], xb[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t q = e + (size_t)u * stride;
+            jj[u] = q < nnz4 ? __ldcs(j4 + q) : make_int4(0, 0, 0, 0);
+            if (MODE == 3) {
+                xa[u] = q < nnz4 ? __ldcs(x2 + 2 * q) : make_double2(0.0, 0.0);
+                xb[u] = q < nnz4 ? __ldcs(x2 + 2 * q + 1) : make_double2(0.0, 0.0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (MODE == 0) {
+                acc += (double)(jj[u].x ^ jj[u].y ^ jj[u].z ^ jj[u].w);
+            } else if (MODE == 1) {
+                acc += __ldg(y + jj[u].x) + __ldg(y + jj[u].y) + __ldg(y + jj[u].z) + __ldg(y + jj[u].w);
+            } else {
+                const int2 a = tex1Dfetch<int2>(tex, jj[u].x), b = tex1Dfetch<int2>(tex, jj[u].y);
+                const int2 c = tex1Dfetch<int2>(tex, jj[u].z), d = tex1Dfetch<int2>(tex, jj[u].w);
+                const double ya = __hiloint2double(a.y, a.x), yb = __hiloint2double(b.y, b.x);
+                const double yc = __hiloint2double(c.y, c.x), yd = __hiloint2double(d.y, d.x);
+                if (MODE == 3) acc = fma(xa[u].x, ya, fma(xa[u].y, yb, fma(xb[u].x, yc, fma(xb[u].y, yd, acc))));
+                else acc += ya + yb + yc + yd;
+            }
+        }
+    }
+    if (acc == 123.456) sink[0] = acc; // never true: keeps the loads alive
+}
+
+int spmv_probe(const mxg_csr_s *A, int mode, const double *d_y, double *d_sink, cudaStream_t stream)
+{
+    if (mode < 0 || mode > 3) return fail(MXG_ERR_ARG, "spmv_probe: mode 0 .. 3");
+    if (A->nnz < 4 || A->base != 0) return fail(MXG_ERR_ARG, "spmv_probe: needs an owned handle with stored entries");
+    if (mode == 3 && !A->d_x64) return fail(MXG_ERR_UNSUPPORTED, "spmv_probe: handle holds no float64 values");
+    if (mode >= 1 && (!d_y || A->K <= 0)) return fail(MXG_ERR_ARG, "spmv_probe: NULL vector");
+    const size_t nnz4 = (size_t)A->nnz / 4;
+    const int4 *j4 = reinterpret_cast<const int4 *>(A->d_j);
+    const double2 *x2 = reinterpret_cast<const double2 *>(A->d_x64);
+    TexLease lease;
+    if (mode >= 2) {
+        MXG_TRY(lease.acquire(d_y, (size_t)A->K * 8));
+        if (!lease.tex) return fail(MXG_ERR_CUDA, "spmv_probe: no texture object");
+    }
+    const int grid = 148 * 16;
+    switch (mode) {
+    case 0: MXG_LAUNCH(k_spmv_probe<0>, grid, 256, 0, stream, nnz4, j4, x2, d_y, lease.tex, d_sink); break;
+    case 1: MXG_LAUNCH(k_spmv_probe<1>, grid, 256, 0, stream, nnz4, j4, x2, d_y, lease.tex, d_sink); break;
+    case 2: MXG_LAUNCH(k_spmv_probe<2>, grid, 256, 0, stream, nnz4, j4, x2, d_y, lease.tex, d_sink); break;
+    default: MXG_LAUNCH(k_spmv_probe<3>, grid, 256, 0, stream, nnz4, j4, x2, d_y, lease.tex, d_sink); break;
+    }
+    MXG_TRY(lease.release(stream));
+    return MXG_OK;
 }
 
 

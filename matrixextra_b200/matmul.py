@@ -18,7 +18,7 @@ import numpy as np
 
 from . import rcpp_exports as rx
 from ._lib import MXG_F32, MXG_F64
-from .classes import check_valid_matrix, dgCMatrix, dgRMatrix, float32, sparseVector, t_shallow
+from .classes import check_valid_matrix, dgCMatrix, dgRMatrix, float32, gpuRsparse, sparseVector, t_shallow
 
 #: options("MatrixExtra.*") read by the hot path (R/zzz.R:116-171).  ``nthreads`` defaults to all cores in the
 #: reference (parallel::detectCores(), R/zzz.R:140-171); here it sizes the library's host staging threads, 0 = all.
@@ -213,9 +213,38 @@ def gemm_dense_csr(x, y: dgRMatrix):
     return np.asfortranarray(res.T)
 
 
+# ---- device-resident left/right operands (rglue/matmul_gpu_methods.R: class gpuRsparse) ----
+def _gpu_product(kind, g: gpuRsparse, d):
+    """kind: 'A.tD' = g %*% t(d), 'D.tA' = d %*% t(g), 'tA.D' = t(g) %*% d — same preparation as the methods above."""
+    nt = _nthreads()
+    f32 = isinstance(d, float32)
+    dm = d.Data if f32 else _as_double(d)
+    fn = {("A.tD", False): rx.gpu_csr_tcrossprod_dense_numeric, ("A.tD", True): rx.gpu_csr_tcrossprod_dense_float32,
+          ("tA.D", False): rx.gpu_csr_crossprod_dense_numeric, ("tA.D", True): rx.gpu_csr_crossprod_dense_float32}
+    if kind == "D.tA":
+        res = (rx.gpu_csr_dense_tcrossprod_float32 if f32 else rx.gpu_csr_dense_tcrossprod_numeric)(dm, g.ptr, nt)
+    else:
+        res = fn[(kind, f32)](g.ptr, dm, nt)
+    return float32(res) if f32 else res
+
+
+def _t_dense(d):
+    return float32(d.Data.T) if isinstance(d, float32) else np.asfortranarray(np.asarray(d).T)
+
+
 # ---- dispatch ---------------------------------------------------------------------------------------
 def matmul(x, y):
     """``x %*% y``."""
+    if isinstance(x, gpuRsparse):
+        if isinstance(y, np.ndarray) and y.ndim == 1:
+            if x.Dim[1] != y.size:
+                raise ValueError("Matrix-vector dimensions do not match.")
+            return rx.gpu_csr_dvec_numeric(x.ptr, y.astype(np.float64, copy=False), _nthreads()).reshape(-1, 1)
+        check_dimensions_match(x, y, matmult=True)
+        return _gpu_product("A.tD", x, _t_dense(y))  # `%*%`(Rsparse, matrix) = tcrossprod(x, t(y)), R/matmul.R:463-465
+    if isinstance(y, gpuRsparse):  # matrix %*% Rsparse = t(crossprod(y, t(x)))
+        check_dimensions_match(x, y, matmult=True)
+        return _t_dense(_gpu_product("tA.D", y, _t_dense(x)))
     if _is_dense(x) and isinstance(y, dgCMatrix):
         return gemm_dense_csc(x, y)
     if isinstance(x, float32) and isinstance(y, dgCMatrix):
@@ -235,6 +264,9 @@ def matmul(x, y):
 
 def crossprod(x, y):
     """``t(x) %*% y``."""
+    if isinstance(x, gpuRsparse):
+        check_dimensions_match(x, y, crossprod=True)
+        return _gpu_product("tA.D", x, y)
     if _is_dense(x) and isinstance(y, dgCMatrix):
         return crossprod_dense_csc(x, y)
     if isinstance(x, float32) and isinstance(y, dgCMatrix):
@@ -246,6 +278,12 @@ def crossprod(x, y):
 
 def tcrossprod(x, y):
     """``x %*% t(y)``."""
+    if isinstance(x, gpuRsparse):
+        check_dimensions_match(x, y, tcrossprod=True)
+        return _gpu_product("A.tD", x, y)
+    if isinstance(y, gpuRsparse):
+        check_dimensions_match(x, y, tcrossprod=True)
+        return _gpu_product("D.tA", y, x)
     if _is_dense(x) and isinstance(y, dgRMatrix):
         return tcrossprod_dense_csr(x, y)
     if isinstance(x, float32) and isinstance(y, dgRMatrix):

@@ -312,3 +312,150 @@ def crossprod_csr_dense(indptr, indices, values, ncols_X, Y_colmajor, dtype=MXG_
     _lib.call("mxg_spmm_csrT_dense", dtype, MXG_COLS_CONTIGUOUS, MXG_COLS_CONTIGUOUS, m, K, n,
               _vp(p), _vp(j), _vp(x), _vp(Y), max(m, 1), _vp(out), max(K, 1))
     return out
+
+
+# ---- device-resident matrices (rglue/handle_gpu_glue.cpp) ----------------------------
+# The callers of the reference multiply one sparse matrix many times (vignettes/Introducing_MatrixExtra.Rmd:454-476);
+# these exports keep the CSR in HBM so that a product moves only the dense operand up and the result down.
+
+class GpuCsrPtr:
+    """What the Rcpp glue returns as an external pointer: the C handle plus its dimensions; released by ``gpu_csr_free``
+    or when the object is collected (the glue registers mxg_csr_free as the pointer's finalizer)."""
+
+    def __init__(self, handle: int, nrows: int, ncols: int, has_f64: bool, has_f32: bool):
+        self.handle, self.nrows, self.ncols, self.has_f64, self.has_f32 = handle, nrows, ncols, has_f64, has_f32
+
+    def _live(self):
+        if not self.handle:
+            raise RuntimeError("gpu matrix has been freed.")
+        return C.c_void_p(self.handle)
+
+    def __del__(self):
+        try:
+            gpu_csr_free(self)
+        except Exception:
+            pass
+
+
+def as_gpu_csr(indptr, indices, values, ncols, keep_float64=True, keep_float32=False) -> GpuCsrPtr:
+    p, j, x = _csr(indptr, indices, values)
+    if not keep_float64 and not keep_float32:
+        keep_float64 = True
+    h = C.c_void_p()
+    _lib.call("mxg_csr_upload", p.size - 1, int(ncols), _vp(p), _vp(j), _vp(x),
+              (_lib.MXG_KEEP_F64 if keep_float64 else 0) | (_lib.MXG_KEEP_F32 if keep_float32 else 0), C.byref(h))
+    return GpuCsrPtr(h.value, p.size - 1, int(ncols), bool(keep_float64), bool(keep_float32))
+
+
+def gpu_csr_free(ptr: GpuCsrPtr) -> None:
+    if ptr.handle:
+        h, ptr.handle = ptr.handle, 0
+        _lib.call("mxg_csr_free", C.c_void_p(h))
+
+
+def gpu_csr_dim(ptr: GpuCsrPtr):
+    ptr._live()
+    return np.array([ptr.nrows, ptr.ncols], dtype=np.int32)
+
+
+def _typed(ptr: GpuCsrPtr, dtype):
+    if not (ptr.has_f64 if dtype == MXG_F64 else ptr.has_f32):
+        raise RuntimeError("gpu matrix was created without values of this type.")
+    return np.float64 if dtype == MXG_F64 else np.float32
+
+
+def _gpu_csr_tcrossprod_dense(ptr, Y_colmajor, dtype, out=None):
+    h = ptr._live()
+    np_t = _typed(ptr, dtype)
+    Y = _fmat(Y_colmajor, np_t)
+    n, K = Y.shape
+    if K != ptr.ncols:
+        raise ValueError("Matrix dimensions do not match.")
+    out = _result((ptr.nrows, n), np_t, out)
+    _lib.call("mxg_csr_spmm_host", h, dtype, MXG_COLS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, n, _vp(Y), max(n, 1), _vp(out),
+              max(ptr.nrows, 1))
+    return out
+
+
+def gpu_csr_tcrossprod_dense_numeric(X: GpuCsrPtr, Y_colmajor, nthreads=0, out=None):
+    """A %*% t(Y): the handle form of tcrossprod_csr_dense_numeric (src/matmul.cpp:345-359)."""
+    _threads(nthreads)
+    return _gpu_csr_tcrossprod_dense(X, Y_colmajor, MXG_F64, out)
+
+
+def gpu_csr_tcrossprod_dense_float32(X: GpuCsrPtr, Y_colmajor, nthreads=0, out=None):
+    _threads(nthreads)
+    return _gpu_csr_tcrossprod_dense(X, Y_colmajor, MXG_F32, out)
+
+
+def _gpu_csr_dense_tcrossprod(X_colmajor, ptr, dtype, out=None):
+    h = ptr._live()
+    np_t = _typed(ptr, dtype)
+    X = _fmat(X_colmajor, np_t)
+    a, K = X.shape
+    if K != ptr.ncols:
+        raise ValueError("Matrix dimensions do not match.")
+    out = _result((a, ptr.nrows), np_t, out)
+    _lib.call("mxg_csr_spmm_host", h, dtype, MXG_ROWS_CONTIGUOUS, MXG_ROWS_CONTIGUOUS, a, _vp(X), max(a, 1), _vp(out), max(a, 1))
+    return out
+
+
+def gpu_csr_dense_tcrossprod_numeric(X_colmajor, Y: GpuCsrPtr, nthreads=0, out=None):
+    """X %*% t(A): the handle form of tcrossprod_dense_csr_numeric (src/matmul.cpp:283-297)."""
+    _threads(nthreads)
+    return _gpu_csr_dense_tcrossprod(X_colmajor, Y, MXG_F64, out)
+
+
+def gpu_csr_dense_tcrossprod_float32(X_colmajor, Y: GpuCsrPtr, nthreads=0, out=None):
+    _threads(nthreads)
+    return _gpu_csr_dense_tcrossprod(X_colmajor, Y, MXG_F32, out)
+
+
+def _gpu_csr_crossprod_dense(ptr, Y_colmajor, dtype, out=None):
+    h = ptr._live()
+    np_t = _typed(ptr, dtype)
+    Y = _fmat(Y_colmajor, np_t)
+    m, n = Y.shape
+    if m != ptr.nrows:
+        raise ValueError("Matrix dimensions do not match.")
+    out = _result((ptr.ncols, n), np_t, out)
+    _lib.call("mxg_csr_spmm_t_host", h, dtype, MXG_COLS_CONTIGUOUS, MXG_COLS_CONTIGUOUS, n, _vp(Y), max(m, 1), _vp(out),
+              max(ptr.ncols, 1))
+    return out
+
+
+def gpu_csr_crossprod_dense_numeric(X: GpuCsrPtr, Y_colmajor, nthreads=0, out=None):
+    """t(A) %*% Y: the CSC is built on the device at the first call and kept with the handle."""
+    _threads(nthreads)
+    return _gpu_csr_crossprod_dense(X, Y_colmajor, MXG_F64, out)
+
+
+def gpu_csr_crossprod_dense_float32(X: GpuCsrPtr, Y_colmajor, nthreads=0, out=None):
+    _threads(nthreads)
+    return _gpu_csr_crossprod_dense(X, Y_colmajor, MXG_F32, out)
+
+
+def gpu_csr_dvec_numeric(X: GpuCsrPtr, y_dense, nthreads=0, out=None):
+    """A %*% dense vector: the handle form of matmul_csr_dvec_numeric (src/matmul.cpp:421-435)."""
+    _threads(nthreads)
+    h = X._live()
+    if not X.has_f64:
+        raise RuntimeError("gpu matrix was created without values of this type.")
+    y = np.ascontiguousarray(y_dense, dtype=np.float64)
+    if y.size != X.ncols:
+        raise ValueError("Matrix dimensions do not match.")
+    out = _result((X.nrows,), np.float64, out)
+    _lib.call("mxg_csr_spmv_host", h, MXG_Y_NUMERIC, _vp(y), _vp(out))
+    return out
+
+
+def mxgpu_configure(gpus=0, cache_mb=-1) -> int:
+    """gpus > 0: spread every level-1 product over that many GPUs (MATRIXEXTRA_GPUS); cache_mb >= 0: size of the
+    device-resident operand cache (MATRIXEXTRA_GPU_CACHE_MB).  Returns the number of devices in use."""
+    if gpus > 0:
+        _lib.call("mxg_set_devices", int(gpus))
+    if cache_mb >= 0:
+        _lib.set_option("cache_mb", int(cache_mb))
+    n = C.c_int(1)
+    _lib.call("mxg_get_devices", C.byref(n))
+    return int(n.value)

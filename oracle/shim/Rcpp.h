@@ -286,6 +286,39 @@ inline void *ListProxy::data_ptr() const
 template <class Fn>
 SEXP unwindProtect(Fn fn, void *arg) { return fn(arg); }
 
+/* External pointers (for the device-resident handles of rglue/handle_gpu_glue.cpp): a reference-counted owner
+ * that runs the finalizer when the last copy goes away (R: when the object is garbage-collected) or on release(). */
+template <class T> struct PreserveStorage {};
+template <class T> void standard_delete_finalizer(T *obj) { delete obj; }
+template <class T, template <class> class StoragePolicy = PreserveStorage, void Finalizer(T *) = standard_delete_finalizer<T>,
+          bool finalizeOnExit = false>
+class XPtr {
+public:
+    explicit XPtr(T *p, bool set_delete_finalizer = true) : box_(std::make_shared<Box>(p, set_delete_finalizer)) {}
+    T *get() const { return box_->ptr; }
+    T *checked_get() const
+    {
+        if (!box_->ptr) throw std::runtime_error("external pointer is not valid");
+        return box_->ptr;
+    }
+    T *operator->() const { return checked_get(); }
+    void release() { box_->finalize(); }
+
+private:
+    struct Box {
+        T *ptr;
+        bool fin;
+        Box(T *p, bool f) : ptr(p), fin(f) {}
+        void finalize()
+        {
+            if (ptr && fin) Finalizer(ptr);
+            ptr = nullptr;
+        }
+        ~Box() { finalize(); }
+    };
+    std::shared_ptr<Box> box_;
+};
+
 } /* namespace Rcpp */
 
 template <class V> static inline int *INTEGER(const V &v) { return (int *)v.data_ptr(); }

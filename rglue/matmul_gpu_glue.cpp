@@ -36,6 +36,8 @@
 #define MXGPU_NEW_VECTOR(Type, n) Type(Rcpp::no_init((n)))
 #endif
 
+#include <cstdlib>
+
 #include "mxgpu.h"
 
 namespace {
@@ -43,6 +45,23 @@ namespace {
 inline void mxgpu_check(int status)
 {
     if (status != MXG_OK) MXGPU_GLUE_STOP(mxg_last_error());
+}
+
+/* Every export starts here.  `nthreads` (the reference's OpenMP team size, R/matmul.R:175-180) sizes the library's
+ * host staging threads.  Once per session the environment is read:
+ *   MATRIXEXTRA_GPUS=n          -> mxg_set_devices(n): one product is spread over n GPUs of the box, in this process
+ *   MATRIXEXTRA_GPU_CACHE_MB=c  -> option "cache_mb": device-resident operand cache for repeated products */
+inline void mxgpu_enter(int nthreads)
+{
+    static bool configured = false;
+    if (!configured) {
+        configured = true;
+        const char *gpus = std::getenv("MATRIXEXTRA_GPUS");
+        if (gpus && std::atoi(gpus) > 1) mxgpu_check(mxg_set_devices(std::atoi(gpus)));
+        const char *cache = std::getenv("MATRIXEXTRA_GPU_CACHE_MB");
+        if (cache && std::atol(cache) >= 0) mxgpu_check(mxg_set_option("cache_mb", std::atol(cache)));
+    }
+    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
 }
 
 template <class RcppMatrix>
@@ -101,7 +120,7 @@ Rcpp::NumericMatrix matmul_dense_csc_numeric(Rcpp::NumericMatrix X_colmajor, Rcp
                                              Rcpp::IntegerVector Y_csc_indices, Rcpp::NumericVector Y_csc_values,
                                              int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     return dense_times_tsparse<Rcpp::NumericMatrix>(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values);
 }
 
@@ -110,7 +129,7 @@ Rcpp::IntegerMatrix matmul_dense_csc_float32(Rcpp::IntegerMatrix X_colmajor, Rcp
                                              Rcpp::IntegerVector Y_csc_indices, Rcpp::NumericVector Y_csc_values,
                                              int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     return dense_times_tsparse<Rcpp::IntegerMatrix>(X_colmajor, Y_csc_indptr, Y_csc_indices, Y_csc_values);
 }
 
@@ -120,7 +139,7 @@ Rcpp::NumericMatrix tcrossprod_dense_csr_numeric(Rcpp::NumericMatrix X_colmajor,
                                                  Rcpp::IntegerVector Y_csr_indices, Rcpp::NumericVector Y_csr_values,
                                                  int nthreads, int ncols_Y)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     (void)ncols_Y;
     return dense_times_tsparse<Rcpp::NumericMatrix>(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values);
 }
@@ -130,7 +149,7 @@ Rcpp::IntegerMatrix tcrossprod_dense_csr_float32(Rcpp::IntegerMatrix X_colmajor,
                                                  Rcpp::IntegerVector Y_csr_indices, Rcpp::NumericVector Y_csr_values,
                                                  int nthreads, int ncols_Y)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     (void)ncols_Y;
     return dense_times_tsparse<Rcpp::IntegerMatrix>(X_colmajor, Y_csr_indptr, Y_csr_indices, Y_csr_values);
 }
@@ -141,7 +160,7 @@ Rcpp::NumericMatrix tcrossprod_csr_dense_numeric(Rcpp::IntegerVector X_csr_indpt
                                                  Rcpp::NumericVector X_csr_values, Rcpp::NumericMatrix Y_colmajor,
                                                  int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     return sparse_times_tdense<Rcpp::NumericMatrix>(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor);
 }
 
@@ -150,7 +169,7 @@ Rcpp::IntegerMatrix tcrossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indpt
                                                  Rcpp::NumericVector X_csr_values, Rcpp::IntegerMatrix Y_colmajor,
                                                  int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     return sparse_times_tdense<Rcpp::IntegerMatrix>(X_csr_indptr, X_csr_indices, X_csr_values, Y_colmajor);
 }
 
@@ -159,7 +178,7 @@ Rcpp::IntegerMatrix tcrossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indpt
 Rcpp::NumericVector matmul_csr_dvec_numeric(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::NumericVector y_dense, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_NUMERIC, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -171,7 +190,7 @@ Rcpp::NumericVector matmul_csr_dvec_numeric(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::NumericVector matmul_csr_dvec_integer(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::IntegerVector y_dense, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_INTEGER, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -183,7 +202,7 @@ Rcpp::NumericVector matmul_csr_dvec_integer(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::NumericVector matmul_csr_dvec_logical(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::LogicalVector y_dense, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::NumericVector out = MXGPU_NEW_VECTOR(Rcpp::NumericVector, m);
     mxgpu_check(mxg_spmv_csr(MXG_Y_LOGICAL, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -195,7 +214,7 @@ Rcpp::NumericVector matmul_csr_dvec_logical(Rcpp::IntegerVector X_csr_indptr, Rc
 Rcpp::IntegerVector matmul_csr_dvec_float32(Rcpp::IntegerVector X_csr_indptr, Rcpp::IntegerVector X_csr_indices,
                                             Rcpp::NumericVector X_csr_values, Rcpp::IntegerVector y_dense, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     Rcpp::IntegerVector out = MXGPU_NEW_VECTOR(Rcpp::IntegerVector, m); /* binary32 bits, like y_dense */
     mxgpu_check(mxg_spmv_csr(MXG_Y_FLOAT32, m, (int)y_dense.size(), INTEGER(X_csr_indptr), INTEGER(X_csr_indices),
@@ -212,7 +231,7 @@ Rcpp::NumericMatrix crossprod_csr_dense_numeric(Rcpp::IntegerVector X_csr_indptr
                                                 Rcpp::NumericVector X_csr_values, int ncols_X,
                                                 Rcpp::NumericMatrix Y_colmajor, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     const int n = Y_colmajor.ncol();
     if (Y_colmajor.nrow() != m) MXGPU_GLUE_STOP("Matrix dimensions do not match.");
@@ -229,7 +248,7 @@ Rcpp::IntegerMatrix crossprod_csr_dense_float32(Rcpp::IntegerVector X_csr_indptr
                                                 Rcpp::NumericVector X_csr_values, int ncols_X,
                                                 Rcpp::IntegerMatrix Y_colmajor, int nthreads)
 {
-    mxg_set_option("host_threads", nthreads > 0 ? nthreads : 0);
+    mxgpu_enter(nthreads);
     const int m = (int)X_csr_indptr.size() - 1;
     const int n = Y_colmajor.ncol();
     if (Y_colmajor.nrow() != m) MXGPU_GLUE_STOP("Matrix dimensions do not match.");

@@ -5,6 +5,7 @@
  * Return value: 0, or 1 with the R error message in gluedrv_last_error(). */
 #include "../rglue/matmul_gpu_glue.cpp"
 #include "../rglue/rowops_gpu_glue.cpp"
+#include "../rglue/handle_gpu_glue.cpp"
 
 #include <cstring>
 #include <string>
@@ -192,6 +193,56 @@ int gluedrv_mul_dvec(const int *p, int m, const int *j, const double *x, int nnz
                                                      false, false, false, true),
                  out);
     });
+}
+
+/* ---- rglue/handle_gpu_glue.cpp: device-resident matrices ---- */
+
+/* returns an opaque box holding the external pointer (NULL + gluedrv_last_error() on failure) */
+void *gluedrv_as_gpu_csr(const int *p, int m, const int *j, const double *x, int nnz, int K, int keep64, int keep32)
+{
+    void *box = nullptr;
+    guarded([&] {
+        box = new MxGpuCsrPtr(as_gpu_csr(IV((int *)p, (size_t)m + 1), IV((int *)j, (size_t)nnz), NV((double *)x, (size_t)nnz), K,
+                                         keep64 != 0, keep32 != 0));
+    });
+    return box;
+}
+
+/* explicit free (R: gpu_csr_free(h)); the box itself goes with gluedrv_gpu_csr_drop (R: the object is collected) */
+int gluedrv_gpu_csr_free(void *box)
+{
+    return guarded([&] { gpu_csr_free(*static_cast<MxGpuCsrPtr *>(box)); });
+}
+
+void gluedrv_gpu_csr_drop(void *box) { delete static_cast<MxGpuCsrPtr *>(box); }
+
+/* op 0: A %*% t(Y) (Y n x K)   1: X %*% t(A) (X a x K)   2: t(A) %*% Y (Y m x n); rows / cols = dims of the dense operand */
+int gluedrv_gpu_csr_product(void *box, int op, int f32, const void *D, int rows, int cols, void *out)
+{
+    return guarded([&] {
+        MxGpuCsrPtr &h = *static_cast<MxGpuCsrPtr *>(box);
+        if (f32) {
+            IM Dm((int *)D, rows, cols);
+            IM r = op == 0 ? gpu_csr_tcrossprod_dense_float32(h, Dm, 1)
+                           : (op == 1 ? gpu_csr_dense_tcrossprod_float32(Dm, h, 1) : gpu_csr_crossprod_dense_float32(h, Dm, 1));
+            copy_out(r, (int *)out);
+        } else {
+            NM Dm((double *)D, rows, cols);
+            NM r = op == 0 ? gpu_csr_tcrossprod_dense_numeric(h, Dm, 1)
+                           : (op == 1 ? gpu_csr_dense_tcrossprod_numeric(Dm, h, 1) : gpu_csr_crossprod_dense_numeric(h, Dm, 1));
+            copy_out(r, (double *)out);
+        }
+    });
+}
+
+int gluedrv_gpu_csr_dvec(void *box, const double *y, int K, double *out)
+{
+    return guarded([&] { copy_out(gpu_csr_dvec_numeric(*static_cast<MxGpuCsrPtr *>(box), NV((double *)y, (size_t)K), 1), out); });
+}
+
+int gluedrv_configure(int gpus, int cache_mb, int *devices)
+{
+    return guarded([&] { *devices = mxgpu_configure(gpus, cache_mb); });
 }
 
 } /* extern "C" */

@@ -23,7 +23,7 @@ def _build():
     from matrixextra_b200 import build_native
     build_native.build()
     srcs = [os.path.join(ROOT, "tests", "glue_driver.cpp"), os.path.join(ROOT, "rglue", "matmul_gpu_glue.cpp"),
-            os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp"),
+            os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp"), os.path.join(ROOT, "rglue", "handle_gpu_glue.cpp"),
             os.path.join(ROOT, "include", "mxgpu.h"), os.path.join(ROOT, "oracle", "shim", "Rcpp.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return LIB

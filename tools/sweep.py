@@ -134,6 +134,30 @@ def main():
             A.free()
         _lib.set_option("piece", 1024)
 
+    if "spmvprobe" in what:
+        # K3's access pattern without the row structure (mxg_dev_spmv_probe): ids only / + 8-byte gathers of y
+        # (plain loads, texture) / + values and FMA — the floor the SpMV kernel is measured against
+        import ctypes as C
+        w2 = WORKLOADS["cfg2"]
+        A = DeviceCSR.synth(w2["m"], w2["K"], w2["nnz"], 1, 0, seed=1002, keep=MXG_KEEP_F64)
+        y = torch.randn(A.K, device="cuda", dtype=torch.float64, generator=g)
+        o = torch.empty(A.m, device="cuda", dtype=torch.float64)
+        sink = torch.zeros(2, device="cuda", dtype=torch.float64)
+        names = {0: "ids only (4 B/entry streamed)", 1: "ids + 8-byte gathers, plain loads", 2: "ids + 8-byte gathers, texture path",
+                 3: "ids + values + texture gathers + FMA (12 B/entry streamed)"}
+        for rep in range(2):
+            for mode in (0, 1, 2, 3):
+                def probe():
+                    _lib.call("mxg_dev_spmv_probe", A._h, mode, C.c_void_p(y.data_ptr()), C.c_void_p(sink.data_ptr()),
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                ms = _time_ms(probe, args.steps, 3)
+                emit(case="spmv_probe", mode=mode, what=names[mode], nnz=A.nnz, ms=ms, Ggathers_per_s=A.nnz / ms / 1e6,
+                     streamed_GBps=A.nnz * (12 if mode == 3 else 4) / ms / 1e6)
+            ms = _time_ms(lambda: A.spmv(y, o), args.steps, 3)
+            emit(case="spmv_probe", mode="k_spmv", what="the SpMV kernel itself (cfg2)", ms=ms,
+                 eff_gbps=w_alg_bytes(A.m, A.K, A.nnz, 1, 8) / ms / 1e6)
+        A.free()
+
     if "transpose" in what:
         w4 = WORKLOADS["cfg4"]
         A = DeviceCSR.synth(w4["m"], w4["K"], w4["nnz"], 1, 0, seed=1004, keep=MXG_KEEP_F64)
