@@ -53,13 +53,48 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
-# `ncu --set full` captures of exactly these workloads (profiles/README.md); None where no capture exists.
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed `ncu --set full`
+# captures of exactly these workloads (profiles/README.md).  Every entry is tied to the kernel it was captured from
+# (mangled instantiation) and to the SHA-256 of the source file that defines it: when the source has changed since the
+# capture, `roofline.traffic` is reported as null instead of a stale number (tools/ncu_summary.py prints the entry to
+# paste here after a new capture).
 NCU_TRAFFIC = {
-    "cfg3": (15.632157e9 + 0.570318e9, "profiles/r01_v6_spmm_f32_k64_cfg3.ncu.txt"),
-    "k64f64": (39.124897e9 + 1.030659e9, "profiles/r01_v6_spmm_f64_k64.ncu.txt"),
-    "cfg2": (1.220678e9 + 0.022964e9, "profiles/r01_v6_spmv_f64_cfg2.ncu.txt"),
+    "cfg3": dict(bytes=15.632157e9 + 0.570318e9, kernel="k_spmm<float, 4, 8, 2, 4, false, false, 6, false>", src="spmm.cu",
+                 src_sha16="", capture="profiles/r01_v6_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": dict(bytes=39.124897e9 + 1.030659e9, kernel="k_spmm<double, 2, 16, 2, 4, true, false, 5, false>", src="spmm.cu",
+                   src_sha16="", capture="profiles/r01_v6_spmm_f64_k64.ncu.txt"),
+    "cfg2": dict(bytes=1.220678e9 + 0.022964e9, kernel="k_spmv<0, double, 16>", src="spmv.cu",
+                 src_sha16="", capture="profiles/r01_v6_spmv_f64_cfg2.ncu.txt"),
 }
+
+
+def source_sha16(name):
+    import hashlib
+    path = os.path.join(ROOT, "matrixextra_b200", "csrc", name)
+    try:
+        with open(path, "rb") as fh:
+            return hashlib.sha256(fh.read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
+def ncu_traffic(workload):
+    """(bytes or None, provenance string) for roofline.traffic."""
+    e = NCU_TRAFFIC.get(workload)
+    if e is None:
+        return None, None
+    now = source_sha16(e["src"])
+    if not e["src_sha16"] or now != e["src_sha16"]:
+        return None, (f"{e['capture']} ({e['kernel']}) was captured from another version of {e['src']} "
+                      f"(sha256 {e['src_sha16'] or 'unrecorded'} then, {now} now): no current figure")
+    return e["bytes"], f"{e['capture']}: {e['kernel']}, {e['src']} sha256 {now}"
+
+
+def bench_config(wl, world, nnz):
+    """`config` of the JSON line — identical in the GPU arm and the reference arm (same workload, same partition)."""
+    return {"workload": wl["desc"], "rows_per_gpu": wl["m"], "cols": wl["K"], "nnz_per_gpu": int(nnz), "n": wl["n"],
+            "parallelism": (f"row-block shards x{world}, replicated dense operand, all-gather of the output row blocks"
+                            if world > 1 else "single GPU")}
 
 
 def w_alg_bytes(m, K, nnz, n, s):
@@ -136,24 +171,24 @@ def measured_peaks():
 # CPU reference arm / cpu_baseline
 # --------------------------------------------------------------------------------------------------
 def cpu_run(cpu, wl, p, j, x, dense, nthreads):
-    """One pass of the reference's CPU path on host arrays; returns seconds (best of the call itself)."""
+    """One pass of the reference's CPU path on host arrays; returns (seconds, result or None)."""
     t0 = time.perf_counter()
     if wl["op"] == "dense_tcsr":
         fn = cpu.tcrossprod_dense_csr_float32 if wl["dtype"] == "f32" else cpu.tcrossprod_dense_csr_numeric
-        fn(dense, p, j, x, nthreads, wl["K"])
+        res = fn(dense, p, j, x, nthreads, wl["K"])
     elif wl["op"] == "csr_dense":
         fn = cpu.tcrossprod_csr_dense_float32 if wl["dtype"] == "f32" else cpu.tcrossprod_csr_dense_numeric
-        fn(p, j, x, dense, nthreads)
+        res = fn(p, j, x, dense, nthreads)
     elif wl["op"] == "spmv":
-        cpu.matmul_csr_dvec_numeric(p, j, x, dense, nthreads)
+        res = cpu.matmul_csr_dvec_numeric(p, j, x, dense, nthreads)
     elif wl["op"] == "crossprod":
         # the all-MatrixExtra CPU route (SURVEY.md §3.4): stable CSR->CSC, then matmul_dense_csc on t(Y)
         from oracle.cpu_oracle import Port
         p2, i2, x2 = Port().csr2csc(p.size - 1, wl["K"], p, j, x)
-        cpu.matmul_dense_csc_numeric(dense, p2, i2, x2, nthreads)
+        res = cpu.matmul_dense_csc_numeric(dense, p2, i2, x2, nthreads)
     else:
         raise ValueError(wl["op"])
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0, res
 
 
 def cpu_dense_operand(wl, rows, rng):
@@ -176,8 +211,32 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(wl, p, j, x, budget_s=12.0):
-    """Time the reference's CPU implementation on a bounded row sample of the SAME matrix."""
+def gpu_level1(rx, wl, p, j, x, dense, nth=0, out=None):
+    """The same product through the reference-facing entry point (Rcpp-export mirror -> level-1 C ABI), host buffers."""
+    from matrixextra_b200._lib import MXG_F32, MXG_F64
+    f32 = wl["dtype"] == "f32"
+    op = wl["op"]
+    if op == "spmv":
+        return rx.matmul_csr_dvec_numeric(p, j, x, dense, nth, out=out)
+    if op == "crossprod":  # dense is t(Y) (n x m) as the CPU route takes it; the export takes Y (m x n) column-major
+        return rx.crossprod_csr_dense(p, j, x, wl["K"], np.asfortranarray(dense.T), MXG_F32 if f32 else MXG_F64).T
+    if op == "dense_tcsr":
+        fn = rx.tcrossprod_dense_csr_float32 if f32 else rx.tcrossprod_dense_csr_numeric
+        return fn(dense, p, j, x, nth, wl["K"], out=out)
+    fn = rx.tcrossprod_csr_dense_float32 if f32 else rx.tcrossprod_csr_dense_numeric
+    return fn(p, j, x, dense, nth, out=out)
+
+
+def rel_err(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    d = float(np.max(np.abs(want))) if want.size else 0.0
+    return float(np.max(np.abs(got - want)) / d) if d > 0 else float(np.max(np.abs(got))) if got.size else 0.0
+
+
+def cpu_baseline(wl, p, j, x, dense=None, budget_s=12.0, rx=None):
+    """Time the reference's CPU implementation on a bounded row sample of the SAME matrix (all rows when that fits the
+    budget) and, with `rx`, check the GPU's level-1 result for exactly that input against it: returns (record, parity)."""
     from oracle.cpu_oracle import best_cpu_baseline
     cpu = best_cpu_baseline()
     cpu.copy_result = False
@@ -189,29 +248,93 @@ def cpu_baseline(wl, p, j, x, budget_s=12.0):
 
     def sample(r):
         pe = p[: r + 1]
-        return pe, j[: pe[-1]], x[: pe[-1]]
+        d = dense
+        if d is None:
+            d = cpu_dense_operand(wl, r, rng)
+        elif wl["op"] == "crossprod":
+            d = np.asfortranarray(dense[:, :r])
+        return pe, j[: pe[-1]], x[: pe[-1]], d
 
-    ps, js, xs = sample(rows)
-    dense = cpu_dense_operand(wl, rows, rng)
-    t_probe = cpu_run(cpu, wl, ps, js, xs, dense, nthreads)
+    ps, js, xs, ds = sample(rows)
+    t_probe, _ = cpu_run(cpu, wl, ps, js, xs, ds, nthreads)
     frac = min(1.0, max(1.0 / 32, (budget_s / 2) / max(t_probe, 1e-4) / 32))
     rows = max(1, int(m * frac))
-    ps, js, xs = sample(rows)
-    dense = cpu_dense_operand(wl, rows, rng)
-    best = min(cpu_run(cpu, wl, ps, js, xs, dense, nthreads) for _ in range(2))
+    ps, js, xs, ds = sample(rows)
+    best = min(cpu_run(cpu, wl, ps, js, xs, ds, nthreads)[0] for _ in range(2))
     nnz_s = int(ps[-1])
     gflops = 2.0 * nnz_s * wl["n"] / best / 1e9
-    return {
+    rec = {
         "value": gflops, "unit": "GFLOP/s", "cores": nthreads, "kind": cpu.kind,
         "sample": f"first {rows} of {m} rows ({nnz_s} nnz), best of 2, {best * 1e3:.1f} ms; build: {cpu.flags}; "
                   f"host: {os.cpu_count()} logical CPUs",
         "seconds": best,
     }
+    parity = None
+    if rx is not None:
+        cpu.copy_result = True
+        _, want = cpu_run(cpu, wl, ps, js, xs, ds, nthreads)
+        got = gpu_level1(rx, wl, ps, js, xs, ds)
+        tol = 1e-5 if wl["dtype"] == "f32" else 1e-12
+        err = rel_err(got, want)
+        parity = {"max_rel_err": err, "tol": tol, "ok": bool(err <= tol), "rows_checked": int(rows), "of_rows": int(m),
+                  "elements_checked": int(np.asarray(want).size),
+                  "against": f"the reference's src/matmul.cpp ({cpu.kind}, {cpu.flags}) on the same host arrays; "
+                             "GPU side: the level-1 call that e2e times"}
+    return rec, parity
 
 
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def _wall(f, k):
+    t0 = time.perf_counter()
+    for _ in range(k):
+        r = f()
+    return (time.perf_counter() - t0) / k, r
+
+
+def _lib_bytes(_lib):
+    import ctypes as _C
+    up, down = _C.c_size_t(0), _C.c_size_t(0)
+    _lib.call("mxg_last_call_bytes", _C.byref(up), _C.byref(down))
+    return int(up.value), int(down.value)
+
+
+def host_dma_roof(ndev, mb=256, reps=3):
+    """Aggregate page-locked host <-> device rate of `ndev` GPUs copying at once (plain cudaMemcpyAsync, both directions
+    together): the roof of a host-buffer call spread over those devices, whatever the library does."""
+    import torch
+    n = mb << 20
+    bufs = []
+    for g in range(ndev):
+        with torch.cuda.device(g):
+            bufs.append((torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
+                         torch.empty(n, dtype=torch.uint8, device=f"cuda:{g}"), torch.empty(n, dtype=torch.uint8, device=f"cuda:{g}"),
+                         torch.cuda.Stream(device=g), torch.cuda.Stream(device=g)))
+    out = {}
+    for what in ("h2d", "d2h", "both"):
+        best = None
+        for _ in range(reps + 1):
+            for g in range(ndev):
+                torch.cuda.synchronize(g)
+            t0 = time.perf_counter()
+            for g, (hin, hout, din, dout, s_up, s_down) in enumerate(bufs):
+                if what in ("h2d", "both"):
+                    with torch.cuda.stream(s_up):
+                        din.copy_(hin, non_blocking=True)
+                if what in ("d2h", "both"):
+                    with torch.cuda.stream(s_down):
+                        hout.copy_(dout, non_blocking=True)
+            for g in range(ndev):
+                torch.cuda.synchronize(g)
+            t = time.perf_counter() - t0
+            best = t if best is None else min(best, t)
+        moved = ndev * n * (2 if what == "both" else 1)
+        out[what + "_GBps"] = moved / best / 1e9
+    del bufs
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -229,9 +352,11 @@ def run_ours(args):
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
     _lib.call("mxg_set_device", local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that leave the other ranks' GPUs idle
 
     wl = dict(WORKLOADS[args.workload])
     if args.scale != 1.0:
@@ -253,12 +378,11 @@ def run_ours(args):
     op = wl["op"]
     At = None
     out_rows = K if op == "crossprod" else m
-    # N > 1: the products store every finished row into ALL ranks' results over NVLink (PeerResult), so the
-    # all-gather of north_star subsystem 4 is fused into the kernel; crossprod keeps the NCCL collective
-    # (column-major results, op csr_dense, keep the NCCL collective: peer stores of 128-byte column segments 200 MB
-    #  apart reach only ~130 GB/s — cfg5 sharded over 8 GPUs: fused 170 ms, product + NCCL all-gather 53.6 ms,
-    #  profiles/r01_v5_bench_cfg5_sharded_8gpu.json — so the fused kernel is used where it wins: row-major rows)
-    fused = world > 1 and op in ("spmv", "dense_tcsr")
+    # N > 1: the all-gather of north_star subsystem 4 is part of the step.  Row-major results (spmv, dense_tcsr): every
+    # finished row is stored into ALL ranks' results over NVLink by the product kernel (peer stores / NVLS multicast),
+    # or finished row slices are pushed by the copy engines (mxg_dev_spmm_push) — the fastest of those is the step.
+    # Column-major results (csr_dense, cfg5's shape): copy-engine pushes of 2-D blocks.  crossprod keeps NCCL.
+    fused = world > 1 and op in ("spmv", "dense_tcsr", "csr_dense")
     peer = None
     if op == "spmv":
         dense = torch.randn(K, device="cuda", dtype=torch.float64, generator=g)
@@ -266,6 +390,9 @@ def run_ours(args):
     elif op == "crossprod":
         dense = torch.randn(m, n, device="cuda", dtype=tdt, generator=g)  # Y rows-contiguous [m][n]
         shape_all, dt_all = (world * K, n), tdt
+    elif op == "csr_dense":
+        dense = torch.randn(K, n, device="cuda", dtype=tdt, generator=g)
+        shape_all, dt_all = (n, world * m), tdt  # ONE column-major (world*m x n) matrix, ldc = world*m
     else:
         dense = torch.randn(K, n, device="cuda", dtype=tdt, generator=g)  # (n x K) column-major R matrix
         shape_all, dt_all = (world * m, n), tdt
@@ -275,11 +402,13 @@ def run_ours(args):
         out_all = peer.tensor(shape_all, dt_all)
     else:
         out_all = torch.empty(shape_all, device="cuda", dtype=dt_all)
-    out_local = out_all[rank * out_rows:(rank + 1) * out_rows]
-    colmajor_tmp = None
     if op == "csr_dense":
-        # column-major (R layout) output block m x n, ldc = m  (N = 1, and the compute-only / NCCL variants)
-        colmajor_tmp = torch.empty(n, m, device="cuda", dtype=tdt)
+        out_local = out_all[:, rank * m:(rank + 1) * m] if world > 1 else out_all  # this rank's rows of every column
+    else:
+        out_local = out_all[rank * out_rows:(rank + 1) * out_rows]
+    colmajor_tmp = None
+    if op == "csr_dense" and world > 1:
+        colmajor_tmp = torch.empty(n, m, device="cuda", dtype=tdt)  # contiguous local block for the NCCL variant
     dst = ldc_all = None
     if fused:
         if op == "spmv":
@@ -289,38 +418,38 @@ def run_ours(args):
         else:  # one global column-major (world*m x n) matrix: this rank owns rows [rank*m, (rank+1)*m)
             dst, ldc_all = peer.dst_ptrs(rank * m * s), world * m
 
-    def compute():
+    def compute(local_cm=None):
         nonlocal At
         if op == "spmv":
             A.spmv(dense, out_local)
         elif op == "dense_tcsr":
             A.spmm(dense, out_local, n, mdt, MXG_ROWS_CONTIGUOUS)
         elif op == "csr_dense":
-            A.spmm(dense, colmajor_tmp, n, mdt, MXG_COLS_CONTIGUOUS)
+            if local_cm is not None:
+                A.spmm(dense, local_cm, n, mdt, MXG_COLS_CONTIGUOUS)
+            else:
+                A.spmm(dense, out_local, n, mdt, MXG_COLS_CONTIGUOUS, ldc=world * m)
         elif op == "crossprod":
             if At is not None:
                 At.free()
             At = A.transpose(keep=keep)
             At.spmm(dense, out_local, n, mdt, MXG_ROWS_CONTIGUOUS)
 
-    def step(with_gather=True):
-        if fused and with_gather:
-            if op == "spmv":
-                A.spmv_bcast(dense, dst)
-            else:
-                A.spmm_bcast(dense, dst, n, mdt, MXG_ROWS_CONTIGUOUS if op == "dense_tcsr" else MXG_COLS_CONTIGUOUS, ldc=ldc_all)
-            peer.barrier()  # device-side: every rank's rows have landed when the stream gets past this
-            return
-        compute()
-        if world > 1 and with_gather:
-            src = colmajor_tmp if op == "csr_dense" else out_local
-            dist.all_gather_into_tensor(out_all.view(-1), src.view(-1))
+    def step_peer():
+        if op == "spmv":
+            A.spmv_bcast(dense, dst)
+        else:
+            A.spmm_bcast(dense, dst, n, mdt, MXG_ROWS_CONTIGUOUS if op == "dense_tcsr" else MXG_COLS_CONTIGUOUS, ldc=ldc_all)
+        peer.barrier()  # device-side: every rank's rows have landed when the stream gets past this
 
-    def nccl_step():
-        # the unfused baseline: product into the local block, then one NCCL all-gather of the blocks
+    def step_push():
+        A.spmm_push(dense, dst, n, mdt, MXG_ROWS_CONTIGUOUS if op == "dense_tcsr" else MXG_COLS_CONTIGUOUS, ldc=ldc_all)
+        peer.barrier()
+
+    def step_plain():
         compute()
-        src = colmajor_tmp if op == "csr_dense" else out_local
-        dist.all_gather_into_tensor(nccl_all.view(-1), src.contiguous().view(-1))
+        if world > 1:
+            dist.all_gather_into_tensor(out_all.view(-1), out_local.contiguous().view(-1))
 
     def timed(fn, steps):
         if world > 1:
@@ -339,27 +468,35 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    # NVLS multicast variant of the fused all-gather (rows-contiguous results): every row is written once with
-    # multimem.st and replicated by the NVSwitch; used for the timed step when the box offers it and it is faster
-    step_fn, how_fused, ms_probe = step, "peer", {}
-    mres = None
-    if fused and op == "dense_tcsr" and args.allgather != "peer":
-        try:
-            from matrixextra_b200.sharded import McastResult
-            mres = McastResult(int(np.prod(shape_all)) * s, dist, rank, world)
-            mc_block = mres.mc_ptr(rank * m * n * s)
+    # candidates for the fused step; `--allgather auto` times each briefly and runs the step with the fastest
+    variants, ms_probe, mres = {}, {}, None
+    if fused:
+        if op != "csr_dense":
+            variants["peer"] = step_peer
+        if op != "spmv":
+            variants["push"] = step_push
+        if op == "dense_tcsr" and args.allgather in ("auto", "mcast"):
+            try:
+                from matrixextra_b200.sharded import McastResult
+                mres = McastResult(int(np.prod(shape_all)) * s, dist, rank, world)
+                mc_block = mres.mc_ptr(rank * m * n * s)
 
-            def step_mc():
-                A.spmm_mcast(dense, mc_block, n, mdt)
-                mres.barrier()
+                def step_mc():
+                    A.spmm_mcast(dense, mc_block, n, mdt)
+                    mres.barrier()
+                variants["mcast"] = step_mc
+            except Exception as e:  # noqa: BLE001  (no multicast support on this box)
+                ms_probe["mcast_unavailable"] = str(e)[:200]
+        if args.allgather != "auto" and args.allgather in variants:
+            variants = {args.allgather: variants[args.allgather]}
+        for name, fn in variants.items():
             for _ in range(3):
-                step_mc()
-                step()
-            ms_probe = {"mcast": timed(step_mc, 5) / 5, "peer": timed(step, 5) / 5}
-            if args.allgather == "mcast" or ms_probe["mcast"] < ms_probe["peer"]:
-                step_fn, how_fused = step_mc, "mcast"
-        except Exception as e:  # noqa: BLE001  (no multicast support: keep the peer-store kernel)
-            ms_probe = {"mcast_unavailable": str(e)[:200]}
+                fn()
+            ms_probe[name] = timed(fn, 5) / 5
+        how_fused = min(variants, key=lambda k: ms_probe[k])
+        step_fn = variants[how_fused]
+    else:
+        how_fused, step_fn = None, step_plain
     for _ in range(max(args.warmup, 3)):
         step_fn()
     sampler = ClockSampler(local_rank)
@@ -369,12 +506,36 @@ def run_ours(args):
     ms_total = timed(step_fn, args.steps)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms_compute = timed(lambda: step(False), args.steps) if world > 1 else ms_total
+    ms_compute = timed(compute, args.steps) if world > 1 else ms_total
     ms_nccl = None
+    bit_identical = None
     if fused:
-        nccl_all = torch.empty(shape_all, device="cuda", dtype=dt_all)
-        for _ in range(2):
-            nccl_step()
+        # the unfused baseline — product into a contiguous local block, then one NCCL all-gather — and the proof that
+        # the fused step left exactly those bytes on this rank (checked on every rank, AND-ed)
+        step_fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        nccl_all = torch.empty(int(np.prod(shape_all)), device="cuda", dtype=dt_all)
+
+        def nccl_step():
+            if op == "csr_dense":
+                compute(colmajor_tmp)
+                dist.all_gather_into_tensor(nccl_all, colmajor_tmp.view(-1))
+            else:
+                compute()
+                dist.all_gather_into_tensor(nccl_all, out_local.contiguous().view(-1))
+        nccl_step()
+        torch.cuda.synchronize()
+        if op == "csr_dense":  # NCCL gathered [world][n][m]; the fused step wrote [n][world*m]
+            same = torch.equal(out_all.view(n, world, m), nccl_all.view(world, n, m).permute(1, 0, 2))
+        else:
+            same = torch.equal(out_all.reshape(-1), nccl_all)
+        if how_fused == "mcast":
+            same = same and torch.equal(mres.tensor(shape_all, dt_all).reshape(-1), nccl_all)
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        bit_identical = bool(flag.item())
+        nccl_step()
         ms_nccl = timed(nccl_step, args.steps) / args.steps
         del nccl_all
         if peer.failed():
@@ -395,17 +556,19 @@ def run_ours(args):
         w_alg = w_alg_bytes(m, K, nnz, n, s)
     ms_kernel = ms_compute / args.steps
     achieved = w_alg / (ms_kernel * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload) if world == 1 else (None, None)
+    fused_text = {"mcast": "fused into the product kernel (NVLS multicast stores)",
+                  "peer": "fused into the product kernel (NVLink peer stores)",
+                  "push": "finished row slices pushed by the copy engines over NVLink while the next slice is computed",
+                  None: "by NCCL"}[how_fused]
 
     result = {
         "metric": "CSR x dense SpMM GFLOP/s (k=%d) & effective HBM GB/s" % n if op != "spmv" else "CSR SpMV GFLOP/s & effective HBM GB/s",
         "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": wl["dtype"], "data": "synthetic (device-generated, Philox4x32-10; SURVEY.md 8d)",
-        "config": {"workload": wl["desc"], "rows_per_gpu": m, "cols": K, "nnz_per_gpu": nnz, "n": n,
-                   "parallelism": (f"row-block shards x{world}, replicated dense operand, all-gather of the output row blocks "
-                                   + (("fused into the product kernel (NVLS multicast stores)" if how_fused == "mcast"
-                                       else "fused into the product kernel (NVLink peer stores)") if fused else "by NCCL"))
-                   if world > 1 else "single GPU",
+        "config": bench_config(wl, world, nnz),
+        "config_details": {"allgather": fused_text if world > 1 else None,
                    "l2_policy": ("operands (CSR %.0f MB + dense %.0f MB + out %.0f MB) " % (nnz * (4 + s) / 1e6, s * K * n / 1e6, s * out_rows * n / 1e6))
                    + ("exceed the 126 MB L2; no flush needed" if nnz * (4 + s) + s * K * n + s * out_rows * n > 2 * 126e6
                       else "FIT in the 126 MB L2: this is a warm-cache, launch-bound number (parity config, not the bench line)"),
@@ -413,15 +576,12 @@ def run_ours(args):
         "effective_GBps": achieved,
         "compute_only": {"value": flops_step / (ms_kernel * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms_kernel},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
-                     "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1] if world == 1 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": w_alg,
-                     # the binding roof: HBM on the ACTUAL traffic of the launch (ncu dram bytes), which is
-                     # ~10x the algorithmic bytes because the dense operand overflows L2 and its rows are re-fetched
-                     "actual_traffic_GBps": (NCU_TRAFFIC[args.workload][0] / ms_kernel / 1e6
-                                             if world == 1 and args.workload in NCU_TRAFFIC else None),
-                     "actual_traffic_frac_of_peak": (NCU_TRAFFIC[args.workload][0] / ms_kernel / 1e6 / peak
-                                                     if world == 1 and args.workload in NCU_TRAFFIC else None),
+                     # the binding roof: HBM on the ACTUAL traffic of the launch (ncu dram bytes), several
+                     # times the algorithmic bytes because the dense operand overflows L2 and its rows are re-fetched
+                     "actual_traffic_GBps": traffic / ms_kernel / 1e6 if traffic else None,
+                     "actual_traffic_frac_of_peak": traffic / ms_kernel / 1e6 / peak if traffic else None,
                      "gather_roofs": "random 256-byte rows, nothing attached (mxg_dev_gather_probe, profiles/"
                                      "r01_v5_gather_roof_probe.jsonl): 14.0 TB/s from L2, 9.0 TB/s on a 256 MB table, "
                                      "6.4 TB/s from DRAM",
@@ -430,141 +590,295 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if world > 1:
-        result["allgather"] = ({"how": ("fused, NVLS multicast: every finished row is written once with multimem.st by the "
-                                        "product kernel (mxg_dev_spmm_mcast) and replicated by the NVSwitch into all ranks' "
-                                        "results + symmetric-memory barrier" if how_fused == "mcast" else
-                                        "fused: every finished row is stored into all ranks' results over NVLink by the product "
-                                        "kernel (mxg_dev_spmm_bcast) + device-side flag barrier"),
-                                "variants_ms_per_step": ms_probe, "ms_per_step": ms_step,
-                                "nccl_after_compute_ms_per_step": ms_nccl, "bytes_received_per_gpu": int((world - 1) * out_rows * n * s)}
+        result["allgather"] = ({"how": fused_text, "variants_ms_per_step": ms_probe, "ms_per_step": ms_step,
+                                "nccl_after_compute_ms_per_step": ms_nccl, "bit_identical_to_nccl": bit_identical,
+                                "bytes_received_per_gpu": int((world - 1) * out_rows * n * s)}
                                if fused else {"how": "NCCL all_gather_into_tensor after the product", "ms_per_step": ms_step})
 
-    # ---- end to end through the reference-facing entry point with host buffers (rank-local) ----------
-    e2e = None
-    cpu = None
+    # ---- end to end through the reference-facing entry point with host buffers ------------------------
+    e2e = cpu = parity = None
+    nth_all = max(1, min(16, os.cpu_count() or 4))
     if not args.skip_e2e:
-        p_h, j_h, x_h = A.to_host()
-        # host staging threads of this rank (the exports' `nthreads`): the box's cores are shared by the ranks
-        nth = max(1, min(16, (os.cpu_count() or 4) // max(world, 1)))
-        # With several ranks calling at once the host's memory bandwidth, not the per-GPU PCIe links, bounds the
-        # calls, and narrowing on the host costs 20 instead of 12 bytes of host memory traffic per entry (measured:
-        # 8 ranks 127 ms per call with host narrowing, 100 ms without; 2 ranks 31.9 vs 30.2 ms): narrow on the device.
-        if world >= 2:
-            _lib.set_option("host_narrow", 0)
-        np_t = np.float32 if f32 else np.float64
-        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
-        p_h, j_h, x_h = pin(p_h), pin(j_h), pin(x_h)
-        def pinned_out(shape, dt):
-            return torch.empty(int(np.prod(shape)), dtype=dt).pin_memory().numpy().reshape(shape, order="F")
-
-        if op == "spmv":
-            d_h = pin(dense.cpu().numpy())
-            o_h = pinned_out((m,), torch.float64)
-            call = lambda out=o_h: rx.matmul_csr_dvec_numeric(p_h, j_h, x_h, d_h, nth, out=out)  # noqa: E731
-            h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
-            d2h = 8 * m
-        elif op == "crossprod":
-            d_h = pin(np.asfortranarray(dense.cpu().numpy()))  # Y (m x n) column-major
-            o_h = None
-            call = lambda out=None: rx.crossprod_csr_dense(p_h, j_h, x_h, K, d_h, mdt)  # noqa: E731
-            h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
-            d2h = s * K * n
+        p_h, j_h, x_h = A.to_host()  # ordinary (pageable) numpy arrays: what an R session holds
+        if op == "crossprod":
+            d_h = np.asfortranarray(dense.cpu().numpy().T)  # t(Y): n x m column-major, the CPU route's operand
+        elif op == "spmv":
+            d_h = dense.cpu().numpy()
         else:
-            d_h = torch.from_numpy(dense.cpu().numpy()).pin_memory().numpy().T  # (n x K) F-order view, pinned
-            fn = {("dense_tcsr", True): rx.tcrossprod_dense_csr_float32, ("dense_tcsr", False): rx.tcrossprod_dense_csr_numeric,
-                  ("csr_dense", True): rx.tcrossprod_csr_dense_float32, ("csr_dense", False): rx.tcrossprod_csr_dense_numeric}[(op, f32)]
-            if op == "dense_tcsr":
-                o_h = pinned_out((n, m), tdt)
-                call = lambda out=o_h: fn(d_h, p_h, j_h, x_h, nth, K, out=out)  # noqa: E731
-            else:
-                o_h = pinned_out((m, n), tdt)
-                call = lambda out=o_h: fn(p_h, j_h, x_h, d_h, nth, out=out)  # noqa: E731
-            h2d = p_h.nbytes + j_h.nbytes + x_h.nbytes + d_h.nbytes
-            d2h = s * m * n
-        call()  # warm-up (allocator pools)
-        k_e2e = max(1, min(args.steps, 5))
+            d_h = np.ascontiguousarray(dense.cpu().numpy()).T  # (n x K) column-major view of the K x n row-major copy
+    if peer is not None:
+        del out_all, out_local
+        peer.close(dist)
+        peer = None
+    if mres is not None:
+        del mres
+    A.free()
+    del dense
+    torch.cuda.empty_cache()
 
-        def time_calls(f, k):
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            for _ in range(k):
-                r = f()
-            t = (time.perf_counter() - t0) / k
-            if world > 1:
-                tt = torch.tensor([t], device="cuda", dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                t = float(tt.item())
-            return t, r
-
-        t_e2e, res = time_calls(call, k_e2e)
-        import ctypes as _C
-        h2d_lib, d2h_lib = _C.c_size_t(0), _C.c_size_t(0)
-        _lib.call("mxg_last_call_bytes", _C.byref(h2d_lib), _C.byref(d2h_lib))  # the last timed call, copy by copy
-        # same call the way R makes it: the result is a freshly allocated (pageable, untouched) matrix
-        call(out=None)  # warm-up: the page-locked arena grows by the output slots once
-        t_fresh, res = time_calls(lambda: call(out=None), 3)
-        # bytes that cross PCIe: a float32 product narrows the float64 values on the host (hoststage.cu)
-        host_narrow = f32 and op != "crossprod" and _lib.get_option("host_narrow") != 0 and _lib.get_option("pipeline") != 0
-        if host_narrow:
-            h2d -= x_h.nbytes // 2
-        # ... and column ids travel packed (2 / 2.5 / 3 bytes per entry) in the chunks where the link, not the host
-        # threads, is the bottleneck (pipeline.cu upload_chunk): take the library's own count of what it copied
-        host_pack = False
-        if h2d_lib.value > 0:
-            host_pack = h2d_lib.value < h2d - 1024
-            h2d, d2h = h2d_lib.value, d2h_lib.value
-        e2e = {"value": 2.0 * nnz_all * n / t_e2e / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "ms_per_step": t_e2e * 1e3,
-               "entry_point": "level-1 C ABI (streamed row chunks) via the Rcpp-export mirror; pinned host inputs, "
-                              "result into a page-locked host buffer"
-                              + ("; float64 values narrowed to float32 by the library's host threads before the copy "
-                                 "(h2d bytes counted after narrowing)" if host_narrow else "")
-                              + ("; column ids of the chunks uploaded while the link was the bottleneck packed to 2-3 "
-                                 "bytes per entry by the same threads and rebuilt on the device" if host_pack else "")
-                              + ("; bytes are the library's count of its copies in the last timed call" if h2d_lib.value else ""),
-               "host_threads": nth,
-               "fresh_pageable_result": {"value": 2.0 * nnz_all * n / t_fresh / 1e9, "ms_per_step": t_fresh * 1e3,
-                                         "note": "same call returning a newly allocated pageable matrix, as the Rcpp glue does"}}
-        if op not in ("crossprod",) and world == 1:
-            # everything pageable, as in an R session: operands are ordinary (non page-locked) arrays, the result is new
-            pg = lambda a: np.array(a, copy=True, order="K")  # noqa: E731
-            p_g, j_g, x_g, d_g = pg(p_h), pg(j_h), pg(x_h), pg(d_h)
-            if op == "spmv":
-                call_pg = lambda: rx.matmul_csr_dvec_numeric(p_g, j_g, x_g, d_g, nth)  # noqa: E731
-            elif op == "dense_tcsr":
-                call_pg = lambda: fn(d_g, p_g, j_g, x_g, nth, K)  # noqa: E731
-            else:
-                call_pg = lambda: fn(p_g, j_g, x_g, d_g, nth)  # noqa: E731
-            call_pg()
-            t_pg, res = time_calls(call_pg, 3)
-            e2e["all_pageable"] = {"value": 2.0 * nnz_all * n / t_pg / 1e9, "ms_per_step": t_pg * 1e3,
-                                   "note": "operands AND result in pageable memory (an R session): bounced through the "
-                                           "library's page-locked ring by its host threads"}
-            del p_g, j_g, x_g, d_g
-        del res
-        if rank == 0 and world == 1 and not args.skip_cpu:
-            cpu = cpu_baseline(wl, p_h, j_h, x_h)
+    if not args.skip_e2e and world == 1:
+        e2e, parity, cpu = e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth_all)
+    elif not args.skip_e2e:
+        e2e, parity = e2e_multi(args, wl, rx, _lib, dist, cpu_group, rank, world, p_h, j_h, x_h, d_h, nth_all)
     result["e2e"] = e2e
     result["cpu_baseline"] = cpu
+    result["parity"] = parity
+
+    if world > 1 and not args.skip_strong:
+        result["strong_cfg5"] = strong_cfg5(args, dist, rank, world)
 
     if rank == 0 and world == 1 and args.others:
         result["others"] = {}
-        A.free()
-        del dense, out_all
-        torch.cuda.empty_cache()
         for name in args.others.split(","):
             if name and name != args.workload:
                 result["others"][name] = quick_kernel_bench(name, args)
 
-    if peer is not None:
-        del out_all, out_local
-        peer.close(dist)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(result))
+
+
+def _pinned(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
+    """N = 1.  Headline: the call an R session makes — every operand in ordinary pageable memory, a new result matrix
+    per call.  Sub-keys: the same call with page-locked buffers, with a device-resident matrix (explicit handle and
+    level-1 cache), and the cpu_baseline / parity of the same product."""
+    import torch
+    op, n, K = wl["op"], wl["n"], wl["K"]
+    m = p_h.size - 1
+    f32 = wl["dtype"] == "f32"
+    flops = 2.0 * nnz_all * n
+    k_e2e = max(1, min(args.steps, 5))
+
+    def rec(t, up_down=None, **kw):
+        out = {"value": flops / t / 1e9, "ms_per_step": t * 1e3}
+        if up_down:
+            out["h2d_bytes_per_step"], out["d2h_bytes_per_step"] = up_down
+        out.update(kw)
+        return out
+
+    call_pg = lambda: gpu_level1(rx, wl, p_h, j_h, x_h, d_h, nth)  # noqa: E731
+    call_pg()  # warm-up: allocator pools, page-locked arena
+    call_pg()
+    t_pg, res = _wall(call_pg, k_e2e)
+    bytes_pg = _lib_bytes(_lib)
+    e2e = {"value": flops / t_pg / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": bytes_pg[0], "d2h_bytes_per_step": bytes_pg[1],
+           "steps": k_e2e, "ms_per_step": t_pg * 1e3, "host_threads": nth,
+           "entry_point": "level-1 C ABI (streamed row chunks) via the Rcpp-export mirror, called the way an R session "
+                          "calls it: CSR, dense operand and the freshly allocated result all in PAGEABLE host memory, bounced "
+                          "through the library's page-locked ring by its host threads; bytes are the library's own count of "
+                          "the copies of the last timed call (float32 values after host narrowing, packed column ids)"}
+    del res
+    if op != "crossprod":
+        # page-locked operands and a reused page-locked result (what the contract's e2e describes; R cannot do this)
+        p_p, j_p, x_p = _pinned(p_h), _pinned(j_h), _pinned(x_h)
+        if op == "spmv":
+            d_p, o_p = _pinned(d_h), _pinned(np.empty(m))
+        else:
+            d_p = _pinned(d_h.T).T
+            shape = (n, m) if op == "dense_tcsr" else (m, n)
+            o_p = _pinned(np.empty(int(np.prod(shape)), dtype=d_h.dtype)).reshape(shape, order="F")
+        call_pin = lambda: gpu_level1(rx, wl, p_p, j_p, x_p, d_p, nth, out=o_p)  # noqa: E731
+        call_pin()
+        t_pin, _ = _wall(call_pin, k_e2e)
+        e2e["pinned"] = rec(t_pin, _lib_bytes(_lib), note="page-locked operands and a reused page-locked result buffer (DMA in place)")
+        call_fresh = lambda: gpu_level1(rx, wl, p_p, j_p, x_p, d_p, nth)  # noqa: E731
+        call_fresh()
+        t_fresh, _ = _wall(call_fresh, 3)
+        e2e["fresh_pageable_result"] = rec(t_fresh, note="page-locked operands, newly allocated pageable result")
+        del p_p, j_p, x_p, o_p
+    if op in ("dense_tcsr", "csr_dense", "spmv"):
+        # SURVEY.md 8 f1: the matrix stays in HBM between calls; a product moves the dense operand up and the result down
+        h = rx.as_gpu_csr(p_h, j_h, x_h, K, keep_float64=not f32 or op == "spmv", keep_float32=f32 and op != "spmv")
+        if op == "spmv":
+            warm = lambda d=d_h: rx.gpu_csr_dvec_numeric(h, d, nth)  # noqa: E731
+        elif op == "dense_tcsr":
+            fn = rx.gpu_csr_dense_tcrossprod_float32 if f32 else rx.gpu_csr_dense_tcrossprod_numeric
+            warm = lambda d=d_h: fn(d, h, nth)  # noqa: E731
+        else:
+            fn = rx.gpu_csr_tcrossprod_dense_float32 if f32 else rx.gpu_csr_tcrossprod_dense_numeric
+            warm = lambda d=d_h: fn(h, d, nth)  # noqa: E731
+        warm()
+        t_w, res_w = _wall(warm, k_e2e)
+        e2e["warm_handle"] = rec(t_w, _lib_bytes(_lib), bit_identical_to_level1=bool(np.array_equal(res_w, call_pg())),
+                                 note="explicit device-resident matrix (as_gpu_csr + gpu_csr_* exports, rglue/handle_gpu_glue.cpp); "
+                                      "pageable dense operand and result: only they cross PCIe")
+        if op != "spmv":  # page-locked dense operand AND result: the PCIe bound of the warm path (R cannot do this)
+            o_w = _pinned(np.empty(res_w.size, dtype=res_w.dtype)).reshape(res_w.shape, order="F")
+            t_wp, _ = _wall(lambda: (fn(d_p, h, nth, out=o_w) if op == "dense_tcsr" else fn(h, d_p, nth, out=o_w)), k_e2e)
+            e2e["warm_handle"]["pinned"] = rec(t_wp, _lib_bytes(_lib), note="page-locked dense operand and result buffer")
+            del o_w
+        rx.gpu_csr_free(h)
+        del res_w
+        # the same through the unchanged ten exports with the level-1 operand cache on (MATRIXEXTRA_GPU_CACHE_MB)
+        _lib.set_option("cache_mb", 8192)
+        call_pg()
+        call_pg()
+        t_c, _ = _wall(call_pg, k_e2e)
+        e2e["cached_level1"] = rec(t_c, _lib_bytes(_lib), note="option cache_mb on: the device CSR (and the dense operand) of "
+                                   "the previous call on the same host arrays is reused; unchanged level-1 exports")
+        _lib.set_option("cache_mb", 0)
+        _lib.call("mxg_cache_clear")
+    cpu = parity = None
+    if not args.skip_cpu:
+        cpu, parity = cpu_baseline(wl, p_h, j_h, x_h, d_h, rx=rx)
+    return e2e, parity, cpu
+
+
+def e2e_multi(args, wl, rx, _lib, dist, cpu_group, rank, world, p_h, j_h, x_h, d_h, nth):
+    """N > 1.  The reference parallelises inside ONE process (src/matmul.cpp:132-136) and an R session is one process:
+    rank 0 makes ONE level-1 call on ONE workload matrix spread over all N GPUs of the box (mxg_set_devices(N): N host
+    threads, N streamed pipelines, each device uploading its row block over its own PCIe link) while the other ranks
+    wait on the host.  Strong scaling: the same call on one device is timed next to it."""
+    op, n = wl["op"], wl["n"]
+    flops = 2.0 * int(p_h[-1]) * n
+    e2e = parity = None
+    dist.barrier(group=cpu_group)
+    if rank == 0 and op != "crossprod":
+        k = max(1, min(args.steps, 5))
+        out = {}
+        call = lambda: gpu_level1(rx, wl, p_h, j_h, x_h, d_h, nth)  # noqa: E731
+        p_p, j_p, x_p = _pinned(p_h), _pinned(j_h), _pinned(x_h)
+        d_p = _pinned(d_h) if op == "spmv" else _pinned(d_h.T).T
+        shape = (p_h.size - 1,) if op == "spmv" else ((n, p_h.size - 1) if op == "dense_tcsr" else (p_h.size - 1, n))
+        o_p = _pinned(np.empty(int(np.prod(shape)), dtype=np.float64 if op == "spmv" else d_h.dtype)).reshape(shape, order="F")
+        call_pin = lambda: gpu_level1(rx, wl, p_p, j_p, x_p, d_p, nth, out=o_p)  # noqa: E731
+        ref_res = None
+        for G in (1, world):
+            _lib.call("mxg_set_devices", G)
+            call()
+            call()
+            t_pg, res = _wall(call, k)
+            b_pg = _lib_bytes(_lib)
+            call_pin()
+            t_pin, _ = _wall(call_pin, k)
+            b_pin = _lib_bytes(_lib)
+            if G == 1:
+                ref_res = res
+            out[G] = {"pageable_ms": t_pg * 1e3, "pageable_GFLOPs": flops / t_pg / 1e9, "pageable_bytes": b_pg,
+                      "pinned_ms": t_pin * 1e3, "pinned_GFLOPs": flops / t_pin / 1e9, "pinned_bytes": b_pin,
+                      "bit_identical_to_one_device": bool(np.array_equal(res, ref_res))}
+        roof = host_dma_roof(world)
+        moved = sum(out[world]["pinned_bytes"])
+        e2e = {"value": out[world]["pageable_GFLOPs"], "unit": "GFLOP/s", "ms_per_step": out[world]["pageable_ms"],
+               "h2d_bytes_per_step": out[world]["pageable_bytes"][0], "d2h_bytes_per_step": out[world]["pageable_bytes"][1],
+               "steps": k, "scaling": "strong", "host_threads": nth, "devices": world,
+               "entry_point": f"ONE level-1 call (Rcpp-export mirror) by ONE process on ONE workload matrix, spread over {world} GPUs by "
+                              f"mxg_set_devices({world}): nnz-balanced row blocks, one host thread + one streamed pipeline per device, "
+                              "the dense operand uploaded once (a slice per device) and completed over NVLink; pageable operands and "
+                              "a new pageable result per call, as in an R session",
+               "pinned": {"value": out[world]["pinned_GFLOPs"], "ms_per_step": out[world]["pinned_ms"],
+                          "h2d_bytes_per_step": out[world]["pinned_bytes"][0], "d2h_bytes_per_step": out[world]["pinned_bytes"][1]},
+               "one_device_same_box": {"pageable_ms": out[1]["pageable_ms"], "pinned_ms": out[1]["pinned_ms"]},
+               "speedup_vs_one_device": {"pageable": out[1]["pageable_ms"] / out[world]["pageable_ms"],
+                                         "pinned": out[1]["pinned_ms"] / out[world]["pinned_ms"]},
+               "bit_identical_to_one_device": out[world]["bit_identical_to_one_device"],
+               "host_roof": dict(roof, note=f"page-locked host <-> device copies on all {world} GPUs at once (plain cudaMemcpyAsync, "
+                                            "both directions together): what this host's memory system and PCIe tree deliver to "
+                                            f"{world} devices, whatever moves the bytes",
+                                 pinned_call_ms_at_roof=moved / roof["both_GBps"] / 1e6)}
+        _lib.call("mxg_set_devices", 1)
+        if not args.skip_cpu:
+            # parity of the multi-device call against the reference on a bounded row sample of the same matrix
+            _lib.call("mxg_set_devices", world)
+            _lib.set_option("multi_min_nnz", 1 << 16)
+            _, parity = cpu_baseline(wl, p_h, j_h, x_h, d_h, budget_s=6.0, rx=rx)
+            parity["against"] += f" (spread over {world} devices)"
+            _lib.call("mxg_set_devices", 1)
+            _lib.set_option("multi_min_nnz", 4 << 20)
+    dist.barrier(group=cpu_group)
+    return e2e, parity
+
+
+def strong_cfg5(args, dist, rank, world):
+    """BASELINE.json configs[4]: CSR 50M x 10M, 2B nnz %*% dense 10M x 128 fp32, ROW-SHARDED over the N GPUs (strong
+    scaling: rows/N and nnz/N per GPU), replicated dense operand, column-major (R layout) result all-gathered to every
+    GPU.  The reference cannot run this shape at all: its `int` strides overflow (src/matmul.cpp:35-39, 156, 182)."""
+    import torch
+    from matrixextra_b200._lib import MXG_COLS_CONTIGUOUS, MXG_F32, MXG_KEEP_F32
+    from matrixextra_b200.device import DeviceCSR
+    from matrixextra_b200.sharded import PeerResult
+    wl = WORKLOADS["cfg5"]
+    sc = args.strong_scale
+    mg, K, n = int(wl["m"] * sc) // world, wl["K"], wl["n"]
+    nnz_g = int(wl["nnz"] * sc) // world
+    free, _ = torch.cuda.mem_get_info()
+    need = 8 * nnz_g + 4 * K * n + 2 * 4 * world * mg * n + 4 * mg * n + (4 << 30)
+    if free < need:
+        return {"skipped": f"needs {need / 1e9:.0f} GB per GPU, {free / 1e9:.0f} GB free"}
+    A = DeviceCSR.synth(mg, K, nnz_g, wl["row_model"], wl["col_model"], seed=wl["seed"] + 7919 * rank, keep=MXG_KEEP_F32)
+    g = torch.Generator(device="cuda").manual_seed(4242)
+    dense = torch.randn(K, n, device="cuda", dtype=torch.float32, generator=g)
+    peer = PeerResult(4 * world * mg * n, dist, rank, world)
+    out_all = peer.tensor((n, world * mg), torch.float32)
+    dst, ldc = peer.dst_ptrs(rank * mg * 4), world * mg
+
+    def timed(fn, steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step():
+        A.spmm_push(dense, dst, n, MXG_F32, MXG_COLS_CONTIGUOUS, ldc=ldc)
+        peer.barrier()
+
+    def compute():
+        A.spmm(dense, out_all[:, rank * mg:(rank + 1) * mg], n, MXG_F32, MXG_COLS_CONTIGUOUS, ldc=ldc)
+
+    local = torch.empty(n, mg, device="cuda", dtype=torch.float32)
+    nccl_all = torch.empty(world * n * mg, device="cuda", dtype=torch.float32)
+
+    def nccl_step():
+        A.spmm(dense, local, n, MXG_F32, MXG_COLS_CONTIGUOUS)
+        dist.all_gather_into_tensor(nccl_all, local.view(-1))
+
+    for _ in range(2):
+        step()
+    steps = 3
+    ms_step = timed(step, steps)
+    ms_compute = timed(compute, steps)
+    step()
+    nccl_step()
+    torch.cuda.synchronize()
+    same = torch.equal(out_all.view(n, world, mg), nccl_all.view(world, n, mg).permute(1, 0, 2))
+    flag = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ms_nccl = timed(nccl_step, steps)
+    t = torch.tensor([A.nnz], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t)
+    nnz_all = int(t.item())
+    failed = peer.failed()
+    del out_all
+    peer.close(dist)
+    A.free()
+    one_gpu_ms = 163.0 * sc
+    return {"workload": wl["desc"] + f" row-sharded over {world} GPUs" + ("" if sc == 1.0 else f" (scaled x{sc})"),
+            "scaling": "strong", "rows_per_gpu": mg, "nnz_total": nnz_all, "steps": steps,
+            "ms_per_step": ms_step, "GFLOPs": 2.0 * nnz_all * n / ms_step / 1e6,
+            "compute_only_ms": ms_compute, "nccl_after_compute_ms": ms_nccl,
+            "how": "product in ~16 row slices per GPU into the global column-major result; every finished slice pushed to the "
+                   "other GPUs as a 2-D block (n column segments) by the copy engines over NVLink while the next slice is "
+                   "computed (mxg_dev_spmm_push) + device-side flag barrier",
+            "bit_identical_to_nccl": bool(flag.item()) and not failed,
+            "bytes_received_per_gpu": int(4 * (world - 1) * mg * n),
+            "ingress_GBps": 4 * (world - 1) * mg * n / ms_step / 1e6,
+            "one_gpu_ms": one_gpu_ms, "one_gpu_source": "163 ms for the whole of cfg5 on one B200 (profiles/r01_v6_bench_cfg5_kernel_only.json; "
+                                                       "`--workload cfg5` re-measures it)",
+            "speedup_vs_one_gpu": one_gpu_ms / ms_step, "efficiency": one_gpu_ms / ms_step / world}
 
 
 def quick_kernel_bench(name, args):
@@ -608,7 +922,7 @@ def quick_kernel_bench(name, args):
             t.free()
         ms_t = _time_ms(tr, 3, 2)
         extra = {"transpose_ms": ms_t, "transpose_GBps": (24 * A.nnz + 4 * (m + K + 2)) / ms_t / 1e6}
-    ms = _time_ms(fn, args.steps, 3)
+    ms = _time_ms(fn, min(args.steps, 20) if name == "cfg5" else args.steps, 3)
     nnz = A.nnz
     w = w_alg_bytes(K if op == "crossprod" else m, m if op == "crossprod" else K, nnz, n, s)
     peak, _ = measured_peaks()
@@ -616,6 +930,8 @@ def quick_kernel_bench(name, args):
              "effective_GBps": w / ms / 1e6, "roofline_frac": w / ms / 1e6 / peak, "nnz": nnz}
     out_d.update(extra)
     A.free()
+    del dense, out
+    torch.cuda.empty_cache()
     return out_d
 
 
@@ -637,52 +953,49 @@ def _time_ms(fn, steps, warmup):
 # reference arm: the reference's own CPU implementation on this box's host cores
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference's src/matmul.cpp (oracle/_ref, all host threads) on the FULL workload matrix — the same shape, nnz,
+    row / column laws, RNG and counters as the GPU arm's device-generated matrix, produced on the host by the oracle's
+    twin of the generator (oracle/mx_synth.c).  Loads nothing of the product (no libmxgpu.so, no CUDA)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.cpu_oracle import best_cpu_baseline
+    from oracle.cpu_oracle import best_cpu_baseline, synth_csr_host
     wl = dict(WORKLOADS[args.workload])
+    if args.scale != 1.0:
+        wl["m"] = max(64, int(wl["m"] * args.scale))
+        wl["nnz"] = max(64, int(wl["nnz"] * args.scale))
     cpu = best_cpu_baseline()
     cpu.copy_result = False
     nthreads = host_cores()  # passed to the reference's `num_threads(nthreads)` clause
-    # bounded sample of the same workload: the first rows of the same synthetic matrix when a GPU is there to
-    # generate it, else a host-generated matrix with the same row-length law
-    m_s = max(1, wl["m"] // 8)
-    nnz_s = max(1, wl["nnz"] // 8)
-    p = j = x = None
-    try:
-        import torch
-        if torch.cuda.is_available():
-            from matrixextra_b200._lib import MXG_KEEP_F64
-            from matrixextra_b200.device import DeviceCSR
-            A = DeviceCSR.synth(m_s, wl["K"], nnz_s, wl["row_model"], wl["col_model"], seed=wl["seed"], keep=MXG_KEEP_F64)
-            p, j, x = A.to_host()
-            A.free()
-    except Exception:
-        p = None
-    if p is None:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import powerlaw_csr
-        m_s = min(m_s, 100_000)
-        p, j, x = powerlaw_csr(m_s, wl["K"], wl["nnz"] / wl["m"], 1, cap=min(wl["K"], 65536))
+    if wl["nnz"] > 400_000_000:
+        raise SystemExit("the reference cannot run this shape (int strides, src/matmul.cpp:35-39); use cfg1..cfg4")
+    p, j, x = synth_csr_host(wl["m"], wl["K"], wl["nnz"], wl["row_model"], wl["col_model"], wl["seed"])
     rng = np.random.default_rng(99)
     dense = cpu_dense_operand(wl, p.size - 1, rng)
-    for _ in range(max(1, min(args.warmup, 1))):
+    warm = max(1, args.warmup)
+    t_one, _ = cpu_run(cpu, wl, p, j, x, dense, nthreads)
+    # every requested step is timed unless that would take more than ~3 minutes on this host
+    steps = max(1, min(args.steps, int(150.0 / max(t_one, 1e-3))))
+    warm = max(1, min(warm, int(30.0 / max(t_one, 1e-3))))
+    for _ in range(warm - 1):
         cpu_run(cpu, wl, p, j, x, dense, nthreads)
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
         cpu_run(cpu, wl, p, j, x, dense, nthreads)
     sec = (time.perf_counter() - t0) / steps
     nnz = int(p[-1])
     value = 2.0 * nnz * wl["n"] / sec / 1e9
-    sample = (f"rows 0..{p.size - 2} of the workload matrix generator ({nnz} nnz, 1/8 of one GPU's block), "
-              f"{steps} timed passes; build: {cpu.flags}")
+    sample = (f"all {p.size - 1} rows of the workload matrix ({nnz} nnz; host twin of the device generator, same seed), "
+              f"{steps} timed passes after {warm} warm-up; build: {cpu.flags}")
     print(json.dumps({
-        "impl": "reference", "metric": "CSR x dense SpMM GFLOP/s (k=%d) & effective HBM GB/s" % wl["n"], "value": value,
-        "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3,
+        "impl": "reference", "metric": ("CSR x dense SpMM GFLOP/s (k=%d) & effective HBM GB/s" % wl["n"]) if wl["op"] != "spmv"
+        else "CSR SpMV GFLOP/s & effective HBM GB/s", "value": value,
+        "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"],
-        "data": "synthetic", "config": {"workload": wl["desc"], "sampled_rows": int(p.size - 1), "sampled_nnz": nnz},
+        "data": "synthetic (host-generated by the oracle's twin of the device generator, Philox4x32-10; SURVEY.md 8d)",
+        "config": bench_config(wl, args.gpus, nnz),
+        "config_details": {"cpu_arm": f"one row block of the workload on the host: {nthreads} OpenMP threads, schedule(dynamic) as "
+                                      "written (src/matmul.cpp:132-136)"},
         "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": nthreads, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -696,11 +1009,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/nnz (debugging only; invalid as a bench value)")
-    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer"],
-                    help="fused all-gather of row-major results at N > 1: NVLS multicast stores, peer stores, or the faster")
+    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer", "push"],
+                    help="all-gather of the step at N > 1: NVLS multicast stores / peer stores from the product kernel, "
+                         "copy-engine pushes of finished row slices, or the fastest of them")
     ap.add_argument("--others", default="cfg2,k64f64,cfg4", help="extra kernel-only configs reported at N=1 ('' to skip)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-strong", action="store_true", help="N > 1: skip the row-sharded cfg5 record")
+    ap.add_argument("--strong-scale", type=float, default=1.0, help="shrink cfg5 for the strong-scaling record (debugging)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) is sent to
     # stderr by pointing fd 1 at fd 2 for the duration of the run; print() below writes to the saved descriptor

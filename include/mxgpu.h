@@ -92,14 +92,15 @@ int mxg_get_devices(int *n);
  *             entries per chunk, 0 = auto), "pipe_slots" (ring slots, 4), "h2d_chunk_mb";
  *   host staging (csrc/hoststage.cu) : "host_threads" (threads that narrow / bounce host memory; the Rcpp exports'
  *             `nthreads`; 0 = all logical CPUs up to 16), "host_narrow" (float32 products narrow the float64 values on
- *             the host before the copy, 1), "host_stage" (pageable caller memory goes through the page-locked ring, 1),
+ *             the host before the copy: 1 = yes, except in multi-device calls fed from page-locked arrays, 2 = always), "host_stage" (pageable caller memory goes through the page-locked ring, 1),
  *             "host_pack" (streamed calls of >= 2^20 entries whose host threads are not narrowing values send, while
  *             the upload stream lags behind them, column ids as 2 / 2.5 / 3 bytes per entry when the matrix has <= 2^16 /
  *             2^20 / 2^24 columns: packed by the host threads, rebuilt on the device, 1; 2 = always, 3 = two chunks
  *             out of three: test modes), "host_pack_lag" (a chunk is packed while the upload of the chunk this many
  *             places before it is still pending, 2),
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
- *             copies are used);
+ *             copies are used), "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
+ *             freshly allocated R matrix is otherwise filled at page-fault speed, 1);
  *   several devices : "multi_min_nnz" (level-1 calls below this many stored entries stay on one device, 4 Mi),
  *             "multi_dense_share" (1 = each device uploads one slice of the dense operand and pulls the rest over NVLink,
  *             0 = every device uploads all of it);
@@ -278,6 +279,15 @@ int mxg_dev_mul_csr_dvec(mxg_csr_t A, const double *d_dvec, size_t len, double *
 int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
                        int n_dst, void *const *d_outs, size_t ldc, void *stream);
 int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream);
+
+/* The same product + all-gather with the COPY ENGINES: the product runs in about 16 row slices of equal nnz into
+ * d_outs[0] and every finished slice is pushed to the other n_dst - 1 destinations by DMA (peer copies over NVLink;
+ * 2-D copies for column-major results, whose blocks are n strided column segments) on the library's copy streams
+ * while the next slice is computed; `stream` continues once every push has landed locally-ordered (close the step
+ * with mxg_dev_peer_barrier).  Bulk transfers instead of 128-byte SM stores: the way to gather column-major results
+ * (BASELINE cfg5) and the faster one for large row-major blocks. */
+int mxg_dev_spmm_push(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb,
+                      int n_dst, void *const *d_outs, size_t ldc, void *stream);
 
 /* The same fused product + all-gather through NVLS MULTICAST: mc_out is this block's first row inside a multicast
  * mapping of the full result (cuMulticast* / torch.distributed._symmetric_memory: one virtual address bound to the

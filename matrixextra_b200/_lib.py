@@ -66,6 +66,7 @@ _SIGNATURES = {
     "mxg_dev_spmm": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_spmv": [_vp, _i32, _vp, _vp, _vp],
     "mxg_dev_spmm_bcast": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
+    "mxg_dev_spmm_push": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
     "mxg_dev_spmv_bcast": [_vp, _i32, _vp, _i32, _vp, _vp],
     "mxg_dev_spmm_mcast": [_vp, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_alloc": [_sz, C.POINTER(_vp)],

@@ -455,6 +455,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "multi_min_nnz")) return &o.multi_min_nnz;
     if (!strcmp(name, "multi_dense_share")) return &o.multi_dense_share;
     if (!strcmp(name, "cache_mb")) return &o.cache_mb;
+    if (!strcmp(name, "host_thp")) return &o.host_thp;
     return nullptr;
 }
 
@@ -659,6 +660,65 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
     if (!A) return fail(MXG_ERR_ARG, "dev_spmm_bcast: NULL handle");
     if (b_layout != MXG_ROWS_CONTIGUOUS) return fail(MXG_ERR_UNSUPPORTED, "dev_spmm_bcast: the dense operand must be rows-contiguous");
     return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, static_cast<cudaStream_t>(stream));
+}
+
+/* Product + all-gather with the copy engines: the product runs in row slices (about 16 of equal nnz) into d_outs[0];
+ * every finished slice is pushed to the other destinations by DMA (peer copies over NVLink, 2-D for column-major
+ * results) on the library's three copy streams while the next slice is being computed.  SM stores to peers carry
+ * 128-byte requests (~550 GB/s into a B200); the copy engines move the same bytes in bulk. */
+int mxg_dev_spmm_push(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, const void *d_B, size_t ldb, int n_dst,
+                      void *const *d_outs, size_t ldc, void *stream)
+{
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmm_push: NULL handle");
+    if (b_layout != MXG_ROWS_CONTIGUOUS) return fail(MXG_ERR_UNSUPPORTED, "dev_spmm_push: the dense operand must be rows-contiguous");
+    if (n_dst < 1 || n_dst > MXG_MAX_DST || !d_outs) return fail(MXG_ERR_ARG, "dev_spmm_push: 1 .. %d destinations", MXG_MAX_DST);
+    if (dtype != MXG_F64 && dtype != MXG_F32) return fail(MXG_ERR_ARG, "bad dtype %d", dtype);
+    if (out_layout != MXG_ROWS_CONTIGUOUS && out_layout != MXG_COLS_CONTIGUOUS) return fail(MXG_ERR_ARG, "bad out_layout %d", out_layout);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (A->m == 0 || n <= 0) return MXG_OK;
+    const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
+    if (rm ? ldc < (size_t)n : ldc < (size_t)A->m) return fail(MXG_ERR_ARG, "dev_spmm_push: ldc too small");
+    DeviceState *st;
+    MXG_TRY(current_state(&st));
+    if (A->nnz == 0 || n_dst == 1) { // nothing to overlap: one launch (a zero fill for an empty matrix) per destination list
+        MXG_TRY(launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, s));
+        return MXG_OK;
+    }
+    MXG_TRY(handle_chunks(A, s));
+    const std::vector<int32_t> &cr = *A->host_chunks;
+    const int C = (int)cr.size() - 1;
+    const size_t es = dtype == MXG_F64 ? 8 : 4;
+    cudaStream_t copy[3] = {st->p2p, st->h2d, st->d2h};
+    while ((int)st->ev_pool.size() < C + 4) {
+        cudaEvent_t e;
+        MXG_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        st->ev_pool.push_back(e);
+    }
+    // long rows first: their rows are written by the fix-up launch, anywhere in the block, so slices wait for it too
+    MXG_TRY(launch_spmm_rows(A, dtype, out_layout, n, d_B, ldb, d_outs[0], ldc, 0, 0, /*pieces=*/1, s));
+    for (int c = 0; c < C; c++) {
+        const size_t r0 = (size_t)cr[(size_t)c], nr = (size_t)cr[(size_t)c + 1] - r0;
+        if (nr == 0) continue;
+        MXG_TRY(launch_spmm_rows(A, dtype, out_layout, n, d_B, ldb, d_outs[0], ldc, (int)r0, (int)(r0 + nr), /*pieces=*/0, s));
+        cudaEvent_t done = st->ev_pool[(size_t)c];
+        MXG_CUDA_TRY(cudaEventRecord(done, s));
+        const size_t off = rm ? r0 * ldc * es : r0 * es;
+        for (int d = 1; d < n_dst; d++) {
+            cudaStream_t q = copy[(d + c) % 3];
+            MXG_CUDA_TRY(cudaStreamWaitEvent(q, done, 0));
+            char *dst = static_cast<char *>(d_outs[d]) + off;
+            const char *src = static_cast<const char *>(d_outs[0]) + off;
+            if (rm && ldc == (size_t)n) MXG_CUDA_TRY(cudaMemcpyAsync(dst, src, nr * ldc * es, cudaMemcpyDefault, q));
+            else if (rm) MXG_CUDA_TRY(cudaMemcpy2DAsync(dst, ldc * es, src, ldc * es, (size_t)n * es, nr, cudaMemcpyDefault, q));
+            else MXG_CUDA_TRY(cudaMemcpy2DAsync(dst, ldc * es, src, ldc * es, nr * es, (size_t)n, cudaMemcpyDefault, q));
+        }
+    }
+    for (int k = 0; k < 3; k++) { // the caller's stream continues when every push has landed
+        cudaEvent_t e = st->ev_pool[(size_t)C + (size_t)k];
+        MXG_CUDA_TRY(cudaEventRecord(e, copy[k]));
+        MXG_CUDA_TRY(cudaStreamWaitEvent(s, e, 0));
+    }
+    return MXG_OK;
 }
 
 int mxg_dev_spmm_mcast(mxg_csr_t A, int dtype, int n, const void *d_B, size_t ldb, void *mc_out, size_t ldc, void *stream)

@@ -63,7 +63,7 @@ struct Options {
     long pipe_chunk_nnz = 0;  // stored entries (and rows) per chunk of the streamed path; 0 = auto (nnz/16, >= 1 Mi)
     long pipeline = 1;        // level-1 products: 1 = streamed row chunks (pipeline.cu), 0 = upload-all-then-compute
     long host_threads = 0;    // host threads of the staging engine (hoststage.cu); 0 = auto (all logical CPUs, <= 16)
-    long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry)
+    long host_narrow = 1;     // float32 products: narrow the float64 values on the host (8 instead of 12 PCIe bytes per entry); 1 = automatic, 2 = always
     long host_stage = 1;      // bounce pageable caller memory through the page-locked arena with the host threads
     long host_pack = 1;       // streamed calls: column ids cross PCIe as 2 / 2.5 / 3 bytes (K <= 2^16 / 2^20 / 2^24), packed by the host threads
     long host_pack_lag = 2;   // a chunk's ids are packed while the upload of the chunk this many places before it is pending
@@ -71,6 +71,7 @@ struct Options {
     long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
     long multi_min_nnz = 4 << 20;  // mxg_set_devices(n > 1): level-1 calls with fewer stored entries stay on one device
     long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
+    long host_thp = 1;             // ask for transparent huge pages on large pageable result buffers before their first touch
     long cache_mb = 0;             // level-1 operand cache (device-resident CSR + dense operands keyed on the host arrays); 0 = off
 };
 Options &options();
@@ -131,6 +132,7 @@ struct DeviceState {
     cudaStream_t h2d = nullptr;
     cudaStream_t d2h = nullptr;
     cudaStream_t p2p = nullptr; // pulls of the other devices' dense-operand slices over NVLink (multi-device calls)
+    std::vector<cudaEvent_t> ev_pool; // timing-disabled events reused by mxg_dev_spmm_push
     // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
     void *pin_base = nullptr;
     size_t pin_bytes = 0;
@@ -182,6 +184,7 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
 int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
                      void *Out, size_t ldc, const void *d_B_resident = nullptr, void **d_B_keep = nullptr);
 int handle_spmv_host(DeviceState *st, mxg_csr_s *A, int ytype, const void *y, void *out);
+int handle_chunks(mxg_csr_s *A, cudaStream_t stream); // fills A->host_chunks (row chunks of about equal nnz) once
 void set_last_call_bytes(size_t h2d, size_t d2h);
 
 // capi.cu
@@ -192,6 +195,7 @@ int multi_devices();
 int set_devices(int n);
 int row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
 bool multi_wanted(int m, const int32_t *p);
+bool multi_wanted_now(); // the calling thread is one device pipeline of a multi-device call
 int multi_spmm(int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p, const int32_t *j,
                const double *x, const void *B, size_t ldb, void *Out, size_t ldc);
 int multi_spmv(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *y, void *out);
@@ -226,6 +230,7 @@ bool host_pack_indices(const int32_t *j, size_t n, int K, int hi_bits, void *dst
 void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst = false);
 void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, bool nt_dst = false);
 bool host_is_pinned(const void *ptr);
+void host_prepare_result(void *ptr, size_t bytes); // madvise(MADV_HUGEPAGE) on a fresh pageable result
 int pinned_arena(DeviceState *st, size_t bytes, char **base);
 int pinned_arena_release(DeviceState *st);
 // one-shot staged copies (non-streamed entry points); every slot is idle again when they return

@@ -320,6 +320,7 @@ struct CsrStream {
     const int32_t *p, *j;
     const double *x;
     bool narrow; // the product runs on float32 values
+    bool multi_call = false; // one of several device pipelines of a multi-device call
     // host staging (hoststage.cu)
     bool staging_unavailable = false; // the arena could not be allocated: every copy takes the driver's path
     bool narrow_on_host = false; // float32 values are produced by the host threads, no device narrowing
@@ -359,7 +360,13 @@ struct CsrStream {
     {
         MXG_TRY(build_plan(m, p, plan, result_row_bytes));
         const bool stage = options().host_stage != 0;
-        narrow_on_host = narrow && options().host_narrow != 0 && nnz > 0;
+        // float32 products: the host threads narrow the float64 values on their way into the slot (8 instead of 12
+        // PCIe bytes per entry).  Not when this call is one of several device pipelines fed from page-locked arrays
+        // (host_narrow = 1, automatic): the devices then share the host's memory system rather than one link, and
+        // narrowing costs it 12 bytes of traffic per entry that a plain DMA of the float64 values does not
+        // (measured, 8 devices: 127 ms with host narrowing, 100 ms without).  host_narrow = 2: always, 0: never.
+        const long hn = options().host_narrow;
+        narrow_on_host = narrow && nnz > 0 && (hn == 2 || (hn == 1 && !(multi_call && host_is_pinned(x))));
         stage_x = nnz > 0 && (narrow_on_host || (stage && !host_is_pinned(x)));
         // Packed column ids pay while the call is PCIe-bound and the host threads have time to spare; a packed chunk
         // costs them more memory traffic (read 4, write 2-3 bytes per entry), so when they are also narrowing values
@@ -676,9 +683,11 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     } trace_scope(&trace);
     Scratch sc(st);
     CsrStream cs(sc, m, K, p, j, x, /*narrow=*/dtype == MXG_F32);
+    cs.multi_call = multi_devices() > 1 && multi_wanted_now();
     const bool stage = options().host_stage != 0;
     const bool stage_B = stage && K > 0 && !host_is_pinned(B);
     bool stage_out = stage && !host_is_pinned(Out);
+    if (stage_out) host_prepare_result(Out, (out_layout == MXG_ROWS_CONTIGUOUS ? (rows - 1) * ldc + nz : (nz - 1) * ldc + rows) * s);
     // dense operand first: every chunk needs all of it.  Device copy is rows-contiguous [K][ld_b].
     const size_t ld_b = round_up(nz, vec);
     char *d_B = nullptr, *d_Out = nullptr, *d_tmp = nullptr;
@@ -809,6 +818,7 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
     const bool stage = options().host_stage != 0;
     const bool stage_y = stage && K > 0 && !host_is_pinned(y);
     bool stage_out = stage && !host_is_pinned(out);
+    if (stage_out) host_prepare_result(out, (size_t)m * os);
     char *d_y = nullptr, *d_out = nullptr;
     MXG_TRY(sc.alloc((void **)&d_y, (size_t)K * ys));
     MXG_TRY(sc.alloc((void **)&d_out, (size_t)m * os));
@@ -867,8 +877,6 @@ int pipeline_spmv(DeviceState *st, int ytype, int m, int K, const int32_t *p, co
 // The result leaves in row chunks: chunk c is downloaded (and, for a pageable result, copied out of its
 // page-locked slot by the host threads) while chunk c + 1 is computed.  Long rows (pieces + fix-up) run first.
 // ================================================================================================
-namespace {
-
 // row chunks of a handle (about 16 of equal nnz, tapered like the streamed plan), computed once per handle
 int handle_chunks(mxg_csr_s *A, cudaStream_t stream)
 {
@@ -881,8 +889,6 @@ int handle_chunks(mxg_csr_s *A, cudaStream_t stream)
     A->host_chunks = new std::vector<int32_t>(plan.chunk_row.begin(), plan.chunk_row.end());
     return MXG_OK;
 }
-
-} // namespace
 
 int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
                      void *Out, size_t ldc, const void *d_B_resident, void **d_B_keep)
@@ -928,6 +934,7 @@ int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, i
     const size_t ld_b = round_up(nz, vec);
     const size_t ld_o = out_layout == MXG_ROWS_CONTIGUOUS ? round_up(nz, vec) : rows;
     const bool rm = out_layout == MXG_ROWS_CONTIGUOUS;
+    if (stage_out) host_prepare_result(Out, (rm ? (rows - 1) * ldc + nz : (nz - 1) * ldc + rows) * s);
     char *d_B = const_cast<char *>(static_cast<const char *>(d_B_resident)), *d_Out = nullptr, *d_tmp = nullptr;
     if (!have_B) {
         if (d_B_keep) { // the caller keeps the device copy (operand cache): not a temporary of this call

@@ -110,6 +110,11 @@ bool multi_wanted(int m, const int32_t *p)
 }
 
 namespace {
+thread_local bool g_in_multi_call = false;
+}
+bool multi_wanted_now() { return g_in_multi_call; }
+
+namespace {
 
 // body(g, st) runs on a thread bound to device g_devs[g]; block 0 runs on the calling thread
 template <class Body>
@@ -125,7 +130,9 @@ int run_on_devices(int G, Body body)
         DeviceState *st = nullptr;
         if (cudaSetDevice(g_devs[g]) != cudaSuccess) r = fail(MXG_ERR_CUDA, "cudaSetDevice(%d) failed", g_devs[g]);
         if (r == MXG_OK) r = current_state(&st);
+        g_in_multi_call = true;
         r = body(g, st, r);
+        g_in_multi_call = false;
         rc[(size_t)g] = r;
         if (r != MXG_OK) err[(size_t)g] = last_error_ref();
         last_call_bytes(&up[(size_t)g], &down[(size_t)g]);

@@ -107,6 +107,17 @@ class DeviceCSR:
         _lib.call("mxg_dev_spmm_bcast", self._h, int(dtype), int(out_layout), MXG_ROWS_CONTIGUOUS, int(n), _dptr(B_t),
                   int(ldb), len(dst_ptrs), arr, int(ldc), _stream_ptr(stream))
 
+    def spmm_push(self, B_t, dst_ptrs, n, dtype, out_layout=MXG_ROWS_CONTIGUOUS, ldb=None, ldc=None, stream=None):
+        """Product in row slices into ``dst_ptrs[0]``; every finished slice is pushed to the other destinations by the
+        copy engines (NVLink peer copies) while the next slice is computed."""
+        if ldb is None:
+            ldb = n
+        if ldc is None:
+            ldc = n if out_layout == MXG_ROWS_CONTIGUOUS else self.m
+        arr = (C.c_void_p * len(dst_ptrs))(*[int(q) for q in dst_ptrs])
+        _lib.call("mxg_dev_spmm_push", self._h, int(dtype), int(out_layout), MXG_ROWS_CONTIGUOUS, int(n), _dptr(B_t),
+                  int(ldb), len(dst_ptrs), arr, int(ldc), _stream_ptr(stream))
+
     def spmm_mcast(self, B_t, mc_ptr, n, dtype, ldb=None, ldc=None, stream=None):
         """Fused product + all-gather through NVLS multicast: ``mc_ptr`` is the raw multicast address of this block's
         first row (rows-contiguous); every row is stored once and replicated by the switch into all GPUs' results."""

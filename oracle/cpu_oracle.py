@@ -488,6 +488,24 @@ class Ref:
         return out
 
 
+def synth_csr_host(m, K, nnz, row_model=1, col_model=0, seed=1000):
+    """The synthetic CSR of SURVEY.md 8d generated on the HOST (oracle/mx_synth.c, the twin of csrc/synth.cu): what
+    bench.py's reference arm multiplies, so that it needs neither the product library nor a GPU."""
+    lib = C.CDLL(os.path.join(_HERE, "libmxoracle.so"))
+    lib.mxs_synth_indptr.restype = C.c_longlong
+    lib.mxs_synth_indptr.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_uint64, _i32p]
+    lib.mxs_synth_entries.restype = None
+    lib.mxs_synth_entries.argtypes = [C.c_int, C.c_int, _i32p, C.c_int, C.c_uint64, _i32p, _f64p]
+    p = np.empty(int(m) + 1, dtype=np.int32)
+    got = lib.mxs_synth_indptr(int(m), int(K), int(nnz), int(row_model), int(seed), _ptr(p, _i32p))
+    if got < 0:
+        raise ValueError("synth_csr_host: bad arguments")
+    j = np.empty(int(got), dtype=np.int32)
+    x = np.empty(int(got), dtype=np.float64)
+    lib.mxs_synth_entries(int(m), int(K), _ptr(p, _i32p), int(col_model), int(seed), _ptr(j, _i32p), _ptr(x, _f64p))
+    return p, j, x
+
+
 def best_cpu_baseline(nthreads: int | None = None):
     """The strongest available CPU implementation of the path: the reference itself when its
     prebuilt library is present (fast build if the CPU supports it), else the port."""

@@ -220,7 +220,6 @@ def test_one_call_over_several_devices_is_bit_identical(rx, lib, port, share):
     ref_cm = [getattr(rx, "tcrossprod_csr_dense_" + _sfx(dt))(p, j, x, Y) for dt, Y in cases]
     ref_rm = [getattr(rx, "tcrossprod_dense_csr_" + _sfx(dt))(Y, p, j, x, 0, K) for dt, Y in cases]
     ref_v = rx.matmul_csr_dvec_numeric(p, j, x, y)
-    bytes_one = None
     lib.call("mxg_set_devices", G)
     got = C.c_int(0)
     lib.call("mxg_get_devices", C.byref(got))
@@ -228,7 +227,7 @@ def test_one_call_over_several_devices_is_bit_identical(rx, lib, port, share):
     for (dt, Y), want_cm, want_rm in zip(cases, ref_cm, ref_rm):
         assert np.array_equal(getattr(rx, "tcrossprod_csr_dense_" + _sfx(dt))(p, j, x, Y), want_cm)
         up, down = _bytes(lib)
-        assert down == want_cm.nbytes
+        assert down == want_cm.nbytes + 4 * G  # + every device's 4-byte validation flag
         if share and Y.nbytes >= 4 << 20:
             assert up < p.nbytes + j.nbytes + x.nbytes + Y.nbytes + (1 << 20)  # the dense operand crossed PCIe once
         assert np.array_equal(getattr(rx, "tcrossprod_dense_csr_" + _sfx(dt))(Y, p, j, x, 0, K), want_rm)
@@ -241,4 +240,3 @@ def test_one_call_over_several_devices_is_bit_identical(rx, lib, port, share):
         rx.tcrossprod_csr_dense_numeric(p, jb, x, cases[0][1])
     # and the next call works
     assert np.array_equal(rx.tcrossprod_csr_dense_numeric(p, j, x, cases[0][1]), ref_cm[0])
-    del bytes_one

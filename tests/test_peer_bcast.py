@@ -28,6 +28,12 @@ def test_multiple_local_destinations_hold_identical_bits():
             A.spmm_bcast(B, [o.data_ptr() for o in outs], n, dtype, layout)
             for o in outs:
                 assert torch.equal(o, want)
+            # the copy-engine variant: product in row slices into outs[0], finished slices pushed to the others by DMA
+            outs = [torch.full((A.m * n,), float("nan"), device="cuda", dtype=tdt) for _ in range(3)]
+            A.spmm_push(B, [o.data_ptr() for o in outs], n, dtype, layout)
+            torch.cuda.synchronize()
+            for o in outs:
+                assert torch.equal(o, want)
     y = torch.randn(A.K, device="cuda", dtype=torch.float64, generator=g)
     want = torch.empty(A.m, device="cuda", dtype=torch.float64)
     A.spmv(y, want)

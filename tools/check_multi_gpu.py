@@ -57,6 +57,19 @@ def main():
             else:  # NCCL gathered [world][n][m]; fused wrote one column-major (world*m x n) matrix = [n][world*m]
                 ok = torch.equal(full.view(n, world, m), gathered.view(world, n, m).permute(1, 0, 2))
             report[f"{name}_{lname}"] = bool(ok) and not res.failed()
+            # the same all-gather by the copy engines (mxg_dev_spmm_push): slices pushed while the next is computed
+            full.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            for _ in range(2):
+                A.spmm_push(B, res.dst_ptrs(off), n, dtype, layout, ldc=ldc)
+                res.barrier()
+            torch.cuda.synchronize()
+            if layout == MXG_ROWS_CONTIGUOUS:
+                ok = torch.equal(full, gathered)
+            else:
+                ok = torch.equal(full.view(n, world, m), gathered.view(world, n, m).permute(1, 0, 2))
+            report[f"{name}_{lname}_push"] = bool(ok) and not res.failed()
             del full
             res.close(dist)
     # the same through NVLS multicast (rows-contiguous results): one multimem.st per row, replicated by the switch
