@@ -435,7 +435,13 @@ def run_ours(args):
             At = A.transpose(keep=keep)
             At.spmm(dense, out_local, n, mdt, MXG_ROWS_CONTIGUOUS)
 
-    def step_peer():
+    def step_bulk():
+        _lib.set_option("spmm_bulk", 1)
+        step_peer(keep_option=True)
+
+    def step_peer(keep_option=False):
+        if not keep_option:
+            _lib.set_option("spmm_bulk", 0)
         if op == "spmv":
             A.spmv_bcast(dense, dst)
         else:
@@ -473,6 +479,8 @@ def run_ours(args):
     if fused:
         if op != "csr_dense":
             variants["peer"] = step_peer
+        if op == "dense_tcsr":
+            variants["bulk"] = step_bulk
         if op != "spmv":
             variants["push"] = step_push
         if op == "dense_tcsr" and args.allgather in ("auto", "mcast"):
@@ -558,6 +566,8 @@ def run_ours(args):
     achieved = w_alg / (ms_kernel * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(args.workload) if world == 1 else (None, None)
     fused_text = {"mcast": "fused into the product kernel (NVLS multicast stores)",
+                  "bulk": "fused into the product kernel (finished rows parked in shared memory and shipped to every GPU as "
+                          "cp.async.bulk copies over NVLink)",
                   "peer": "fused into the product kernel (NVLink peer stores)",
                   "push": "finished row slices pushed by the copy engines over NVLink while the next slice is computed",
                   None: "by NCCL"}[how_fused]
@@ -769,10 +779,12 @@ def e2e_multi(args, wl, rx, _lib, dist, cpu_group, rank, world, p_h, j_h, x_h, d
         e2e = {"value": out[world]["pageable_GFLOPs"], "unit": "GFLOP/s", "ms_per_step": out[world]["pageable_ms"],
                "h2d_bytes_per_step": out[world]["pageable_bytes"][0], "d2h_bytes_per_step": out[world]["pageable_bytes"][1],
                "steps": k, "scaling": "strong", "host_threads": nth, "devices": world,
-               "entry_point": f"ONE level-1 call (Rcpp-export mirror) by ONE process on ONE workload matrix, spread over {world} GPUs by "
-                              f"mxg_set_devices({world}): nnz-balanced row blocks, one host thread + one streamed pipeline per device, "
-                              "the dense operand uploaded once (a slice per device) and completed over NVLink; pageable operands and "
-                              "a new pageable result per call, as in an R session",
+               "entry_point": f"ONE level-1 call (Rcpp-export mirror) by ONE process on ONE workload matrix with mxg_set_devices({world}) "
+                              "in force, called the way an R session calls it: pageable operands, a new pageable result.  Such a call is "
+                              "bound by the host threads that bounce pageable memory, so the library keeps it on ONE device (option "
+                              f"multi_pageable); `pinned` is the same call from page-locked arrays, which IS spread over the {world} GPUs: "
+                              "nnz-balanced row blocks, one host thread + one streamed pipeline per device, the dense operand uploaded once "
+                              "(a slice per device) and completed over NVLink",
                "pinned": {"value": out[world]["pinned_GFLOPs"], "ms_per_step": out[world]["pinned_ms"],
                           "h2d_bytes_per_step": out[world]["pinned_bytes"][0], "d2h_bytes_per_step": out[world]["pinned_bytes"][1]},
                "one_device_same_box": {"pageable_ms": out[1]["pageable_ms"], "pinned_ms": out[1]["pinned_ms"]},
@@ -788,10 +800,12 @@ def e2e_multi(args, wl, rx, _lib, dist, cpu_group, rank, world, p_h, j_h, x_h, d
             # parity of the multi-device call against the reference on a bounded row sample of the same matrix
             _lib.call("mxg_set_devices", world)
             _lib.set_option("multi_min_nnz", 1 << 16)
+            _lib.set_option("multi_pageable", 1)  # the check runs on pageable arrays: spread them all the same
             _, parity = cpu_baseline(wl, p_h, j_h, x_h, d_h, budget_s=6.0, rx=rx)
             parity["against"] += f" (spread over {world} devices)"
             _lib.call("mxg_set_devices", 1)
             _lib.set_option("multi_min_nnz", 4 << 20)
+            _lib.set_option("multi_pageable", 0)
     dist.barrier(group=cpu_group)
     return e2e, parity
 
@@ -1009,7 +1023,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/nnz (debugging only; invalid as a bench value)")
-    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer", "push"],
+    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer", "bulk", "push"],
                     help="all-gather of the step at N > 1: NVLS multicast stores / peer stores from the product kernel, "
                          "copy-engine pushes of finished row slices, or the fastest of them")
     ap.add_argument("--others", default="cfg2,k64f64,cfg4", help="extra kernel-only configs reported at N=1 ('' to skip)")

@@ -77,7 +77,8 @@ int mxg_set_device(int device);
  * dense operand crosses PCIe once, a slice per device, and is completed over NVLink peer copies.  This is the
  * in-process counterpart of the reference's one OpenMP team over the rows (src/matmul.cpp:132-136,
  * R/matmul.R:175-180) — an R session is one process.  Devices used: the calling thread's current device and the
- * n - 1 that follow it.  Calls with fewer than option "multi_min_nnz" stored entries stay on one device.
+ * n - 1 that follow it.  Calls with fewer than option "multi_min_nnz" stored entries, or with pageable CSR arrays
+ * (option "multi_pageable"), stay on one device.
  * Results are bit-identical to n = 1.  The Rcpp glue reads MATRIXEXTRA_GPUS once and calls this. */
 int mxg_set_devices(int n);
 int mxg_get_devices(int *n);
@@ -102,6 +103,8 @@ int mxg_get_devices(int *n);
  *             copies are used), "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
  *             freshly allocated R matrix is otherwise filled at page-fault speed, 1);
  *   several devices : "multi_min_nnz" (level-1 calls below this many stored entries stay on one device, 4 Mi),
+ *             "multi_pageable" (0 = calls whose CSR arrays are pageable stay on one device: they are bound by the host
+ *             threads' bounce copies, which more devices do not speed up; 1 = spread them too),
  *             "multi_dense_share" (1 = each device uploads one slice of the dense operand and pulls the rest over NVLink,
  *             0 = every device uploads all of it);
  *   residency : "cache_mb" (level-1 operand cache, MiB of device memory, 0 = off: see mxg_cache_clear). */

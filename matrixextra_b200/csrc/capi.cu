@@ -438,6 +438,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "spmm_panel_cols")) return &o.spmm_panel_cols;
     if (!strcmp(name, "spmm_rpw")) return &o.spmm_rpw;
     if (!strcmp(name, "spmm_cpl")) return &o.spmm_cpl;
+    if (!strcmp(name, "spmm_bulk")) return &o.spmm_bulk;
     if (!strcmp(name, "radix_bits")) return &o.radix_bits;
     if (!strcmp(name, "host_threads")) return &o.host_threads;
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
@@ -454,6 +455,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "pipe_chunk_nnz")) return &o.pipe_chunk_nnz;
     if (!strcmp(name, "multi_min_nnz")) return &o.multi_min_nnz;
     if (!strcmp(name, "multi_dense_share")) return &o.multi_dense_share;
+    if (!strcmp(name, "multi_pageable")) return &o.multi_pageable;
     if (!strcmp(name, "cache_mb")) return &o.cache_mb;
     if (!strcmp(name, "host_thp")) return &o.host_thp;
     return nullptr;
@@ -884,7 +886,7 @@ int mxg_spmm_csr_dense(int dtype, int out_layout, int b_layout, int m, int K, in
     DeviceState *st;
     MXG_TRY(current_state(&st));
     // several devices (mxg_set_devices): nnz-balanced row blocks, one host thread and one streamed pipeline per device
-    if (options().pipeline != 0 && multi_wanted(m, p) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
+    if (options().pipeline != 0 && multi_wanted(m, p, j, x) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
         return multi_spmm(dtype, out_layout, b_layout, m, K, n, p, j, x, B, ldb, Out, ldc);
     // operand cache (option cache_mb): the device CSR of these host arrays is kept between calls
     if (p[0] == 0 && options().pipeline != 0 && cache_enabled() && m > 0 && n > 0 && p[m] > 0 && j && x) {
@@ -983,7 +985,7 @@ int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, co
     std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     DeviceState *st;
     MXG_TRY(current_state(&st));
-    if (options().pipeline != 0 && multi_wanted(m, p) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
+    if (options().pipeline != 0 && multi_wanted(m, p, j, x) && (int64_t)p[m] >= (int64_t)p[0] && p[0] >= 0)
         return multi_spmv(ytype, m, K, p, j, x, y, out);
     if (p[0] == 0 && options().pipeline != 0 && cache_enabled() && m > 0 && p[m] > 0 && j && x) {
         mxg_csr_s *hit = cache_find_csr(m, K, p, j, x, MXG_KEEP_F64);

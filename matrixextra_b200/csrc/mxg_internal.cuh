@@ -54,6 +54,7 @@ struct Options {
     long spmm_panel_mb = 0;   // column-panel size of the dense operand in MiB; 0 = no panels (default)
     long spmm_panel_cols = 0; // force a panel width in columns of A (tests / sweeps); 0 = by size
     long spmm_rpw = 0;        // consecutive rows per warp (row-major output); 0 = auto
+    long spmm_bulk = 1;       // multi-destination rows-contiguous products ship finished rows as bulk copies from shared memory (TMA)
     long spmm_cpl = 0;        // vectors per lane of the SpMM teams: 0 = auto (2 when a row of B exceeds 128 bytes), 1, 2
     long radix_bits = 8;      // CSR->CSC: largest digit of the radix passes (4 .. 10 bits)
     long spmv_lpr = 0;        // 0 = auto
@@ -70,6 +71,7 @@ struct Options {
     long pipe_slots = 4;      // ring slots of the staging arena (chunks in flight between host and device)
     long host_arena_max_mb = 4096; // largest page-locked arena the library may hold; beyond it copies take the driver's path
     long multi_min_nnz = 4 << 20;  // mxg_set_devices(n > 1): level-1 calls with fewer stored entries stay on one device
+    long multi_pageable = 0;       // ... and calls whose CSR arrays are pageable stay on one device too (they are bound by the host threads)
     long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
     long host_thp = 1;             // ask for transparent huge pages on large pageable result buffers before their first touch
     long cache_mb = 0;             // level-1 operand cache (device-resident CSR + dense operands keyed on the host arrays); 0 = off
@@ -194,7 +196,7 @@ int csr_handle_free(mxg_csr_s *h);
 int multi_devices();
 int set_devices(int n);
 int row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
-bool multi_wanted(int m, const int32_t *p);
+bool multi_wanted(int m, const int32_t *p, const int32_t *j, const double *x);
 bool multi_wanted_now(); // the calling thread is one device pipeline of a multi-device call
 int multi_spmm(int dtype, int out_layout, int b_layout, int m, int K, int n, const int32_t *p, const int32_t *j,
                const double *x, const void *B, size_t ldb, void *Out, size_t ldc);

@@ -103,10 +103,16 @@ int row_partition(int m, const int32_t *p, int parts, int32_t *row_starts)
 
 // Should this call be spread over the devices?  Small products stay on one (a second device costs a thread start,
 // a second staging arena and — for SpMM — the NVLink exchange of the dense operand).
-bool multi_wanted(int m, const int32_t *p)
+// Nor do calls whose CSR arrays are ordinary pageable memory (option multi_pageable = 0): those are bound by the host
+// threads that bounce the arrays into page-locked slots — the memory bandwidth of the host cores, not a PCIe link — and
+// more pipelines only cut the same work into smaller pieces (measured on the 16-core B200 box, cfg3: 55 ms on one
+// device, 64 ms on two, 97 ms on eight; page-locked arrays: 26.4 -> 14.6 ms on eight, the host's DMA roof).
+bool multi_wanted(int m, const int32_t *p, const int32_t *j, const double *x)
 {
     if (g_ndev <= 1 || m < g_ndev) return false;
-    return (int64_t)p[m] - (int64_t)p[0] >= (int64_t)std::max<long>(options().multi_min_nnz, 1);
+    if ((int64_t)p[m] - (int64_t)p[0] < (int64_t)std::max<long>(options().multi_min_nnz, 1)) return false;
+    if (options().multi_pageable == 0 && !(host_is_pinned(j) && host_is_pinned(x))) return false;
+    return true;
 }
 
 namespace {

@@ -227,6 +227,7 @@ struct SpmmArgs {
     void *extra[MXG_MAX_DST - 1];
     int n_extra;
     int mcast; // Out is a multicast address: rows are written with multimem.st and land on every GPU (row-major only)
+    int bulk;  // MULTI launches: rows leave as bulk copies from shared memory (BULK instantiation; ldc == n == one column block)
     int rpw; // consecutive rows per warp (<= 31; column-major output uses SPMM_CM_RPW)
     int piece;
     int n_pieces;
@@ -255,8 +256,13 @@ struct SpmmArgs {
 // MULTI (row-major results only): the launch writes more than the local result — peer copies (g.extra) or an NVLS
 // multicast address (g.mcast).  A separate instantiation so that the single-destination kernel keeps the exact
 // instruction schedule it was tuned with (the shared version cost the fp64 variant 17 %).
+// BULK (a MULTI variant for results whose rows are exactly one column block wide, ldc == n == NB): a warp's SPMM_CM_RPW
+// finished rows are parked in its slice of shared memory — they are contiguous in the rows-contiguous result — and
+// shipped to every destination (the local result and the peer-mapped results of the other GPUs) as ONE bulk
+// asynchronous copy each (cp.async.bulk.global.shared::cta: the TMA unit streams 2 - 4 KB per destination over NVLink)
+// instead of rpw x n/V 16-byte stores per destination issued by the SM's load/store path.
 template <typename T, int V, int LPR, int CPL, int U, bool COLMAJOR, bool PANELS, int MB = (CPL == 1 ? SPMM_MINB : 4),
-          bool MULTI = false>
+          bool MULTI = false, bool BULK = false>
 __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 {
     constexpr int NB = LPR * V * CPL; // output columns per CTA column block
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
     constexpr int TLD = BR + 1;
     __shared__ T tile[COLMAJOR ? NB * TLD : 1];
     __shared__ unsigned char s_write[COLMAJOR ? BR : 1]; // tile rows this launch has to write
+    __shared__ __align__(128) T stage[BULK ? BR * NB : 1]; // [warp][row of the warp][column]
 
     const int32_t *__restrict__ p = g.p;
     const int32_t *__restrict__ j = g.j;
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
     }
 
     const int rb = blockIdx.x - g.piece_blocks;
-    const int rpw = COLMAJOR ? SPMM_CM_RPW : g.rpw;
+    const int rpw = (COLMAJOR || BULK) ? SPMM_CM_RPW : g.rpw;
     const int row0 = (rb * SPMM_WARPS + warp) * rpw;
     const int nr = min(rpw, g.m - row0); // rows this warp owns (<= 0: none)
 
@@ -415,6 +422,11 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
 #pragma unroll
                                     for (int i = 0; i < V; i++) tile[(col[c] - col0 + i) * TLD + rl] = acc[c].v[i];
                                 }
+                        } else if (BULK) {
+                            T *srow = stage + (size_t)(warp * SPMM_CM_RPW + r) * NB;
+#pragma unroll
+                            for (int c = 0; c < CPL; c++)
+                                if (cok[c]) st_pack<T, V>(srow + (col[c] - col0), acc[c]);
                         } else {
                             T *dst = Out + (size_t)(row0 + r) * g.ldc;
 #pragma unroll
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                                 }
                         }
                     }
-                    if (MULTI && !COLMAJOR && !PANELS) {
+                    if (MULTI && !COLMAJOR && !PANELS && !BULK) {
                         // copies for the other GPUs: after the butterfly every sub-team holds the same bits, so the
                         // destinations are dealt out over the sub-teams and one store instruction of the warp writes
                         // to 32 / LPR peers at once
@@ -440,6 +452,13 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                                 if (cok[c]) st_stream(dst + col[c], acc[c]);
                         }
                     }
+                }
+                if (BULK && skip && sub == 0) {
+                    // a long row: written by the fix-up launch afterwards; its slot must not ship stale shared memory
+                    T *srow = stage + (size_t)(warp * SPMM_CM_RPW + r) * NB;
+#pragma unroll
+                    for (int c = 0; c < CPL; c++)
+                        if (cok[c]) st_pack<T, V>(srow + (col[c] - col0), acc[c]); // acc is zero: nothing was gathered
                 }
                 zero_acc<T, V, CPL>(acc);
                 if (nrow >= nr) break;
@@ -454,6 +473,24 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
         }
     }
 
+    if (BULK && nr > 0) {
+        // the warp's nr rows are nr * NB contiguous elements of every destination: one bulk copy per destination,
+        // issued by one lane each (generic proxy writes -> async proxy reads need the proxy fence)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane <= g.n_extra) {
+            T *base = Out;
+#pragma unroll
+            for (int d = 0; d < MXG_MAX_DST - 1; d++)
+                if (lane == d + 1) base = static_cast<T *>(g.extra[d]);
+            T *dst = base + (size_t)row0 * g.ldc;
+            const unsigned bytes = (unsigned)(nr * NB * (int)sizeof(T));
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(stage + (size_t)warp * SPMM_CM_RPW * NB);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory stays valid until it has been read
+        }
+    }
     if (MULTI && !COLMAJOR && !PANELS && g.mcast) __threadfence_system(); // multicast rows are on their way before the step's barrier
     if (COLMAJOR) {
         __syncthreads();
@@ -545,7 +582,9 @@ static int launch_two(SpmmArgs &args, int row_blocks, cudaStream_t stream)
     constexpr int MB = sizeof(T) == 4 ? 6 : 5;
     constexpr int NB = LPR * V * 2;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
-    if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
+    if (!COLMAJOR && args.bulk && args.n == NB)
+        MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB, !COLMAJOR, !COLMAJOR>), grid, SPMM_THREADS, 0, stream, args);
+    else if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
         MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB, !COLMAJOR>), grid, SPMM_THREADS, 0, stream, args);
     else
         MXG_LAUNCH((k_spmm<T, V, LPR, 2, 4, COLMAJOR, false, MB>), grid, SPMM_THREADS, 0, stream, args);
@@ -558,7 +597,10 @@ static int launch_variant(SpmmArgs &args, int row_blocks, cudaStream_t stream)
     constexpr int NB = LPR * V * CPL;
     dim3 grid((unsigned)(args.piece_blocks + row_blocks), (unsigned)ceil_div_i(args.n, NB), 1);
     if (args.n_panels <= 1) {
-        if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
+        if (!COLMAJOR && args.bulk && args.n == NB)
+            MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false, (CPL == 1 ? SPMM_MINB : 4), !COLMAJOR, !COLMAJOR>), grid,
+                       SPMM_THREADS, 0, stream, args);
+        else if (!COLMAJOR && (args.n_extra > 0 || args.mcast))
             MXG_LAUNCH((k_spmm<T, V, LPR, CPL, U, COLMAJOR, false, (CPL == 1 ? SPMM_MINB : 4), !COLMAJOR>), grid, SPMM_THREADS, 0,
                        stream, args);
         else
@@ -578,6 +620,9 @@ static int dispatch_geom(int lpr, int cpl, SpmmArgs &args, cudaStream_t stream)
     int rpw = COLMAJOR ? SPMM_CM_RPW : (int)options().spmm_rpw;
     if (rpw <= 0) rpw = 8;
     if (rpw > 31) rpw = 31;
+    // bulk copies ship exactly one column block per row: the row must be one block wide (and whole vectors)
+    if (args.bulk && (COLMAJOR || V == 1 || args.n != lpr * V * cpl)) args.bulk = 0;
+    if (args.bulk) rpw = SPMM_CM_RPW;
     args.rpw = rpw;
     args.piece_blocks = ceil_div_i(args.n_pieces, SPMM_WARPS);
     const int row_blocks = ceil_div_i(args.m, SPMM_WARPS * rpw);
@@ -708,6 +753,8 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.ldc = ldc;
     args.n_extra = n_dst - 1;
     args.mcast = mcast;
+    // several destinations of a rows-contiguous result whose rows are stored back to back: bulk copies from shared memory
+    args.bulk = (n_dst > 1 && !mcast && !colmajor && vec && ldc == (size_t)n && options().spmm_bulk != 0) ? 1 : 0;
     for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.piece = A->piece;
     args.n_pieces = part == 1 ? 0 : A->n_pieces;

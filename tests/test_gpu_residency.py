@@ -32,6 +32,7 @@ def lib():
     _lib.call("mxg_set_devices", 1)
     _lib.set_option("multi_min_nnz", 4 << 20)
     _lib.set_option("multi_dense_share", 1)
+    _lib.set_option("multi_pageable", 0)
     _lib.set_option("piece", 1024)
     _lib.set_option("pipe_chunk_nnz", 0)
 
@@ -211,6 +212,7 @@ def test_one_call_over_several_devices_is_bit_identical(rx, lib, port, share):
     rng = np.random.default_rng(31)
     lib.set_option("multi_min_nnz", 1000)
     lib.set_option("multi_dense_share", share)
+    lib.set_option("multi_pageable", 1)  # numpy arrays are pageable: by default such calls stay on one device
     cases = []
     for dt, n in ((np.float64, 32), (np.float32, 64), (np.float64, 5)):
         Y = np.asfortranarray(rng.standard_normal((n, K)).astype(dt))

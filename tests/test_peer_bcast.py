@@ -19,15 +19,23 @@ def test_multiple_local_destinations_hold_identical_bits():
     A = DeviceCSR.synth(30000, 8000, 900000, row_model=1, col_model=1, seed=77)
     assert A.n_long > 0
     g = torch.Generator(device="cuda").manual_seed(3)
-    for dtype, tdt, n in ((MXG_F32, torch.float32, 64), (MXG_F64, torch.float64, 24)):
+    from matrixextra_b200 import _lib
+    # n = 64 (fp32 and fp64), n = 32 fp32: rows exactly one column block wide -> the bulk-copy instantiation (finished rows
+    # leave shared memory as cp.async.bulk copies, one per destination); n = 24: peer stores from registers
+    for dtype, tdt, n in ((MXG_F32, torch.float32, 64), (MXG_F64, torch.float64, 64), (MXG_F32, torch.float32, 32),
+                          (MXG_F64, torch.float64, 24)):
         B = torch.randn(A.K, n, device="cuda", dtype=tdt, generator=g)
         for layout in (MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS):
             want = torch.empty(A.m * n, device="cuda", dtype=tdt)
             A.spmm(B, want, n, dtype, layout)
-            outs = [torch.full((A.m * n,), float("nan"), device="cuda", dtype=tdt) for _ in range(3)]
-            A.spmm_bcast(B, [o.data_ptr() for o in outs], n, dtype, layout)
-            for o in outs:
-                assert torch.equal(o, want)
+            for bulk in (1, 0):
+                _lib.set_option("spmm_bulk", bulk)
+                for n_dst in (3, 8):
+                    outs = [torch.full((A.m * n,), float("nan"), device="cuda", dtype=tdt) for _ in range(n_dst)]
+                    A.spmm_bcast(B, [o.data_ptr() for o in outs], n, dtype, layout)
+                    for o in outs:
+                        assert torch.equal(o, want)
+            _lib.set_option("spmm_bulk", 1)
             # the copy-engine variant: product in row slices into outs[0], finished slices pushed to the others by DMA
             outs = [torch.full((A.m * n,), float("nan"), device="cuda", dtype=tdt) for _ in range(3)]
             A.spmm_push(B, [o.data_ptr() for o in outs], n, dtype, layout)

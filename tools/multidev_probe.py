@@ -44,6 +44,7 @@ def main():
     fn = rx.tcrossprod_dense_csr_float32 if f32 else rx.tcrossprod_dense_csr_numeric
     ndev = torch.cuda.device_count()
     want = None
+    _lib.set_option("multi_pageable", 1 if args.pageable else 0)  # pageable calls stay on one device by default
     for share in (1, 0):
         _lib.set_option("multi_dense_share", share)
         for G in [g for g in (1, 2, 4, 8) if g <= ndev]:

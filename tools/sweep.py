@@ -134,6 +134,18 @@ def main():
             A.free()
         _lib.set_option("piece", 1024)
 
+    if "panels" in what:
+        # column panels (k_spmm<PANELS>: one launch per L2-sized slab of the dense operand) vs none, on the cfg3 matrix
+        A = DeviceCSR.synth(m, K, wl["nnz"], 1, 1, seed=1003, keep=MXG_KEEP_F32 | MXG_KEEP_F64)
+        for rep in range(2):
+            spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm_nopanels")
+            for mb in (40, 48, 56, 64, 86, 128):
+                spmm_case(A, MXG_F32, MXG_ROWS_CONTIGUOUS, 64, "cfg3_f32_rm_panels", spmm_panel_mb=mb)
+            spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm_nopanels")
+            for mb in (48, 56, 64, 86):
+                spmm_case(A, MXG_F64, MXG_ROWS_CONTIGUOUS, 64, "k64_f64_rm_panels", spmm_panel_mb=mb)
+        A.free()
+
     if "spmvprobe" in what:
         # K3's access pattern without the row structure (mxg_dev_spmv_probe): ids only / + 8-byte gathers of y
         # (plain loads, texture) / + values and FMA — the floor the SpMV kernel is measured against
