@@ -355,9 +355,18 @@ def run_ours(args):
     cpu_group = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        # collectives that overlap a product (sharded.PipelinedColumnMajorGather) must not queue behind its CTAs
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")  # host-side waits that leave the other ranks' GPUs idle
 
+    if world > 1 and args.strong_only:
+        rec = strong_cfg5(args, dist, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"strong_cfg5": rec}))
+        return
     wl = dict(WORKLOADS[args.workload])
     if args.scale != 1.0:
         wl["m"] = max(64, int(wl["m"] * args.scale))
@@ -823,7 +832,7 @@ def strong_cfg5(args, dist, rank, world):
     mg, K, n = int(wl["m"] * sc) // world, wl["K"], wl["n"]
     nnz_g = int(wl["nnz"] * sc) // world
     free, _ = torch.cuda.mem_get_info()
-    need = 8 * nnz_g + 4 * K * n + 2 * 4 * world * mg * n + 4 * mg * n + (4 << 30)
+    need = 8 * nnz_g + 4 * K * n + 3 * 4 * world * mg * n + 3 * 4 * mg * n + (8 << 30)
     if free < need:
         return {"skipped": f"needs {need / 1e9:.0f} GB per GPU, {free / 1e9:.0f} GB free"}
     A = DeviceCSR.synth(mg, K, nnz_g, wl["row_model"], wl["col_model"], seed=wl["seed"] + 7919 * rank, keep=MXG_KEEP_F32)
@@ -853,25 +862,50 @@ def strong_cfg5(args, dist, rank, world):
     def compute():
         A.spmm(dense, out_all[:, rank * mg:(rank + 1) * mg], n, MXG_F32, MXG_COLS_CONTIGUOUS, ldc=ldc)
 
+    from matrixextra_b200 import _lib
     local = torch.empty(n, mg, device="cuda", dtype=torch.float32)
     nccl_all = torch.empty(world * n * mg, device="cuda", dtype=torch.float32)
+    nccl_out = out_all  # the re-arranged copy lands in the same result buffer (checked against the other variants' bits)
 
-    def nccl_step():
+    import ctypes as _C
+    cur = torch.cuda.current_stream
+
+    def nccl_step(rearrange=False):
+        # the unfused baseline: product into a contiguous local block, ONE all-gather ([G][n][m]), and — for the result R
+        # needs — the local re-arrangement of the G blocks into one column-major (G*m x n) matrix (copy engines)
         A.spmm(dense, local, n, MXG_F32, MXG_COLS_CONTIGUOUS)
         dist.all_gather_into_tensor(nccl_all, local.view(-1))
+        if rearrange:
+            for q in range(world):
+                _lib.call("mxg_dev_copy_2d", _C.c_void_p(nccl_out.data_ptr() + q * mg * 4), world * mg * 4,
+                          _C.c_void_p(nccl_all.data_ptr() + q * n * mg * 4), mg * 4, mg * 4, n, _C.c_void_p(cur().cuda_stream))
 
+    from matrixextra_b200.sharded import PipelinedColumnMajorGather
+    pipe = PipelinedColumnMajorGather(A, n, MXG_F32, torch.float32, dist, rank, world, slices=8)
+    step_pipe = lambda: pipe.step(dense)  # noqa: E731
     for _ in range(2):
         step()
+        step_pipe()
     steps = 3
-    ms_step = timed(step, steps)
+    ms_push = timed(step, steps)
+    ms_pipe = timed(step_pipe, steps)
     ms_compute = timed(compute, steps)
     step()
+    step_pipe()
     nccl_step()
     torch.cuda.synchronize()
-    same = torch.equal(out_all.view(n, world, mg), nccl_all.view(world, n, mg).permute(1, 0, 2))
+    want = nccl_all.view(world, n, mg).permute(1, 0, 2)
+    same = torch.equal(out_all.view(n, world, mg), want) and torch.equal(pipe.out_all.view(n, world, mg), want)
     flag = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    ms_nccl = timed(nccl_step, steps)
+    ms_nccl_raw = timed(nccl_step, steps)
+    ms_nccl = timed(lambda: nccl_step(True), steps)
+    torch.cuda.synchronize()
+    same_r = torch.equal(out_all.view(n, world, mg), want)
+    flag2 = torch.tensor([1 if same_r else 0], device="cuda")
+    dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
+    ms_step = min(ms_push, ms_pipe, ms_nccl)
+    del pipe
     t = torch.tensor([A.nnz], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)
     nnz_all = int(t.item())
@@ -883,11 +917,17 @@ def strong_cfg5(args, dist, rank, world):
     return {"workload": wl["desc"] + f" row-sharded over {world} GPUs" + ("" if sc == 1.0 else f" (scaled x{sc})"),
             "scaling": "strong", "rows_per_gpu": mg, "nnz_total": nnz_all, "steps": steps,
             "ms_per_step": ms_step, "GFLOPs": 2.0 * nnz_all * n / ms_step / 1e6,
-            "compute_only_ms": ms_compute, "nccl_after_compute_ms": ms_nccl,
-            "how": "product in ~16 row slices per GPU into the global column-major result; every finished slice pushed to the "
-                   "other GPUs as a 2-D block (n column segments) by the copy engines over NVLink while the next slice is "
-                   "computed (mxg_dev_spmm_push) + device-side flag barrier",
-            "bit_identical_to_nccl": bool(flag.item()) and not failed,
+            "compute_only_ms": ms_compute, "nccl_after_compute_ms": ms_nccl, "nccl_after_compute_without_rearrangement_ms": ms_nccl_raw,
+            "variants_ms_per_step": {"push": ms_push, "pipelined_nccl": ms_pipe, "nccl_after_compute": ms_nccl},
+            "how": {ms_pipe: "product in 8 row slices into this GPU's rows of the global column-major result; behind every slice "
+                             "one stream packs it (copy engine) and all-gathers it with NCCL, another unpacks the received slices "
+                             "into the result (copy engines) while the next slice is computed (sharded.PipelinedColumnMajorGather)",
+                    ms_push: "product in ~16 row slices per GPU into the global column-major result; every finished slice pushed "
+                             "to the other GPUs as a 2-D block (n column segments) by the copy engines over NVLink while the next "
+                             "slice is computed (mxg_dev_spmm_push) + device-side flag barrier",
+                    ms_nccl: "product into a contiguous local column-major block, ONE NCCL all-gather of the blocks ([G][n][m]), "
+                             "then the local re-arrangement into one column-major (G*m x n) matrix on copy engines"}[ms_step],
+            "bit_identical_to_nccl": bool(flag.item()) and bool(flag2.item()) and not failed,
             "bytes_received_per_gpu": int(4 * (world - 1) * mg * n),
             "ingress_GBps": 4 * (world - 1) * mg * n / ms_step / 1e6,
             "one_gpu_ms": one_gpu_ms, "one_gpu_source": "163 ms for the whole of cfg5 on one B200 (profiles/r01_v6_bench_cfg5_kernel_only.json; "
@@ -1030,6 +1070,7 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-strong", action="store_true", help="N > 1: skip the row-sharded cfg5 record")
+    ap.add_argument("--strong-only", action="store_true", help="N > 1: only the row-sharded cfg5 record (development)")
     ap.add_argument("--strong-scale", type=float, default=1.0, help="shrink cfg5 for the strong-scaling record (debugging)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) is sent to

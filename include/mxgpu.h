@@ -283,6 +283,16 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
                        int n_dst, void *const *d_outs, size_t ldc, void *stream);
 int mxg_dev_spmv_bcast(mxg_csr_t A, int ytype, const void *d_y, int n_dst, void *const *d_outs, void *stream);
 
+/* One slice of a product: rows [r0, r1) of the handle without their long rows (pieces == 0), or only the long rows
+ * (pieces != 0).  d_Out is the origin of the FULL result (ldc as for mxg_dev_spmm).  A product can so be issued as
+ * "long rows, then row slices" with something else — a collective, a copy — started behind every slice. */
+int mxg_dev_spmm_rows(mxg_csr_t A, int dtype, int out_layout, int n, const void *d_B, size_t ldb, void *d_Out, size_t ldc,
+                      int r0, int r1, int pieces, void *stream);
+
+/* Strided device-to-device copy (`height` lines of `width_bytes`) on a copy engine, asynchronous on `stream`. */
+int mxg_dev_copy_2d(void *d_dst, size_t dpitch, const void *d_src, size_t spitch, size_t width_bytes, size_t height,
+                    void *stream);
+
 /* The same product + all-gather with the COPY ENGINES: the product runs in about 16 row slices of equal nnz into
  * d_outs[0] and every finished slice is pushed to the other n_dst - 1 destinations by DMA (peer copies over NVLink;
  * 2-D copies for column-major results, whose blocks are n strided column segments) on the library's copy streams

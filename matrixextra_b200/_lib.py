@@ -66,6 +66,8 @@ _SIGNATURES = {
     "mxg_dev_spmm": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _vp],
     "mxg_dev_spmv": [_vp, _i32, _vp, _vp, _vp],
     "mxg_dev_spmm_bcast": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
+    "mxg_dev_spmm_rows": [_vp, _i32, _i32, _i32, _vp, _sz, _vp, _sz, _i32, _i32, _i32, _vp],
+    "mxg_dev_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz, _vp],
     "mxg_dev_spmm_push": [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _i32, _vp, _sz, _vp],
     "mxg_dev_spmv_bcast": [_vp, _i32, _vp, _i32, _vp, _vp],
     "mxg_dev_spmm_mcast": [_vp, _i32, _i32, _vp, _sz, _vp, _sz, _vp],

@@ -664,6 +664,32 @@ int mxg_dev_spmm_bcast(mxg_csr_t A, int dtype, int out_layout, int b_layout, int
     return launch_spmm_multi(A, dtype, out_layout, n, d_B, ldb, n_dst, d_outs, ldc, static_cast<cudaStream_t>(stream));
 }
 
+/* One slice of a product on a handle: rows [r0, r1) without their long rows (pieces == 0), or only the long rows
+ * (pieces != 0: piece kernels + fix-up, r0 / r1 ignored).  d_Out is the origin of the FULL result in both cases.
+ * Lets a caller pipeline its own exchange of finished row slices (sharded.PipelinedColumnMajorGather). */
+int mxg_dev_spmm_rows(mxg_csr_t A, int dtype, int out_layout, int n, const void *d_B, size_t ldb, void *d_Out, size_t ldc,
+                      int r0, int r1, int pieces, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!A) return fail(MXG_ERR_ARG, "dev_spmm_rows: NULL handle");
+    if (A->m == 0 || n <= 0 || A->nnz == 0) return fail(MXG_ERR_ARG, "dev_spmm_rows: empty product");
+    if (out_layout == MXG_ROWS_CONTIGUOUS ? ldc < (size_t)n : ldc < (size_t)A->m) return fail(MXG_ERR_ARG, "dev_spmm_rows: ldc too small");
+    if (ldb < (size_t)n) return fail(MXG_ERR_ARG, "dev_spmm_rows: ldb < n");
+    return launch_spmm_rows(A, dtype, out_layout, n, d_B, ldb, d_Out, ldc, r0, r1, pieces, static_cast<cudaStream_t>(stream));
+}
+
+/* Strided device-to-device copy on `stream` (cudaMemcpy2DAsync): `height` lines of `width_bytes`.  Runs on a copy engine,
+ * not on SMs: how sharded.PipelinedColumnMajorGather packs a row slice of a column-major block and unpacks the gathered
+ * slices into their rows of the global result while the product kernel keeps the SMs. */
+int mxg_dev_copy_2d(void *d_dst, size_t dpitch, const void *d_src, size_t spitch, size_t width_bytes, size_t height, void *stream)
+{
+    if (width_bytes == 0 || height == 0) return MXG_OK;
+    if (!d_dst || !d_src || dpitch < width_bytes || spitch < width_bytes) return fail(MXG_ERR_ARG, "dev_copy_2d: bad arguments");
+    MXG_CUDA_TRY(cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, width_bytes, height, cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(stream)));
+    return MXG_OK;
+}
+
 /* Product + all-gather with the copy engines: the product runs in row slices (about 16 of equal nnz) into d_outs[0];
  * every finished slice is pushed to the other destinations by DMA (peer copies over NVLink, 2-D for column-major
  * results) on the library's three copy streams while the next slice is being computed.  SM stores to peers carry
@@ -690,8 +716,14 @@ int mxg_dev_spmm_push(mxg_csr_t A, int dtype, int out_layout, int b_layout, int 
     const std::vector<int32_t> &cr = *A->host_chunks;
     const int C = (int)cr.size() - 1;
     const size_t es = dtype == MXG_F64 ? 8 : 4;
-    cudaStream_t copy[3] = {st->p2p, st->h2d, st->d2h};
-    while ((int)st->ev_pool.size() < C + 4) {
+    // one copy stream per destination: the pushes to different peers run on different copy engines at the same time
+    while ((int)st->push_streams.size() < MXG_MAX_DST - 1) {
+        cudaStream_t q;
+        MXG_CUDA_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+        st->push_streams.push_back(q);
+    }
+    const std::vector<cudaStream_t> &copy = st->push_streams;
+    while ((int)st->ev_pool.size() < C + MXG_MAX_DST) {
         cudaEvent_t e;
         MXG_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         st->ev_pool.push_back(e);
@@ -706,7 +738,7 @@ int mxg_dev_spmm_push(mxg_csr_t A, int dtype, int out_layout, int b_layout, int 
         MXG_CUDA_TRY(cudaEventRecord(done, s));
         const size_t off = rm ? r0 * ldc * es : r0 * es;
         for (int d = 1; d < n_dst; d++) {
-            cudaStream_t q = copy[(d + c) % 3];
+            cudaStream_t q = copy[(size_t)(d - 1)];
             MXG_CUDA_TRY(cudaStreamWaitEvent(q, done, 0));
             char *dst = static_cast<char *>(d_outs[d]) + off;
             const char *src = static_cast<const char *>(d_outs[0]) + off;
@@ -715,9 +747,9 @@ int mxg_dev_spmm_push(mxg_csr_t A, int dtype, int out_layout, int b_layout, int 
             else MXG_CUDA_TRY(cudaMemcpy2DAsync(dst, ldc * es, src, ldc * es, nr * es, (size_t)n, cudaMemcpyDefault, q));
         }
     }
-    for (int k = 0; k < 3; k++) { // the caller's stream continues when every push has landed
-        cudaEvent_t e = st->ev_pool[(size_t)C + (size_t)k];
-        MXG_CUDA_TRY(cudaEventRecord(e, copy[k]));
+    for (int d = 1; d < n_dst; d++) { // the caller's stream continues when every push has landed
+        cudaEvent_t e = st->ev_pool[(size_t)C + (size_t)d];
+        MXG_CUDA_TRY(cudaEventRecord(e, copy[(size_t)(d - 1)]));
         MXG_CUDA_TRY(cudaStreamWaitEvent(s, e, 0));
     }
     return MXG_OK;

@@ -314,6 +314,11 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
     if (h->m == 0) return MXG_OK;
     int *d_stats = nullptr;
     MXG_CUDA_TRY(cudaMallocAsync(&d_stats, sizeof(int) * 8, stream));
+    struct Release { // on every path, stream-ordered
+        int *q;
+        cudaStream_t s;
+        ~Release() { cudaFreeAsync(q, s); }
+    } release{d_stats, stream};
     MXG_CUDA_TRY(cudaMemsetAsync(d_stats, 0, sizeof(int) * 8, stream));
     int grid = ceil_div_i(h->m, 256);
     if (grid > 148 * 8) grid = 148 * 8;
@@ -326,14 +331,8 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
     int stats[8];
     MXG_CUDA_TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, stream));
     MXG_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (stats[0] & 1) {
-        cudaFreeAsync(d_stats, stream);
-        return fail(MXG_ERR_INDEX, "CSR indptr is negative or decreasing");
-    }
-    if (stats[0] & 2) {
-        cudaFreeAsync(d_stats, stream);
-        return fail(MXG_ERR_INDEX, "CSR column index outside [0, %d)", h->K);
-    }
+    if (stats[0] & 1) return fail(MXG_ERR_INDEX, "CSR indptr is negative or decreasing");
+    if (stats[0] & 2) return fail(MXG_ERR_INDEX, "CSR column index outside [0, %d)", h->K);
     h->max_len = stats[1];
     h->n_long = stats[2];
     h->n_pieces = stats[3];
@@ -346,7 +345,6 @@ int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream)
         MXG_LAUNCH(k_fill_long_tables, grid, 256, 0, stream, h->m, h->d_p, h->piece, d_stats, h->d_long_rows,
                    h->d_long_first, h->d_long_np, h->d_piece_row, h->d_piece_k);
     }
-    MXG_CUDA_TRY(cudaFreeAsync(d_stats, stream));
     return MXG_OK;
 }
 
@@ -398,20 +396,26 @@ int peer_barrier_failed(int *failed)
     return MXG_OK;
 }
 
-int ensure_partial(mxg_csr_s *h, size_t bytes)
+// Long-row partial sums live in a workspace that belongs to the CALL, not to the handle: stream-ordered allocation on
+// the call's stream, released behind the fix-up launch.  Two products on the same handle on different streams never
+// share it, and nothing synchronises the device.  The streamed level-1 path brings its own (one per call, sized for its
+// largest chunk) in mxg_csr_s::d_partial.
+int PartialLease::acquire(const mxg_csr_s *A, size_t bytes, cudaStream_t s)
 {
-    if (bytes <= h->partial_bytes) return MXG_OK;
-    // the previous buffer may still be in use by kernels in flight on other streams
-    MXG_CUDA_TRY(cudaDeviceSynchronize());
-    if (h->d_partial) {
-        MXG_CUDA_TRY(cudaFreeAsync(h->d_partial, h->stream));
-        h->d_partial = nullptr;
-        h->partial_bytes = 0;
+    stream = s;
+    if (A->d_partial && A->partial_bytes >= bytes) {
+        ptr = A->d_partial;
+        owned = false;
+        return MXG_OK;
     }
-    MXG_CUDA_TRY(cudaMallocAsync(&h->d_partial, bytes, h->stream));
-    MXG_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    h->partial_bytes = bytes;
+    MXG_CUDA_TRY(cudaMallocAsync(&ptr, bytes > 0 ? bytes : 16, s));
+    owned = true;
     return MXG_OK;
+}
+
+PartialLease::~PartialLease()
+{
+    if (owned && ptr) cudaFreeAsync(ptr, stream);
 }
 
 } // namespace mxg

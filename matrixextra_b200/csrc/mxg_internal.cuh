@@ -106,7 +106,8 @@ struct mxg_csr_s {
     int32_t *d_piece_row = nullptr;  // [n_pieces]
     int32_t *d_piece_k = nullptr;    // [n_pieces] piece number inside its row
 
-    // partial-sum workspace for long rows (grow-only)
+    // partial-sum workspace for long rows: only set on the chunk views of the streamed level-1 path (one workspace per
+    // call); products on real handles lease theirs per call (PartialLease)
     void *d_partial = nullptr;
     size_t partial_bytes = 0;
 
@@ -135,6 +136,7 @@ struct DeviceState {
     cudaStream_t d2h = nullptr;
     cudaStream_t p2p = nullptr; // pulls of the other devices' dense-operand slices over NVLink (multi-device calls)
     std::vector<cudaEvent_t> ev_pool; // timing-disabled events reused by mxg_dev_spmm_push
+    std::vector<cudaStream_t> push_streams; // one per destination of mxg_dev_spmm_push
     // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
     void *pin_base = nullptr;
     size_t pin_bytes = 0;
@@ -248,7 +250,15 @@ int peer_barrier_failed(int *failed);
 int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream);
 int convert_f64_to_f32(const double *d_src, float *d_dst, size_t n, cudaStream_t stream);
 int exclusive_scan_i32(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t stream); // out[i] = sum in[0..i)
-int ensure_partial(mxg_csr_s *h, size_t bytes);
+// workspace of the long-row partial sums for ONE product: leased on the call's stream, released when the lease dies
+// (stream-ordered, i.e. behind the fix-up launch that reads it)
+struct PartialLease {
+    void *ptr = nullptr;
+    bool owned = false;
+    cudaStream_t stream = nullptr;
+    int acquire(const mxg_csr_s *A, size_t bytes, cudaStream_t s);
+    ~PartialLease();
+};
 
 // spmm.cu
 int launch_spmm(const mxg_csr_s *A, int dtype, int out_layout, int n, const void *d_B, size_t ldb,

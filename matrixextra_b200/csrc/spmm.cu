@@ -768,9 +768,10 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.n_panels = 1;
     args.panel_width = A->K > 0 ? A->K : 1;
     if (n_dst == 1 && part == 0) MXG_TRY(plan_panels(const_cast<mxg_csr_s *>(A), (size_t)A->K * ldb * sizeof(T), stream, args));
+    PartialLease partial; // lives until the fix-up launch below has been enqueued
     if (args.n_pieces > 0) {
-        MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * (size_t)n * sizeof(T)));
-        args.partial = A->d_partial;
+        MXG_TRY(partial.acquire(A, (size_t)A->n_pieces * (size_t)n * sizeof(T), stream));
+        args.partial = partial.ptr;
     }
 
     int rc;
@@ -789,10 +790,10 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
         for (int d = 0; d < MXG_MAX_DST; d++) out.dst[d] = d < n_dst ? d_outs[d] : nullptr;
         if (colmajor)
             MXG_LAUNCH((k_spmm_fixup<T, true>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort, mcast);
+                       A->d_long_np, static_cast<const T *>(partial.ptr), out, ldc, A->d_abort, mcast);
         else
             MXG_LAUNCH((k_spmm_fixup<T, false>), A->n_long, 128, 0, stream, n, A->d_long_rows, A->d_long_first,
-                       A->d_long_np, static_cast<const T *>(A->d_partial), out, ldc, A->d_abort, mcast);
+                       A->d_long_np, static_cast<const T *>(partial.ptr), out, ldc, A->d_abort, mcast);
     }
     return MXG_OK;
 }

@@ -380,11 +380,12 @@ static int spmv_dispatch(const mxg_csr_s *A, const XT *d_x, const void *d_y, int
     args.partial = nullptr;
     args.partial_na = nullptr;
     args.abort = A->d_abort;
+    PartialLease partial; // lives until the fix-up launch below has been enqueued
     if (A->n_pieces > 0) {
         // doubles first, flags after (16 bytes per piece reserved)
-        MXG_TRY(ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * 16));
-        args.partial = static_cast<double *>(A->d_partial);
-        args.partial_na = reinterpret_cast<int *>(static_cast<double *>(A->d_partial) + A->n_pieces);
+        MXG_TRY(partial.acquire(A, (size_t)A->n_pieces * 16, stream));
+        args.partial = static_cast<double *>(partial.ptr);
+        args.partial_na = reinterpret_cast<int *>(static_cast<double *>(partial.ptr) + A->n_pieces);
     }
 
     int lpr = (int)options().spmv_lpr;
@@ -569,19 +570,31 @@ struct SvecValue<MXG_Y_BINARY> {
 };
 
 // dense image + bitmap of the sparse vector.  A repeated index keeps its FIRST occurrence, as the
-// reference's merge does for a sorted list (src/matmul.cpp:520-535: both cursors advance on a match).
-template <int YTYPE>
-__global__ void __launch_bounds__(256) k_svec_scatter(int n_y, const int32_t *__restrict__ yidx_base1,
-                                                      const typename SvecValue<YTYPE>::elem *__restrict__ yvals, int K,
-                                                      double *__restrict__ yd, unsigned *__restrict__ mask)
+// reference's merge does for a sorted list (src/matmul.cpp:520-535: both cursors advance on a match) — also when the
+// vector is not sorted and the repeats are far apart: pass 1 records, per column, the smallest position k that names
+// it (integer atomicMin: commutative, so the winner does not depend on scheduling), pass 2 lets exactly that entry
+// write the value.  `first` is a K-entry int scratch initialised to INT_MAX.
+__global__ void __launch_bounds__(256) k_svec_first(int n_y, const int32_t *__restrict__ yidx_base1, int K, int *__restrict__ first,
+                                                    unsigned *__restrict__ mask)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_y) return;
     const int c = yidx_base1[k] - 1;
     if (c < 0 || c >= K) return; // can never equal a column id of A
-    if (k > 0 && yidx_base1[k - 1] == yidx_base1[k]) return;
+    atomicMin(first + c, k);
     atomicOr(mask + (c >> 5), 1u << (c & 31));
-    yd[c] = SvecValue<YTYPE>::get(yvals, k);
+}
+
+template <int YTYPE>
+__global__ void __launch_bounds__(256) k_svec_scatter(int n_y, const int32_t *__restrict__ yidx_base1,
+                                                      const typename SvecValue<YTYPE>::elem *__restrict__ yvals, int K,
+                                                      double *__restrict__ yd, const int *__restrict__ first)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_y) return;
+    const int c = yidx_base1[k] - 1;
+    if (c < 0 || c >= K) return;
+    if (first[c] == k) yd[c] = SvecValue<YTYPE>::get(yvals, k);
 }
 
 struct SvecArgs {
@@ -689,10 +702,10 @@ __global__ void __launch_bounds__(SMASK ? 1024 : 256) k_spmv_svec(const SvecArgs
 }
 
 template <int YTYPE>
-static int svec_scatter(int n_y, const int32_t *d_yidx, const void *d_yvals, int K, double *yd, unsigned *mask, cudaStream_t stream)
+static int svec_scatter(int n_y, const int32_t *d_yidx, const void *d_yvals, int K, double *yd, const int *first, cudaStream_t stream)
 {
     MXG_LAUNCH((k_svec_scatter<YTYPE>), ceil_div_i(n_y, 256), 256, 0, stream, n_y, d_yidx,
-               static_cast<const typename SvecValue<YTYPE>::elem *>(d_yvals), K, yd, mask);
+               static_cast<const typename SvecValue<YTYPE>::elem *>(d_yvals), K, yd, first);
     return MXG_OK;
 }
 
@@ -710,16 +723,33 @@ int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_
     const int words = ceil_div_i(K, 32);
     double *yd = nullptr;
     unsigned *mask = nullptr;
+    int *first = nullptr;
+    // stream-ordered temporaries, released on every path
+    struct Temps {
+        cudaStream_t s;
+        void *q[3] = {nullptr, nullptr, nullptr};
+        ~Temps()
+        {
+            for (void *v : q)
+                if (v) cudaFreeAsync(v, s);
+        }
+    } temps{stream};
     MXG_CUDA_TRY(cudaMallocAsync(&yd, sizeof(double) * (size_t)K, stream));
+    temps.q[0] = yd;
     MXG_CUDA_TRY(cudaMallocAsync(&mask, sizeof(unsigned) * (size_t)words, stream));
+    temps.q[1] = mask;
+    MXG_CUDA_TRY(cudaMallocAsync(&first, sizeof(int) * (size_t)K, stream));
+    temps.q[2] = first;
     MXG_CUDA_TRY(cudaMemsetAsync(mask, 0, sizeof(unsigned) * (size_t)words, stream));
+    MXG_CUDA_TRY(cudaMemsetAsync(first, 0x7f, sizeof(int) * (size_t)K, stream)); // 0x7f7f7f7f: above every position
+    MXG_LAUNCH(k_svec_first, ceil_div_i(n_y, 256), 256, 0, stream, n_y, d_yidx_base1, K, first, mask);
     int rc = MXG_OK;
     switch (ytype) {
-    case MXG_Y_NUMERIC: rc = svec_scatter<MXG_Y_NUMERIC>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
-    case MXG_Y_INTEGER: rc = svec_scatter<MXG_Y_INTEGER>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
-    case MXG_Y_LOGICAL: rc = svec_scatter<MXG_Y_LOGICAL>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
-    case MXG_Y_FLOAT32: rc = svec_scatter<MXG_Y_FLOAT32>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
-    case MXG_Y_BINARY: rc = svec_scatter<MXG_Y_BINARY>(n_y, d_yidx_base1, d_yvals, K, yd, mask, stream); break;
+    case MXG_Y_NUMERIC: rc = svec_scatter<MXG_Y_NUMERIC>(n_y, d_yidx_base1, d_yvals, K, yd, first, stream); break;
+    case MXG_Y_INTEGER: rc = svec_scatter<MXG_Y_INTEGER>(n_y, d_yidx_base1, d_yvals, K, yd, first, stream); break;
+    case MXG_Y_LOGICAL: rc = svec_scatter<MXG_Y_LOGICAL>(n_y, d_yidx_base1, d_yvals, K, yd, first, stream); break;
+    case MXG_Y_FLOAT32: rc = svec_scatter<MXG_Y_FLOAT32>(n_y, d_yidx_base1, d_yvals, K, yd, first, stream); break;
+    case MXG_Y_BINARY: rc = svec_scatter<MXG_Y_BINARY>(n_y, d_yidx_base1, d_yvals, K, yd, first, stream); break;
     default: rc = fail(MXG_ERR_ARG, "svec: bad ytype %d", ytype);
     }
     if (rc == MXG_OK) {
@@ -740,10 +770,11 @@ int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_
         args.partial = nullptr;
         args.partial_na = nullptr;
         args.abort = A->d_abort;
+        PartialLease partial;
         if (A->n_pieces > 0) {
-            rc = ensure_partial(const_cast<mxg_csr_s *>(A), (size_t)A->n_pieces * 16);
-            args.partial = static_cast<double *>(A->d_partial);
-            args.partial_na = reinterpret_cast<int *>(static_cast<double *>(A->d_partial) + A->n_pieces);
+            rc = partial.acquire(A, (size_t)A->n_pieces * 16, stream);
+            args.partial = static_cast<double *>(partial.ptr);
+            args.partial_na = reinterpret_cast<int *>(static_cast<double *>(partial.ptr) + A->n_pieces);
         }
         int lpr = (int)options().spmv_lpr;
         if (lpr != 4 && lpr != 8 && lpr != 16 && lpr != 32) {
@@ -781,9 +812,7 @@ int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_
             rc = body();
         }
     }
-    cudaFreeAsync(yd, stream);
-    cudaFreeAsync(mask, stream);
-    return rc;
+    return rc; // (temps released by ~Temps)
 }
 
 } // namespace mxg

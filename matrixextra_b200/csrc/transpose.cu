@@ -23,6 +23,7 @@
 #include "mxg_internal.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace mxg {
 
@@ -314,15 +315,32 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     const double *x64 = h64 ? d_x64 + base : nullptr;
     const float *x32 = h32 ? d_x32 + base : nullptr;
 
+    // stream-ordered temporaries, released on every path (an out-of-memory error half way must not strand the rest)
+    struct Temps {
+        cudaStream_t s;
+        std::vector<void *> q;
+        int alloc(void **out, size_t bytes)
+        {
+            *out = nullptr;
+            MXG_CUDA_TRY(cudaMallocAsync(out, bytes > 0 ? bytes : 16, s));
+            q.push_back(*out);
+            return MXG_OK;
+        }
+        ~Temps()
+        {
+            for (void *v : q) cudaFreeAsync(v, s);
+        }
+    } temps{stream, {}};
+
     // p2 = exclusive scan of the per-column counts (K+1 slots so the scan output is the full pointer array); the
     // counts are accumulated by the LAST radix pass, where equal column ids sit next to each other in a tile
     int32_t *d_count = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_count, sizeof(int32_t) * ((size_t)K + 1), stream));
+    MXG_TRY(temps.alloc((void **)&d_count, sizeof(int32_t) * ((size_t)K + 1)));
     MXG_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * ((size_t)K + 1), stream));
 
     // row ids per entry
     int32_t *d_rowid = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_rowid, sizeof(int32_t) * n, stream));
+    MXG_TRY(temps.alloc((void **)&d_rowid, sizeof(int32_t) * n));
     {
         const double mean = (double)nnz / (double)m;
         // power-law rows: the median is about half the mean, so teams of (mean / 2) lanes rounded down to a power of two
@@ -347,15 +365,15 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     const int ntiles = ceil_div_i(nnz, RS_TILE);
     const size_t hist_n = ((size_t)1 << digit_bits) * (size_t)ntiles;
     int32_t *d_hist = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_hist, sizeof(int32_t) * hist_n, stream));
+    MXG_TRY(temps.alloc((void **)&d_hist, sizeof(int32_t) * hist_n));
     // ping-pong record buffers (only as many as the pass count needs)
     struct Rec { int32_t *key = nullptr, *row = nullptr; double *x64 = nullptr; float *x32 = nullptr; } buf[2];
     const int nbuf = passes >= 3 ? 2 : (passes == 2 ? 1 : 0);
     for (int b = 0; b < nbuf; b++) {
-        MXG_CUDA_TRY(cudaMallocAsync(&buf[b].key, sizeof(int32_t) * n, stream));
-        MXG_CUDA_TRY(cudaMallocAsync(&buf[b].row, sizeof(int32_t) * n, stream));
-        if (h64) MXG_CUDA_TRY(cudaMallocAsync(&buf[b].x64, sizeof(double) * n, stream));
-        if (h32) MXG_CUDA_TRY(cudaMallocAsync(&buf[b].x32, sizeof(float) * n, stream));
+        MXG_TRY(temps.alloc((void **)&buf[b].key, sizeof(int32_t) * n));
+        MXG_TRY(temps.alloc((void **)&buf[b].row, sizeof(int32_t) * n));
+        if (h64) MXG_TRY(temps.alloc((void **)&buf[b].x64, sizeof(double) * n));
+        if (h32) MXG_TRY(temps.alloc((void **)&buf[b].x32, sizeof(float) * n));
     }
 
     RadixIO io;
@@ -390,16 +408,7 @@ int csr2csc_device(int m, int K, int64_t nnz, const int32_t *d_p, const int32_t 
     }
 
     MXG_TRY(exclusive_scan_i32(d_count, d_p2, (size_t)K + 1, stream));
-    MXG_CUDA_TRY(cudaFreeAsync(d_count, stream));
-    MXG_CUDA_TRY(cudaFreeAsync(d_hist, stream));
-    for (int b = 0; b < nbuf; b++) {
-        MXG_CUDA_TRY(cudaFreeAsync(buf[b].key, stream));
-        MXG_CUDA_TRY(cudaFreeAsync(buf[b].row, stream));
-        if (buf[b].x64) MXG_CUDA_TRY(cudaFreeAsync(buf[b].x64, stream));
-        if (buf[b].x32) MXG_CUDA_TRY(cudaFreeAsync(buf[b].x32, stream));
-    }
-    MXG_CUDA_TRY(cudaFreeAsync(d_rowid, stream));
-    return MXG_OK;
+    return MXG_OK; // (temporaries released by ~Temps, stream-ordered behind the last kernel)
 }
 
 } // namespace mxg

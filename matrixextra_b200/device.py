@@ -107,6 +107,12 @@ class DeviceCSR:
         _lib.call("mxg_dev_spmm_bcast", self._h, int(dtype), int(out_layout), MXG_ROWS_CONTIGUOUS, int(n), _dptr(B_t),
                   int(ldb), len(dst_ptrs), arr, int(ldc), _stream_ptr(stream))
 
+    def spmm_rows(self, B_t, out_ptr, n, dtype, out_layout, ldc, r0=0, r1=0, pieces=False, ldb=None, stream=None):
+        """Rows [r0, r1) of the product without their long rows, or (``pieces``) only the long rows; ``out_ptr`` is the
+        raw device address of the FULL result's origin."""
+        _lib.call("mxg_dev_spmm_rows", self._h, int(dtype), int(out_layout), int(n), _dptr(B_t), int(ldb or n),
+                  C.c_void_p(int(out_ptr)), int(ldc), int(r0), int(r1), 1 if pieces else 0, _stream_ptr(stream))
+
     def spmm_push(self, B_t, dst_ptrs, n, dtype, out_layout=MXG_ROWS_CONTIGUOUS, ldb=None, ldc=None, stream=None):
         """Product in row slices into ``dst_ptrs[0]``; every finished slice is pushed to the other destinations by the
         copy engines (NVLink peer copies) while the next slice is computed."""

@@ -220,3 +220,76 @@ class McastResult:
 
     def barrier(self):
         self.handle.barrier()
+
+
+class PipelinedColumnMajorGather:
+    """Row-sharded ``A %*% B`` with a COLUMN-MAJOR (R layout) result gathered to every GPU (BASELINE cfg5's shape).
+
+    A rank's block of a column-major (G*m x n) matrix is n strided column segments, which neither peer stores (128-byte
+    segments) nor copy-engine pushes (2-D peer copies) move at NVLink speed on 8 GPUs; NCCL's all-gather does, on
+    contiguous buffers.  So the product is issued in ``slices`` row slices (long rows first, ``DeviceCSR.spmm_rows``)
+    straight into the rank's rows of the global result, and behind every slice
+      * the COMM stream packs the slice into a contiguous (n x rows) buffer (one 2-D copy on a copy engine) and
+        all-gathers it with NCCL,
+      * the UNPACK stream moves the G - 1 received slices into their rows of the global result (2-D copies on copy
+        engines; the rank's own slice is already in place),
+    while the next slice is being computed: the step costs about max(product, all-gather) instead of their sum."""
+
+    def __init__(self, A, n, dtype, torch_dtype, dist, rank, world, slices=8):
+        import torch
+        self.A, self.n, self.dtype, self.dist, self.rank, self.world = A, n, dtype, dist, rank, world
+        m = A.m
+        self.bounds = [m * k // slices for k in range(slices + 1)]
+        rows_max = max(self.bounds[k + 1] - self.bounds[k] for k in range(slices))
+        self.out_all = torch.empty((n, world * m), device="cuda", dtype=torch_dtype)  # column-major (world*m x n), ldc = world*m
+        self.pack = [torch.empty(n * rows_max, device="cuda", dtype=torch_dtype) for _ in range(2)]
+        self.stage = [torch.empty(world * n * rows_max, device="cuda", dtype=torch_dtype) for _ in range(2)]
+        self.comm, self.unpack = torch.cuda.Stream(), torch.cuda.Stream()
+        self.ev_done = [torch.cuda.Event() for _ in range(slices)]
+        self.ev_gathered = [torch.cuda.Event() for _ in range(slices)]
+        self.ev_unpacked = [torch.cuda.Event() for _ in range(slices)]
+
+    def step(self, B_t):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+        from ._lib import MXG_COLS_CONTIGUOUS
+        A, n, G, m = self.A, self.n, self.world, self.A.m
+        ldc = G * m
+        es = self.out_all.element_size()
+        base = self.out_all.data_ptr()
+        origin = base + self.rank * m * es  # this rank's first row inside column 0
+        main = torch.cuda.current_stream()
+
+        def copy2d(dst, dpitch, src, spitch, width, height, stream):
+            _lib.call("mxg_dev_copy_2d", C.c_void_p(dst), dpitch, C.c_void_p(src), spitch, width, height, C.c_void_p(stream.cuda_stream))
+
+        if A.n_pieces > 0:
+            A.spmm_rows(B_t, origin, n, self.dtype, MXG_COLS_CONTIGUOUS, ldc, pieces=True)
+        self.comm.wait_stream(main)
+        self.unpack.wait_stream(main)
+        S = len(self.bounds) - 1
+        for k in range(S):
+            r0, r1 = self.bounds[k], self.bounds[k + 1]
+            rows = r1 - r0
+            A.spmm_rows(B_t, origin, n, self.dtype, MXG_COLS_CONTIGUOUS, ldc, r0, r1)
+            self.ev_done[k].record(main)
+            b = k % 2
+            send = self.pack[b][: n * rows]
+            recv = self.stage[b][: G * n * rows]
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_done[k])
+                if k >= 2:
+                    self.comm.wait_event(self.ev_unpacked[k - 2])  # the staging buffer's previous slice has left it
+                copy2d(send.data_ptr(), rows * es, origin + r0 * es, ldc * es, rows * es, n, self.comm)
+                self.dist.all_gather_into_tensor(recv, send)
+                self.ev_gathered[k].record(self.comm)
+            self.unpack.wait_event(self.ev_gathered[k])
+            for g in range(G):
+                if g != self.rank:
+                    copy2d(base + (g * m + r0) * es, ldc * es, recv.data_ptr() + g * n * rows * es, rows * es, rows * es, n, self.unpack)
+            self.ev_unpacked[k].record(self.unpack)
+        main.wait_stream(self.comm)
+        main.wait_stream(self.unpack)

@@ -143,6 +143,27 @@ def test_svec_edge_cases(rx, port):
     assert rel_err(got, want) <= FP64_TOL
 
 
+def test_svec_unsorted_vector_with_distant_repeats_keeps_the_first(rx, port):
+    # mxgpu.h: "a repeated index keeps its first entry; y need not be sorted" — also when the repeats are far apart
+    # (resolved with an integer atomicMin over the positions: the same entry wins on every run)
+    A = rsparsematrix(400, 300, 0.2, 61)
+    p, j, x = A.indptr, A.indices, A.data
+    rng = np.random.default_rng(61)
+    base = rng.choice(300, 120, replace=False).astype(np.int32) + 1
+    yi = np.concatenate([base, base[::-1][:80], base[:40]]).astype(np.int32)  # every index up to three times, far apart
+    yv = rng.standard_normal(yi.size)
+    first = {}
+    for k, c in enumerate(yi):
+        first.setdefault(int(c), k)
+    keep = np.array(sorted(first.values()))
+    order = np.argsort(yi[keep], kind="stable")
+    want = port.matmul_csr_svec_numeric(p, j, x, yi[keep][order], yv[keep][order])  # the sorted, de-duplicated vector
+    runs = [rx.matmul_csr_svec_numeric(p, j, x, yi, yv, ncols=300) for _ in range(5)]
+    assert rel_err(runs[0], want) <= FP64_TOL
+    for r in runs[1:]:
+        assert np.array_equal(r, runs[0])
+
+
 def test_svec_s4_dispatch(port):
     # R/matmul.R:595-646 through the S4 mirror
     from matrixextra_b200 import dgRMatrix, matmul, sparseVector

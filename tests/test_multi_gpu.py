@@ -38,7 +38,7 @@ def test_fused_allgather_bit_identical_to_nccl(world):
     assert report["world"] == world and report["all_ranks_ok"], report
     checked = report["rank0"]
     for key in ("f32_n64_rows", "f32_n64_cols", "f64_n24_rows", "f64_n24_cols", "f32_n64_rows_push", "f32_n64_cols_push",
-                "f64_n24_rows_push", "f64_n24_cols_push", "spmv"):
+                "f64_n24_rows_push", "f64_n24_cols_push", "f32_n64_cols_pipelined", "f64_n24_cols_pipelined", "spmv"):
         assert checked.get(key) is True, report
     if not checked.get("mcast_unavailable"):
         assert checked.get("f32_n64_rows_mcast") is True and checked.get("f64_n24_rows_mcast") is True, report

@@ -72,6 +72,21 @@ def main():
             report[f"{name}_{lname}_push"] = bool(ok) and not res.failed()
             del full
             res.close(dist)
+    # column-major results gathered by the pipelined pack / NCCL all-gather / unpack behind every row slice
+    from matrixextra_b200.sharded import PipelinedColumnMajorGather
+    for name, dtype, tdt, n in (("f32_n64", MXG_F32, torch.float32, 64), ("f64_n24", MXG_F64, torch.float64, 24)):
+        B = torch.randn(K, n, device="cuda", dtype=tdt, generator=gen)
+        pipe = PipelinedColumnMajorGather(A, n, dtype, tdt, dist, rank, world, slices=5)
+        pipe.out_all.fill_(float("nan"))
+        for _ in range(2):
+            pipe.step(B)
+        torch.cuda.synchronize()
+        local_out = torch.empty(m * n, device="cuda", dtype=tdt)
+        A.spmm(B, local_out, n, dtype, MXG_COLS_CONTIGUOUS)
+        gathered = torch.empty(world * m * n, device="cuda", dtype=tdt)
+        dist.all_gather_into_tensor(gathered, local_out)
+        report[f"{name}_cols_pipelined"] = bool(torch.equal(pipe.out_all.view(n, world, m), gathered.view(world, n, m).permute(1, 0, 2)))
+        del pipe
     # the same through NVLS multicast (rows-contiguous results): one multimem.st per row, replicated by the switch
     try:
         for name, dtype, tdt, n in (("f32_n64", MXG_F32, torch.float32, 64), ("f64_n24", MXG_F64, torch.float64, 24)):
