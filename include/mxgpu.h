@@ -376,6 +376,13 @@ int mxg_synth_csr(int m, int K, int64_t target_nnz, int row_model, int col_model
 int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
                          float *d_sink, long long *gathers_done, void *stream);
 
+/* The same random-row gathers issued through the TMA unit: one cp.async.bulk.tensor.2d ... tile::gather4 per four rows
+ * (one thread, destination shared memory, completion on an mbarrier), 8 operations in flight per warp — the Blackwell
+ * alternative to LDG.128 gathers for the dense-operand rows of K1/K2, measured side by side with mxg_dev_gather_probe.
+ * d_table 128-byte aligned, rows < 2^31; d_sink: 2 floats (d_sink[1] is set to -1 when a gather never completed). */
+int mxg_dev_tma_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed,
+                             float *d_sink, long long *gathers_done, void *stream);
+
 /* Measurement probe for K3: the handle's column ids streamed 16 bytes per thread with the row structure taken away.
  * mode 0: ids only; 1: + an 8-byte gather of d_y[j] per entry (plain loads); 2: the same through the texture path;
  * 3: ids + float64 values + texture gathers + FMA (12 streamed bytes and one gather per entry, what the SpMV must

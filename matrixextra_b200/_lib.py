@@ -87,6 +87,7 @@ _SIGNATURES = {
     "mxg_host_pack_indices": [_vp, _sz, _i32, _vp, C.POINTER(_sz), C.POINTER(C.c_int)],
     "mxg_last_call_bytes": [C.POINTER(_sz), C.POINTER(_sz)],
     "mxg_host_chunk_plan": [_i32, _vp, _sz, _vp, _i32] + [C.POINTER(C.c_int)] * 4,
+    "mxg_dev_tma_gather_probe": [_i32, _vp, _sz, C.c_longlong, C.c_uint64, _vp, C.POINTER(C.c_longlong), _vp],
     "mxg_dev_spmv_probe": [_vp, _i32, _vp, _vp, _vp],
     "mxg_synth_csr": [_i32, _i32, _i64, _i32, _i32, C.c_uint64, _i32, _vp, C.POINTER(_vp)],
 }

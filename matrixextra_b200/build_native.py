@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(CSRC, "build")
-SOURCES = ["capi.cu", "layout.cu", "pipeline.cu", "spmm.cu", "spmv.cu", "transpose.cu", "synth.cu", "rowops.cu", "hoststage.cu", "residency.cu"]
+SOURCES = ["capi.cu", "layout.cu", "pipeline.cu", "spmm.cu", "spmv.cu", "transpose.cu", "synth.cu", "rowops.cu", "hoststage.cu", "residency.cu", "tmaprobe.cu"]
 HEADERS = ["mxg_internal.cuh", os.path.join("..", "..", "include", "mxgpu.h")]
 LIB = os.path.join(CSRC, "libmxgpu.so")
 

@@ -866,6 +866,14 @@ int mxg_dev_gather_probe(int row_bytes, const void *d_table, size_t rows, long l
     return MXG_OK;
 }
 
+int mxg_dev_tma_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed, float *d_sink,
+                             long long *gathers_done, void *stream)
+{
+    MXG_TRY(ensure_device_ready());
+    if (!d_table || !d_sink) return fail(MXG_ERR_ARG, "tma_gather_probe: NULL buffer");
+    return tma_gather_probe(row_bytes, d_table, rows, gathers, seed, d_sink, gathers_done, static_cast<cudaStream_t>(stream));
+}
+
 int mxg_dev_spmv_probe(mxg_csr_t A, int mode, const double *d_y, double *d_sink, void *stream)
 {
     MXG_TRY(ensure_device_ready());

@@ -279,6 +279,9 @@ void texture_cache_clear(); // cached texture objects over dense vectors (mxg_tr
 // CSR x sparse vector (indices base 1, K = columns covered by the presence bitmap), double result
 int launch_spmv_svec(const mxg_csr_s *A, int ytype, int K, int n_y, const int32_t *d_yidx_base1, const void *d_yvals,
                      double *d_out, cudaStream_t stream);
+// tmaprobe.cu: random-row gathers through the TMA unit (tile::gather4), measurement only
+int tma_gather_probe(int row_bytes, const void *d_table, size_t rows, long long gathers, uint64_t seed, float *d_sink,
+                     long long *gathers_done, cudaStream_t stream);
 // rowops.cu
 int launch_mul_csr_dense(const mxg_csr_s *A, int dtype, const void *d_dense, double *d_out, cudaStream_t stream);
 int launch_mul_csr_dvec(const mxg_csr_s *A, const double *d_dvec, size_t len, double *d_out, cudaStream_t stream);

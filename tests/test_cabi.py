@@ -94,3 +94,63 @@ def test_header_is_plain_c_and_cxx():
                    check=True, env=env)
     text = open(hdr).read()
     assert "torch" not in text.replace("torch symmetric memory", "").replace("torch.distributed._symmetric_memory", "")
+
+
+def test_new_entry_points_fail_loudly_without_a_device():
+    """mxg_set_devices, the handle products with host operands and the operand cache have no CPU path either."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from matrixextra_b200 import _lib, rcpp_exports as rx
+    with pytest.raises(_lib.MxgError) as ei:
+        _lib.call("mxg_set_devices", 2)
+    assert ei.value.code == _lib.MXG_ERR_CUDA
+    with pytest.raises(_lib.MxgError) as ei:
+        rx.as_gpu_csr([0, 1], [0], [1.0], 1)
+    assert ei.value.code == _lib.MXG_ERR_CUDA
+    _lib.set_option("cache_mb", 64)
+    try:
+        with pytest.raises(_lib.MxgError) as ei:
+            rx.tcrossprod_csr_dense_numeric([0, 1], [0], [1.0], np.ones((2, 1), order="F"))
+        assert ei.value.code == _lib.MXG_ERR_CUDA
+    finally:
+        _lib.set_option("cache_mb", 0)
+    # the cache bookkeeping itself needs no device
+    hits, misses, nbytes, entries = C.c_ulonglong(), C.c_ulonglong(), C.c_size_t(), C.c_int()
+    _lib.call("mxg_cache_stats", C.byref(hits), C.byref(misses), C.byref(nbytes), C.byref(entries))
+    assert nbytes.value == 0 and entries.value == 0
+    n = C.c_int(0)
+    _lib.call("mxg_get_devices", C.byref(n))
+    assert n.value == 1
+
+
+def test_r_side_artefacts_are_files_and_apply():
+    """rglue/: the glue sources, the R methods file and the patch for the two reference files that change."""
+    for f in ("matmul_gpu_glue.cpp", "rowops_gpu_glue.cpp", "handle_gpu_glue.cpp", "matmul_gpu_methods.R", "mxgpu.patch"):
+        assert os.path.getsize(os.path.join(ROOT, "rglue", f)) > 500, f
+    r = open(os.path.join(ROOT, "rglue", "matmul_gpu_methods.R")).read()
+    for sig in ('setMethod("crossprod", signature(x="RsparseMatrix", y="matrix")', 'signature(x="CsparseMatrix", y="matrix")',
+                'signature(x="matrix", y="RsparseMatrix")', 'setClass("gpuRsparse"', "as.gpu.csr <- function", "mxgpu.settings <- function"):
+        assert sig in r, sig
+    # every glue export the R file calls exists in the glue sources
+    glue = "".join(open(os.path.join(ROOT, "rglue", f)).read() for f in ("matmul_gpu_glue.cpp", "handle_gpu_glue.cpp"))
+    for fn in ("crossprod_csr_dense_numeric", "crossprod_csr_dense_float32", "as_gpu_csr", "gpu_csr_free", "gpu_csr_tcrossprod_dense_numeric",
+               "gpu_csr_tcrossprod_dense_float32", "gpu_csr_dense_tcrossprod_numeric", "gpu_csr_dense_tcrossprod_float32",
+               "gpu_csr_crossprod_dense_numeric", "gpu_csr_crossprod_dense_float32", "gpu_csr_dvec_numeric", "mxgpu_configure"):
+        assert fn + "(" in r and fn + "(" in glue, fn
+    patch = open(os.path.join(ROOT, "rglue", "mxgpu.patch")).read()
+    assert "-DMATRIXEXTRA_USE_MXGPU" in patch and "#ifndef MATRIXEXTRA_USE_MXGPU" in patch and "-lmxgpu" in patch
+    ref = "/root/reference"
+    if os.path.isdir(os.path.join(ref, "src")):  # build container only: the patch applies to the reference tree as it is
+        import shutil
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            shutil.copytree(os.path.join(ref, "src"), os.path.join(tmp, "src"))
+            subprocess.run(["patch", "-p1", "-s", "-i", os.path.join(ROOT, "rglue", "mxgpu.patch")], cwd=tmp, check=True)
+            fenced = open(os.path.join(tmp, "src", "matmul.cpp")).read()
+            a, b = fenced.index("#ifndef MATRIXEXTRA_USE_MXGPU"), fenced.index("#endif /* MATRIXEXTRA_USE_MXGPU */")
+            inside = fenced[a:b]
+            for name in ("gemm_csr_drm_as_drm", "gemm_csr_drm_as_dcm", "matmul_dense_csc_numeric", "tcrossprod_csr_dense_float32",
+                         "matmul_csr_dvec_float32"):
+                assert name in inside, name
+            assert "matmul_colvec_by_scolvecascsr" not in inside and "matmul_colvec_by_scolvecascsr" in fenced[b:]

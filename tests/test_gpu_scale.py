@@ -143,3 +143,27 @@ def test_result_with_more_than_2_31_elements(ref, layout):
     if empty.size:
         assert not rows_of(int(empty[0]), int(empty[0]) + 1).any()
     A.free()
+
+
+def test_host_twin_generates_the_device_generators_matrix():
+    """bench.py's reference arm multiplies the matrix of oracle/mx_synth.c; the GPU arm that of csrc/synth.cu.  Same
+    recipe, same counters: identical row lengths except where pow() differs in the last ulp, identical columns and values
+    wherever the row lengths agree."""
+    from matrixextra_b200._lib import MXG_KEEP_F64
+    from matrixextra_b200.device import DeviceCSR
+    from oracle.cpu_oracle import synth_csr_host
+    for row_model, col_model, m, K, nnz, seed in ((1, 1, 200_000, 100_000, 10_000_000, 1003), (0, 0, 10_000, 5_000, 500_000, 1001)):
+        A = DeviceCSR.synth(m, K, nnz, row_model, col_model, seed=seed, keep=MXG_KEEP_F64)
+        pd, jd, xd = A.to_host()
+        A.free()
+        ph, jh, xh = synth_csr_host(m, K, nnz, row_model, col_model, seed)
+        assert abs(int(pd[-1]) - int(ph[-1])) <= 64
+        same_len = np.diff(pd) == np.diff(ph)
+        assert same_len.mean() > 0.999
+        if np.array_equal(pd, ph):
+            assert np.array_equal(jd, jh) and np.array_equal(xd, xh)
+        else:  # compare the rows whose lengths agree
+            rows = np.flatnonzero(same_len)[:20000]
+            for r in rows[:: max(1, rows.size // 2000)]:
+                assert np.array_equal(jd[pd[r]:pd[r + 1]], jh[ph[r]:ph[r + 1]])
+                assert np.array_equal(xd[pd[r]:pd[r + 1]], xh[ph[r]:ph[r + 1]])

@@ -162,3 +162,27 @@ def test_rowvec_by_csc_restatement_equals_reference(port, ref):
                 dense = np.zeros((K, ncols))
                 dense[Y.indices, np.repeat(np.arange(ncols), np.diff(Y.indptr))] = 1.0
             assert np.allclose(a.ravel(), rv.astype(np.float64) @ dense, rtol=1e-5, atol=1e-5)
+
+
+def test_host_twin_of_the_synthetic_generator():
+    """oracle/mx_synth.c (what bench.py's reference arm multiplies): exact entry counts, sorted unique in-range columns,
+    the power-law tail and cap, values in [-1, 1), determinism."""
+    from oracle.cpu_oracle import synth_csr_host
+    p, j, x = synth_csr_host(10_000, 5_000, 500_000, row_model=0, col_model=0, seed=1001)  # BASELINE cfg1
+    lens = np.diff(p)
+    assert p[0] == 0 and p[-1] == 500_000 and lens.min() >= 40 and lens.max() <= 60
+    m, K, nnz = 40_000, 30_000, 2_000_000
+    for col_model in (0, 1):
+        p, j, x = synth_csr_host(m, K, nnz, row_model=1, col_model=col_model, seed=1003)
+        lens = np.diff(p)
+        assert p[0] == 0 and abs(int(p[-1]) - nnz) <= nnz // 1000 and lens.min() >= 0 and lens.max() <= K
+        assert lens.max() > 20 * lens.mean()  # heavy tail
+        assert j.min() >= 0 and j.max() < K and np.abs(x).max() < 1.0
+        inside = np.ones(j.size, dtype=bool)
+        starts = p[1:-1]
+        inside[starts[starts < j.size]] = False
+        assert (np.diff(j.astype(np.int64), prepend=-1)[inside] > 0).all()  # sorted and unique inside every row
+        if col_model == 1:  # popular low columns: the first fifth of the columns holds far more than a fifth of the entries
+            assert (j < K // 5).mean() > 0.35
+        p2, j2, x2 = synth_csr_host(m, K, nnz, row_model=1, col_model=col_model, seed=1003)
+        assert np.array_equal(p, p2) and np.array_equal(j, j2) and np.array_equal(x, x2)

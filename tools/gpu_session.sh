@@ -14,8 +14,8 @@ for w in $WHAT; do
   case $w in
     smoke) timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" ;;
     tests) timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/${TAG}_tests.log ;;
-    bench) timeout 900 python bench.py --steps 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json ;;
-    benchref) timeout 600 python bench.py --impl reference --steps 3 > gpurun_out/${TAG}_benchref.json 2> gpurun_out/${TAG}_benchref.err; echo "benchref rc=$?"; cat gpurun_out/${TAG}_benchref.json ;;
+    bench) timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench.json ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_benchref.json 2> gpurun_out/${TAG}_benchref.err; echo "benchref rc=$?"; cat gpurun_out/${TAG}_benchref.json ;;
     cfg5) timeout 900 python bench.py --workload cfg5 --steps 3 --skip-e2e --skip-cpu --others '' > gpurun_out/${TAG}_bench_cfg5.json 2> gpurun_out/${TAG}_bench_cfg5.err; echo "cfg5 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_cfg5.json; tail -3 gpurun_out/${TAG}_bench_cfg5.err ;;
     cfg1) timeout 300 python bench.py --workload cfg1 --steps 20 --others '' > gpurun_out/${TAG}_bench_cfg1.json 2> gpurun_out/${TAG}_bench_cfg1.err; echo "cfg1 rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_cfg1.json ;;
     sweep) timeout 900 python tools/sweep.py > gpurun_out/${TAG}_sweep.jsonl 2> gpurun_out/${TAG}_sweep.err; echo "sweep rc=$?"; tail -3 gpurun_out/${TAG}_sweep.err ;;

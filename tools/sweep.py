@@ -106,6 +106,31 @@ def main():
                      gather_TBps=done.value * row_bytes / ms / 1e9, Ggathers_per_s=done.value / ms / 1e6)
             del table
 
+    if "tmagather" in what:
+        # the same random-row gathers through LDG.128 (mxg_dev_gather_probe) and through the TMA unit (tile::gather4)
+        import ctypes as C
+        sink = torch.zeros(4, device="cuda", dtype=torch.float32)
+        for table_mb in (32, 256, 2048):
+            table = torch.randn(table_mb * (1 << 20) // 4, device="cuda", dtype=torch.float32)
+            for row_bytes in (128, 256, 512):
+                rows = table.numel() * 4 // row_bytes
+                gathers = 200_000_000 * 256 // row_bytes // 2
+                for name in ("mxg_dev_gather_probe", "mxg_dev_tma_gather_probe"):
+                    done = C.c_longlong(0)
+
+                    def probe():
+                        _lib.call(name, row_bytes, C.c_void_p(table.data_ptr()), rows, gathers, 12345,
+                                  C.c_void_p(sink.data_ptr()), C.byref(done), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                    try:
+                        sink.zero_()
+                        ms = _time_ms(probe, args.steps, 3)
+                        emit(case="gather_ldg_vs_tma", path="TMA tile::gather4" if "tma" in name else "LDG.128", table_mb=table_mb,
+                             row_bytes=row_bytes, gathers=done.value, ms=ms, gather_TBps=done.value * row_bytes / ms / 1e9,
+                             timed_out=bool(sink[1].item() != 0))
+                    except Exception as e:  # noqa: BLE001
+                        emit(case="gather_ldg_vs_tma", path=name, table_mb=table_mb, row_bytes=row_bytes, error=str(e)[:300])
+            del table
+
     if "l2res" in what:
         # the same product with a dense operand that fits L2: the ceiling column-panel tiling could reach
         for KK in (62_500, 125_000, 250_000, 500_000):
