@@ -19,6 +19,11 @@
  *     R matrix, src/matmul.cpp:197/261/323/389).
  * There is no CPU fallback: without a CUDA device every compute entry point fails with
  * MXG_ERR_CUDA.
+ * Threads: every entry point that takes HOST buffers (level 1, mxg_csr_upload, the mxg_csr_*_host handle products,
+ * mxg_set_devices, mxg_cache_clear) runs under one process-wide lock — they share per-device streams, the page-locked
+ * staging arena and the operand cache, and the reference's caller is a single R thread.  mxg_last_error() and
+ * mxg_last_call_bytes() are per calling thread.  Device-buffer (mxg_dev_*) products are asynchronous on the caller's
+ * stream and may run concurrently on one handle from different streams.
  */
 #ifndef MXGPU_H
 #define MXGPU_H

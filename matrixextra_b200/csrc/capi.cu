@@ -539,6 +539,7 @@ int mxg_trim(void)
 
 int mxg_csr_upload(int m, int K, const int32_t *p, const int32_t *j, const double *x, int keep, mxg_csr_t *handle)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (!handle) return fail(MXG_ERR_ARG, "handle is NULL");
     *handle = nullptr;
     DeviceState *st;
@@ -1076,6 +1077,7 @@ int mxg_dev_spmv_svec(mxg_csr_t A, int ytype, int n_y, const int32_t *d_yidx_bas
 int mxg_spmv_csr_svec(int ytype, int m, int K, const int32_t *p, const int32_t *j, const double *x, int n_y,
                       const int32_t *y_idx_base1, const void *y_vals, double *out)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (ytype < MXG_Y_NUMERIC || ytype > MXG_Y_BINARY) return fail(MXG_ERR_ARG, "bad ytype %d", ytype);
     if (m < 0 || n_y < 0) return fail(MXG_ERR_ARG, "svec: negative size");
     if (!p) return fail(MXG_ERR_ARG, "csr: indptr is NULL");
@@ -1203,6 +1205,7 @@ struct DevTemps {
 
 int mxg_check_valid_csr(int m, int ncols, const int32_t *p, const int32_t *j, int64_t nnz, int *code)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (!code || m < 0 || nnz < 0 || !p || (nnz > 0 && !j)) return fail(MXG_ERR_ARG, "check_valid_csr: bad argument");
     DeviceState *st;
     MXG_TRY(current_state(&st));
@@ -1215,6 +1218,7 @@ int mxg_check_valid_csr(int m, int ncols, const int32_t *p, const int32_t *j, in
 
 int mxg_rows_sorted(int m, const int32_t *p, const int32_t *j, int *sorted)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (!sorted || m < 0 || !p) return fail(MXG_ERR_ARG, "rows_sorted: bad argument");
     *sorted = 1;
     const int64_t nnz = (int64_t)p[m] - p[0];
@@ -1231,6 +1235,7 @@ int mxg_rows_sorted(int m, const int32_t *p, const int32_t *j, int *sorted)
 
 int mxg_sort_csr_indices(int m, const int32_t *p, int32_t *j, double *x)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (m < 0 || !p) return fail(MXG_ERR_ARG, "sort_csr_indices: bad argument");
     if (m == 0 || p[m] <= 0) return MXG_OK;
     if (!j) return fail(MXG_ERR_ARG, "sort_csr_indices: indices is NULL");
@@ -1264,6 +1269,7 @@ int mxg_sort_csr_indices(int m, const int32_t *p, int32_t *j, double *x)
 int mxg_mul_csr_dense(int dtype, int m, int K, const int32_t *p, const int32_t *j, const double *x, const void *dense,
                       double *values_out)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (dtype < MXG_Y_NUMERIC || dtype > MXG_Y_FLOAT32) return fail(MXG_ERR_ARG, "mul_csr_dense: bad element type %d", dtype);
     if (m < 0 || K < 0 || !p) return fail(MXG_ERR_ARG, "mul_csr_dense: bad argument");
     const int64_t nnz = (int64_t)p[m] - p[0];
@@ -1295,6 +1301,7 @@ int mxg_mul_csr_dense(int dtype, int m, int K, const int32_t *p, const int32_t *
 int mxg_mul_csr_dvec(int m, int K, const int32_t *p, const int32_t *j, const double *x, const double *dvec, size_t len,
                      double *values_out)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (m < 0 || K < 0 || !p) return fail(MXG_ERR_ARG, "mul_csr_dvec: bad argument");
     const int64_t nnz = (int64_t)p[m] - p[0];
     if (m == 0 || nnz <= 0) return MXG_OK;
@@ -1323,6 +1330,7 @@ int mxg_mul_csr_dvec(int m, int K, const int32_t *p, const int32_t *j, const dou
 
 int mxg_csr2csc(int m, int K, const int32_t *p, const int32_t *j, const double *x, int32_t *p2, int32_t *i2, double *x2)
 {
+    std::lock_guard<std::recursive_mutex> level1(g_level1_mu);
     if (!p2) return fail(MXG_ERR_ARG, "p2 is NULL");
     DeviceState *st;
     MXG_TRY(current_state(&st));
