@@ -665,8 +665,10 @@ def _pinned(a):
 
 
 def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
-    """N = 1.  Headline: the call an R session makes — every operand in ordinary pageable memory, a new result matrix
-    per call.  Sub-keys: the same call with page-locked buffers, with a device-resident matrix (explicit handle and
+    """N = 1.  Headline: the call an R session makes — every operand in ordinary pageable memory, a NEW result matrix per
+    call, allocated by the callee the way the Rcpp glue allocates it (Rf_allocVector3 with the library's allocator hooks,
+    rglue/mxgpu_result_alloc.h: a recycled page-locked block; to R an ordinary matrix).  Sub-keys: the same call writing
+    into a result on the caller's heap, with page-locked operands, with a device-resident matrix (explicit handle and
     level-1 cache), and the cpu_baseline / parity of the same product."""
     import torch
     op, n, K = wl["op"], wl["n"], wl["K"]
@@ -683,17 +685,28 @@ def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
         return out
 
     call_pg = lambda: gpu_level1(rx, wl, p_h, j_h, x_h, d_h, nth)  # noqa: E731
-    call_pg()  # warm-up: allocator pools, page-locked arena
+    call_pg()  # warm-up: allocator pools, page-locked arena, result pool
     call_pg()
     t_pg, res = _wall(call_pg, k_e2e)
     bytes_pg = _lib_bytes(_lib)
+    res_shape, res_dtype = res.shape, res.dtype
     e2e = {"value": flops / t_pg / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": bytes_pg[0], "d2h_bytes_per_step": bytes_pg[1],
            "steps": k_e2e, "ms_per_step": t_pg * 1e3, "host_threads": nth,
            "entry_point": "level-1 C ABI (streamed row chunks) via the Rcpp-export mirror, called the way an R session "
-                          "calls it: CSR, dense operand and the freshly allocated result all in PAGEABLE host memory, bounced "
-                          "through the library's page-locked ring by its host threads; bytes are the library's own count of "
-                          "the copies of the last timed call (float32 values after host narrowing, packed column ids)"}
+                          "calls it: CSR and dense operand in PAGEABLE host memory (bounced through the library's page-locked "
+                          "ring by its host threads), a NEW result per call allocated by the callee like the Rcpp glue does "
+                          "(Rf_allocVector3 + the library's allocator hooks: a recycled page-locked block the device writes "
+                          "into directly); bytes are the library's own count of the copies of the last timed call (float32 "
+                          "values after host narrowing, packed column ids)"}
     del res
+    if op != "crossprod":
+        # the same call when the result lives on the CALLER's heap (a fresh np.empty / malloc per call: pages that do not
+        # exist yet): bounced through a page-locked slot and first-touched by the host threads
+        call_heap = lambda: gpu_level1(rx, wl, p_h, j_h, x_h, d_h, nth, out=np.empty(res_shape, dtype=res_dtype, order="F"))  # noqa: E731
+        call_heap()
+        t_heap, _ = _wall(call_heap, 3)
+        e2e["caller_heap_result"] = rec(t_heap, _lib_bytes(_lib), note="everything pageable, the result a freshly allocated array "
+                                        "on the caller's heap (round 1's `all_pageable`)")
     if op != "crossprod":
         # page-locked operands and a reused page-locked result (what the contract's e2e describes; R cannot do this)
         p_p, j_p, x_p = _pinned(p_h), _pinned(j_h), _pinned(x_h)
@@ -707,10 +720,10 @@ def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
         call_pin()
         t_pin, _ = _wall(call_pin, k_e2e)
         e2e["pinned"] = rec(t_pin, _lib_bytes(_lib), note="page-locked operands and a reused page-locked result buffer (DMA in place)")
-        call_fresh = lambda: gpu_level1(rx, wl, p_p, j_p, x_p, d_p, nth)  # noqa: E731
+        call_fresh = lambda: gpu_level1(rx, wl, p_p, j_p, x_p, d_p, nth, out=np.empty(res_shape, dtype=res_dtype, order="F"))  # noqa: E731
         call_fresh()
         t_fresh, _ = _wall(call_fresh, 3)
-        e2e["fresh_pageable_result"] = rec(t_fresh, note="page-locked operands, newly allocated pageable result")
+        e2e["fresh_pageable_result"] = rec(t_fresh, note="page-locked operands, newly allocated result on the caller's heap")
         del p_p, j_p, x_p, o_p
     if op in ("dense_tcsr", "csr_dense", "spmv"):
         # the matrix stays in HBM between calls; a product moves the dense operand up and the result down
@@ -727,7 +740,7 @@ def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
         t_w, res_w = _wall(warm, k_e2e)
         e2e["warm_handle"] = rec(t_w, _lib_bytes(_lib), bit_identical_to_level1=bool(np.array_equal(res_w, call_pg())),
                                  note="explicit device-resident matrix (as_gpu_csr + gpu_csr_* exports, rglue/handle_gpu_glue.cpp); "
-                                      "pageable dense operand and result: only they cross PCIe")
+                                      "pageable dense operand, new glue-allocated result: only they cross PCIe")
         if op != "spmv":  # page-locked dense operand AND result: the PCIe bound of the warm path (R cannot do this)
             o_w = _pinned(np.empty(res_w.size, dtype=res_w.dtype)).reshape(res_w.shape, order="F")
             t_wp, _ = _wall(lambda: (fn(d_p, h, nth, out=o_w) if op == "dense_tcsr" else fn(h, d_p, nth, out=o_w)), k_e2e)

@@ -105,7 +105,8 @@ int mxg_get_devices(int *n);
  *             out of three: test modes), "host_pack_lag" (a chunk is packed while the upload of the chunk this many
  *             places before it is still pending, 2),
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
- *             copies are used), "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
+ *             copies are used), "host_result_pool_mb" (page-locked result memory handed out by mxg_host_alloc, 4096),
+ *             "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
  *             freshly allocated R matrix is otherwise filled at page-fault speed, 1);
  *   several devices : "multi_min_nnz" (level-1 calls below this many stored entries stay on one device, 4 Mi),
  *             "multi_pageable" (0 = calls whose CSR arrays are pageable stay on one device: they are bound by the host
@@ -348,6 +349,16 @@ int mxg_row_partition(int m, const int32_t *p, int parts, int32_t *row_starts);
  * streaming_stores != 0 writes the destination with cache-bypassing stores (used when it is a ring slot that the
  * DMA engine reads next). */
 int mxg_host_narrow(const double *src, float *dst, size_t n);
+/* Page-locked memory for RESULTS the glue allocates (R: Rf_allocVector3 with an R_allocator_t whose hooks are these two;
+ * rglue/mxgpu_result_alloc.h).  A freshly malloc'ed result consists of pages that do not exist yet: filling it costs a
+ * bounce through a page-locked slot plus the kernel's page zeroing (cfg3's 512 MB: 27 of the call's 54 ms).  A block from
+ * this pool is DMA'd into directly.  Blocks are recycled (2 MiB granularity, <= 25 % waste) when freed — by R's garbage
+ * collector through the allocator's free hook; the pool holds at most option "host_result_pool_mb" (4096), beyond which
+ * mxg_host_alloc fails and the glue falls back to the ordinary allocator.  mxg_host_free returns MXG_ERR_ARG, and does
+ * nothing, for a pointer that is not a live block of the pool.  mxg_trim releases the free blocks. */
+int mxg_host_alloc(size_t bytes, void **ptr);
+int mxg_host_free(void *ptr);
+int mxg_host_pool_stats(size_t *live_bytes, size_t *free_bytes, int *blocks);
 int mxg_host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height,
                      int streaming_stores);
 /* mxg_host_pack_indices: the wire format of column ids in a streamed call (option "host_pack"): n uint16 low

@@ -82,6 +82,9 @@ _SIGNATURES = {
     "mxg_dev_transpose_dense": [_i32, _sz, _sz, _vp, _sz, _vp, _sz, _vp],
     "mxg_row_partition": [_i32, _vp, _i32, _vp],
     "mxg_dev_gather_probe": [_i32, _vp, _sz, C.c_longlong, C.c_uint64, _vp, C.POINTER(C.c_longlong), _vp],
+    "mxg_host_alloc": [_sz, C.POINTER(_vp)],
+    "mxg_host_free": [_vp],
+    "mxg_host_pool_stats": [C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_int)],
     "mxg_host_narrow": [_vp, _vp, _sz],
     "mxg_host_copy_2d": [_vp, _sz, _vp, _sz, _sz, _sz, _i32],
     "mxg_host_pack_indices": [_vp, _sz, _i32, _vp, C.POINTER(_sz), C.POINTER(C.c_int)],

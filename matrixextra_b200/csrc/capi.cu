@@ -458,6 +458,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "multi_pageable")) return &o.multi_pageable;
     if (!strcmp(name, "cache_mb")) return &o.cache_mb;
     if (!strcmp(name, "host_thp")) return &o.host_thp;
+    if (!strcmp(name, "host_result_pool_mb")) return &o.host_result_pool_mb;
     return nullptr;
 }
 
@@ -478,6 +479,24 @@ int mxg_get_option(const char *name, long *value)
 }
 
 unsigned long long mxg_launch_count(void) { return g_launches.load(); }
+
+int mxg_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr) return fail(MXG_ERR_ARG, "host_alloc: NULL argument");
+    return result_pool_alloc(bytes, ptr);
+}
+
+int mxg_host_free(void *ptr)
+{
+    if (!ptr) return MXG_OK;
+    return result_pool_free(ptr) == MXG_OK ? MXG_OK : fail(MXG_ERR_ARG, "host_free: not a block of the result pool");
+}
+
+int mxg_host_pool_stats(size_t *live_bytes, size_t *free_bytes, int *blocks)
+{
+    result_pool_stats(live_bytes, free_bytes, blocks);
+    return MXG_OK;
+}
 
 int mxg_host_narrow(const double *src, float *dst, size_t n)
 {
@@ -528,6 +547,7 @@ int mxg_trim(void)
     MXG_CUDA_TRY(cudaDeviceSynchronize());
     cache_clear();
     texture_cache_clear();
+    result_pool_trim();
     cudaMemPool_t pool;
     MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
     MXG_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));

@@ -362,6 +362,108 @@ int pinned_arena_release(DeviceState *st)
 
 
 // ------------------------------------------------------------------------------------------------
+// Page-locked RESULT memory for the glue (mxg_host_alloc / mxg_host_free).  The result of a product is allocated by the
+// callee: the Rcpp glue creates the R matrix it returns.  A freshly malloc'ed 512 MB matrix consists of pages that do not
+// exist yet, and filling it is bound by the kernel's page zeroing (19 - 26 GB/s on the 16-core B200 host, against a
+// 52 GB/s link; profiles/r02_host_first_touch_probe.jsonl) on top of a bounce through a page-locked slot.  R lets a
+// package supply the allocator of a vector (Rf_allocVector3 + R_allocator_t), so the glue allocates large results HERE:
+// a pool of cudaHostAlloc'ed blocks that are recycled when R's garbage collector frees the matrix.  The device then
+// writes the result straight into the R object — no slot, no host copy, no first touch.
+// Blocks are rounded up to 2 MiB and reused for requests they fit with at most 25 % waste; the pool holds at most
+// option "host_result_pool_mb" (4096) of free + live blocks, beyond which mxg_host_alloc fails and the glue falls back to
+// R's own allocator (the bounce path).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock {
+    void *ptr;
+    size_t bytes;
+    unsigned long long stamp;
+};
+std::mutex g_rp_mu;
+std::vector<PoolBlock> g_rp_free, g_rp_live;
+size_t g_rp_bytes = 0; // free + live
+unsigned long long g_rp_clock = 0;
+} // namespace
+
+int result_pool_alloc(size_t bytes, void **out)
+{
+    *out = nullptr;
+    const size_t cap = (size_t)std::max<long>(options().host_result_pool_mb, 0) << 20;
+    const size_t want = (std::max<size_t>(bytes, 1) + ((size_t)1 << 21) - 1) & ~(((size_t)1 << 21) - 1);
+    if (want > cap) return fail(MXG_ERR_CUDA, "host_alloc: %zu MiB exceeds host_result_pool_mb", want >> 20);
+    std::lock_guard<std::mutex> lk(g_rp_mu);
+    int best = -1;
+    for (size_t i = 0; i < g_rp_free.size(); i++)
+        if (g_rp_free[i].bytes >= want && g_rp_free[i].bytes <= want + want / 4 &&
+            (best < 0 || g_rp_free[i].bytes < g_rp_free[(size_t)best].bytes))
+            best = (int)i;
+    if (best >= 0) {
+        PoolBlock b = g_rp_free[(size_t)best];
+        g_rp_free.erase(g_rp_free.begin() + best);
+        g_rp_live.push_back(b);
+        *out = b.ptr;
+        return MXG_OK;
+    }
+    // make room: the least recently freed blocks go back to the driver
+    while (g_rp_bytes + want > cap && !g_rp_free.empty()) {
+        size_t oldest = 0;
+        for (size_t i = 1; i < g_rp_free.size(); i++)
+            if (g_rp_free[i].stamp < g_rp_free[oldest].stamp) oldest = i;
+        cudaFreeHost(g_rp_free[oldest].ptr);
+        g_rp_bytes -= g_rp_free[oldest].bytes;
+        g_rp_free.erase(g_rp_free.begin() + (long)oldest);
+    }
+    if (g_rp_bytes + want > cap) return fail(MXG_ERR_CUDA, "host_alloc: result pool is full (%zu MiB live)", g_rp_bytes >> 20);
+    void *q = nullptr;
+    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MXG_ERR_CUDA, "host_alloc: cudaHostAlloc of %zu MiB failed", want >> 20);
+    }
+    g_rp_live.push_back(PoolBlock{q, want, 0});
+    g_rp_bytes += want;
+    *out = q;
+    return MXG_OK;
+}
+
+// MXG_ERR_ARG (and nothing else happens) when `ptr` is not a live block of the pool: the glue's free hook then knows the
+// block came from its fallback allocator
+int result_pool_free(void *ptr)
+{
+    std::lock_guard<std::mutex> lk(g_rp_mu);
+    for (size_t i = 0; i < g_rp_live.size(); i++)
+        if (g_rp_live[i].ptr == ptr) {
+            PoolBlock b = g_rp_live[i];
+            g_rp_live.erase(g_rp_live.begin() + (long)i);
+            b.stamp = ++g_rp_clock;
+            g_rp_free.push_back(b);
+            return MXG_OK;
+        }
+    return MXG_ERR_ARG;
+}
+
+void result_pool_stats(size_t *live_bytes, size_t *free_bytes, int *blocks)
+{
+    std::lock_guard<std::mutex> lk(g_rp_mu);
+    size_t l = 0, f = 0;
+    for (const PoolBlock &b : g_rp_live) l += b.bytes;
+    for (const PoolBlock &b : g_rp_free) f += b.bytes;
+    if (live_bytes) *live_bytes = l;
+    if (free_bytes) *free_bytes = f;
+    if (blocks) *blocks = (int)(g_rp_live.size() + g_rp_free.size());
+}
+
+// mxg_trim: free blocks go back to the driver (live ones belong to the caller)
+void result_pool_trim()
+{
+    std::lock_guard<std::mutex> lk(g_rp_mu);
+    for (const PoolBlock &b : g_rp_free) {
+        cudaFreeHost(b.ptr);
+        g_rp_bytes -= b.bytes;
+    }
+    g_rp_free.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Staged one-shot copies for the entry points that are not streamed chunk by chunk (handle uploads, crossprod,
 // CSR->CSC): the same bounce through the arena, 16 MiB blocks over a 4-slot ring on `stream`.  They return with
 // every slot idle again (the arena is shared with the streamed calls), i.e. after the last block has been copied.

@@ -73,6 +73,7 @@ struct Options {
     long multi_min_nnz = 4 << 20;  // mxg_set_devices(n > 1): level-1 calls with fewer stored entries stay on one device
     long multi_pageable = 0;       // ... and calls whose CSR arrays are pageable stay on one device too (they are bound by the host threads)
     long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
+    long host_result_pool_mb = 4096; // page-locked result memory the glue's allocator hook may hold (mxg_host_alloc)
     long host_thp = 1;             // ask for transparent huge pages on large pageable result buffers before their first touch
     long cache_mb = 0;             // level-1 operand cache (device-resident CSR + dense operands keyed on the host arrays); 0 = off
 };
@@ -234,7 +235,12 @@ bool host_pack_indices(const int32_t *j, size_t n, int K, int hi_bits, void *dst
 void host_copy(void *dst, const void *src, size_t bytes, bool nt_dst = false);
 void host_copy_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, bool nt_dst = false);
 bool host_is_pinned(const void *ptr);
-void host_prepare_result(void *ptr, size_t bytes); // madvise(MADV_HUGEPAGE) on a fresh pageable result
+void host_prepare_result(void *ptr, size_t bytes);
+// page-locked result blocks handed to the glue's allocator hook (recycled; hoststage.cu)
+int result_pool_alloc(size_t bytes, void **out);
+int result_pool_free(void *ptr);
+void result_pool_stats(size_t *live_bytes, size_t *free_bytes, int *blocks);
+void result_pool_trim(); // madvise(MADV_HUGEPAGE) on a fresh pageable result
 int pinned_arena(DeviceState *st, size_t bytes, char **base);
 int pinned_arena_release(DeviceState *st);
 // one-shot staged copies (non-streamed entry points); every slot is idle again when they return

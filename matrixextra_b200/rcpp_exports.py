@@ -40,11 +40,33 @@ def _fmat(a, dtype):
     return np.asfortranarray(a)
 
 
+#: results of at least this many bytes come from the library's page-locked pool, like the glue's (rglue/mxgpu_result_alloc.h)
+PINNED_RESULT_MIN = 1 << 20
+
+
+def _pooled_empty(shape, np_t):
+    """What the glue does through Rf_allocVector3 + R_allocator_t: the result's memory is a block of the library's
+    page-locked pool (``mxg_host_alloc``), handed back (``mxg_host_free``) when the array is garbage-collected.  Falls
+    back to an ordinary array when the pool is full or there is no device."""
+    import weakref
+    nbytes = int(np.prod(shape)) * np.dtype(np_t).itemsize
+    if nbytes < PINNED_RESULT_MIN:
+        return None
+    ptr = C.c_void_p()
+    if _lib.load().mxg_host_alloc(nbytes, C.byref(ptr)) != _lib.MXG_OK or not ptr.value:
+        return None
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    weakref.finalize(buf, _lib.load().mxg_host_free, C.c_void_p(ptr.value))
+    return np.frombuffer(buf, dtype=np_t).reshape(shape, order="F")
+
+
 def _result(shape, np_t, out):
     """The freshly allocated column-major result (what Rcpp returns), or the caller's buffer: ``out=`` is an
-    addition of this mirror so that a caller can hand in page-locked memory and reuse it across calls."""
+    addition of this mirror so that a caller can hand in memory of its own (a page-locked buffer it reuses, or an
+    ordinary ``np.empty`` to see what a result on the caller's heap costs)."""
     if out is None:
-        return np.empty(shape, dtype=np_t, order="F")
+        pooled = _pooled_empty(shape, np_t)
+        return pooled if pooled is not None else np.empty(shape, dtype=np_t, order="F")
     if out.shape != tuple(shape) or out.dtype != np_t or not out.flags.f_contiguous or not out.flags.writeable:
         raise ValueError("out= must be a writeable column-major array of the result's shape and type")
     return out
@@ -308,7 +330,7 @@ def crossprod_csr_dense(indptr, indices, values, ncols_X, Y_colmajor, dtype=MXG_
     if p.size - 1 != m:
         raise ValueError("Matrix dimensions do not match.")
     K = int(ncols_X)
-    out = np.empty((K, n), dtype=np_t, order="F")
+    out = _result((K, n), np_t, None)
     _lib.call("mxg_spmm_csrT_dense", dtype, MXG_COLS_CONTIGUOUS, MXG_COLS_CONTIGUOUS, m, K, n,
               _vp(p), _vp(j), _vp(x), _vp(Y), max(m, 1), _vp(out), max(K, 1))
     return out

@@ -105,6 +105,8 @@ public:
     }
     /* non-owning view over caller memory (what Rcpp does with a SEXP) */
     ShimVector(T *borrowed, size_t n) : ptr_(borrowed), n_(n) {}
+    /* storage from a custom allocator; the deleter runs when the last handle goes (R: Rf_allocVector3 + garbage collection) */
+    ShimVector(std::shared_ptr<T> owned, size_t n) : own_(owned), ptr_(owned.get()), n_(n) {}
     /* Rcpp's copying iterator-range constructor */
     template <class It, class = typename std::enable_if<!std::is_integral<It>::value>::type,
               class = typename std::iterator_traits<It>::value_type>
@@ -164,6 +166,8 @@ public:
         : ShimVector<T, Tag>((size_t)nrow * (size_t)ncol), nrow_(nrow), ncol_(ncol) {}
     ShimMatrix(T *borrowed, int nrow, int ncol)
         : ShimVector<T, Tag>(borrowed, (size_t)nrow * (size_t)ncol), nrow_(nrow), ncol_(ncol) {}
+    ShimMatrix(std::shared_ptr<T> owned, int nrow, int ncol)
+        : ShimVector<T, Tag>(owned, (size_t)nrow * (size_t)ncol), nrow_(nrow), ncol_(ncol) {}
     int nrow() const { return nrow_; }
     int ncol() const { return ncol_; }
 private:

@@ -26,19 +26,18 @@
 #include <stdexcept>
 #include <string>
 #define MXGPU_GLUE_STOP(msg) throw std::runtime_error(std::string(msg))
-#define MXGPU_NEW_MATRIX(Type, nr, nc) Type((nr), (nc))
-#define MXGPU_NEW_VECTOR(Type, n) Type((n))
 #else
 #include <Rcpp.h>
 #define MXGPU_GLUE_STOP(msg) Rcpp::stop("%s", (msg))
-/* no zero fill: every element is written by the device-to-host copy */
-#define MXGPU_NEW_MATRIX(Type, nr, nc) Type(Rcpp::no_init((nr), (nc)))
-#define MXGPU_NEW_VECTOR(Type, n) Type(Rcpp::no_init((n)))
 #endif
 
 #include <cstdlib>
 
 #include "mxgpu.h"
+#include "mxgpu_result_alloc.h" /* results come from the library's page-locked pool (Rf_allocVector3) */
+
+#define MXGPU_NEW_MATRIX(Type, nr, nc) mxgpu_new_matrix<Type>((nr), (nc))
+#define MXGPU_NEW_VECTOR(Type, n) mxgpu_new_vector<Type>((size_t)(n))
 
 namespace {
 

@@ -14,17 +14,19 @@
 #include <string>
 #ifndef MXGPU_GLUE_STOP
 #define MXGPU_GLUE_STOP(msg) throw std::runtime_error(std::string(msg))
-#define MXGPU_NEW_VECTOR(Type, n) Type((n))
 #endif
 #else
 #include <Rcpp.h>
 #ifndef MXGPU_GLUE_STOP
 #define MXGPU_GLUE_STOP(msg) Rcpp::stop("%s", (msg))
-#define MXGPU_NEW_VECTOR(Type, n) Type(Rcpp::no_init((n)))
 #endif
 #endif
 
 #include "mxgpu.h"
+#include "mxgpu_result_alloc.h" /* results come from the library's page-locked pool (Rf_allocVector3) */
+
+#define MXGPU_NEW_MATRIX(Type, nr, nc) mxgpu_new_matrix<Type>((nr), (nc))
+#define MXGPU_NEW_VECTOR(Type, n) mxgpu_new_vector<Type>((size_t)(n))
 
 namespace {
 

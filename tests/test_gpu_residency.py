@@ -33,6 +33,7 @@ def lib():
     _lib.set_option("multi_min_nnz", 4 << 20)
     _lib.set_option("multi_dense_share", 1)
     _lib.set_option("multi_pageable", 0)
+    _lib.set_option("host_result_pool_mb", 4096)
     _lib.set_option("piece", 1024)
     _lib.set_option("pipe_chunk_nnz", 0)
 
@@ -242,3 +243,65 @@ def test_one_call_over_several_devices_is_bit_identical(rx, lib, port, share):
         rx.tcrossprod_csr_dense_numeric(p, jb, x, cases[0][1])
     # and the next call works
     assert np.array_equal(rx.tcrossprod_csr_dense_numeric(p, j, x, cases[0][1]), ref_cm[0])
+
+
+def test_results_are_allocated_from_the_page_locked_pool(rx, lib, port):
+    """What the glue does with Rf_allocVector3 (rglue/mxgpu_result_alloc.h), mirrored by rcpp_exports._result: a large
+    result is a block of the library's page-locked pool — written by the device directly, recycled when collected."""
+    import gc
+
+    def stats():
+        live, free, blocks = C.c_size_t(), C.c_size_t(), C.c_int()
+        lib.call("mxg_host_pool_stats", C.byref(live), C.byref(free), C.byref(blocks))
+        return live.value, free.value, blocks.value
+
+    m, K, n = 30000, 4000, 16  # 3.84 MB result
+    p, j, x = powerlaw_csr(m, K, 12, seed=71, cap=2000)
+    Y = np.asfortranarray(np.random.default_rng(71).standard_normal((n, K)))
+    gc.collect()
+    live0, _, _ = stats()
+    res = rx.tcrossprod_csr_dense_numeric(p, j, x, Y)
+    assert res.flags.f_contiguous and res.flags.writeable and res.shape == (m, n)
+    live1, _, _ = stats()
+    assert live1 - live0 >= res.nbytes  # its memory is a live pool block ...
+    up, down = _bytes(lib)
+    assert down == res.nbytes + 4
+    want = port.tcrossprod_csr_dense_numeric(p, j, x, Y)
+    assert rel_err(res, want) <= FP64_TOL
+    heap = rx.tcrossprod_csr_dense_numeric(p, j, x, Y, out=np.empty((m, n), order="F"))  # a result on the caller's heap
+    assert np.array_equal(res, heap) and stats()[0] == live1
+    addr = res.ctypes.data
+    view = res[:, 3]  # a view keeps the block alive
+    del res
+    gc.collect()
+    assert stats()[0] == live1 and np.array_equal(view, heap[:, 3])
+    del view
+    gc.collect()
+    live2, free2, _ = stats()
+    assert live2 == live0 and free2 >= heap.nbytes  # ... handed back when the array is collected ...
+    again = rx.tcrossprod_csr_dense_numeric(p, j, x, Y)
+    assert again.ctypes.data == addr and np.array_equal(again, heap)  # ... and reused by the next result of that size
+    small = rx.matmul_csr_dvec_numeric(p, j, x, np.ones(K))  # 240 KB: stays on the ordinary heap
+    assert stats()[0] == live1
+    del again, small
+    gc.collect()
+    # a pool that may hold nothing: results fall back to ordinary arrays, same bits
+    lib.call("mxg_trim")
+    lib.set_option("host_result_pool_mb", 0)
+    res = rx.tcrossprod_csr_dense_numeric(p, j, x, Y)
+    assert np.array_equal(res, heap) and stats()[0] == 0
+    # the raw entry points: alignment, unknown pointers, recycling with at most 25 % waste
+    lib.set_option("host_result_pool_mb", 64)
+    a, b = C.c_void_p(), C.c_void_p()
+    lib.call("mxg_host_alloc", 5 << 20, C.byref(a))
+    assert a.value % 4096 == 0
+    with pytest.raises(lib.MxgError):
+        lib.call("mxg_host_free", C.c_void_p(a.value + 64))
+    lib.call("mxg_host_free", a)
+    lib.call("mxg_host_alloc", 1 << 20, C.byref(b))  # far smaller: a block of its own, not the 6 MiB one
+    assert b.value != a.value
+    lib.call("mxg_host_free", b)
+    with pytest.raises(lib.MxgError):
+        lib.call("mxg_host_alloc", 65 << 20, C.byref(a))  # beyond the cap: the caller falls back
+    lib.call("mxg_trim")
+    assert stats()[1] == 0

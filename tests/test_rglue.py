@@ -24,12 +24,14 @@ def _build():
     build_native.build()
     srcs = [os.path.join(ROOT, "tests", "glue_driver.cpp"), os.path.join(ROOT, "rglue", "matmul_gpu_glue.cpp"),
             os.path.join(ROOT, "rglue", "rowops_gpu_glue.cpp"), os.path.join(ROOT, "rglue", "handle_gpu_glue.cpp"),
+            os.path.join(ROOT, "rglue", "mxgpu_result_alloc.h"),
             os.path.join(ROOT, "include", "mxgpu.h"), os.path.join(ROOT, "oracle", "shim", "Rcpp.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-DMXGPU_GLUE_SHIM",
-           "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), "-o", LIB, srcs[0],
+           "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "rglue"),
+           "-o", LIB, srcs[0],
            "-L" + os.path.join(ROOT, "matrixextra_b200", "csrc"), "-lmxgpu",
            "-Wl,-rpath," + os.path.join(ROOT, "matrixextra_b200", "csrc")]
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
@@ -241,3 +243,71 @@ def test_rowops_glue_float32_row_vector_by_csc(drv, port):
     assert rel_err(out, port.matmul_rowvec_by_csc(rv, p, i, x).ravel()) <= FP32_TOL
     assert drv.gluedrv_rowvec_by_csc(_p(rv), 400, _p(p), 150, _p(i), None, i.size, _p(out)) == 0
     assert rel_err(out, port.matmul_rowvec_by_csc(rv, p, i, None).ravel()) <= FP32_TOL
+
+
+# ---- rglue/handle_gpu_glue.cpp: device-resident matrices behind an external pointer ------------------
+def test_handle_glue_exports_and_finalizer_wiring():
+    text = open(os.path.join(ROOT, "rglue", "handle_gpu_glue.cpp")).read()
+    for name in ("as_gpu_csr", "gpu_csr_free", "gpu_csr_dim", "gpu_csr_tcrossprod_dense_numeric", "gpu_csr_tcrossprod_dense_float32",
+                 "gpu_csr_dense_tcrossprod_numeric", "gpu_csr_dense_tcrossprod_float32", "gpu_csr_crossprod_dense_numeric",
+                 "gpu_csr_crossprod_dense_float32", "gpu_csr_dvec_numeric", "mxgpu_configure"):
+        assert text.count(name + "(") >= 1, name
+    assert text.count("\n// [[Rcpp::export(rng = false)]]\n") == 11
+    assert "Rcpp::XPtr<MxGpuCsr, Rcpp::PreserveStorage, mxgpu_csr_finalizer, true>" in text  # mxg_csr_free runs on GC and at exit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f32", [0, 1])
+def test_handle_glue_products_match_the_level1_exports(drv, port, f32):
+    dt = np.float32 if f32 else np.float64
+    tol = FP32_TOL if f32 else FP64_TOL
+    sfx = "float32" if f32 else "numeric"
+    m, K = 900, 350
+    p, j, x = powerlaw_csr(m, K, 14, seed=46, cap=340)
+    rng = np.random.default_rng(46)
+    drv.gluedrv_as_gpu_csr.restype = C.c_void_p
+    box = drv.gluedrv_as_gpu_csr(_p(p), m, _p(j), _p(x), j.size, K, 1, 1)
+    assert box, drv.gluedrv_last_error()
+    box = C.c_void_p(box)
+    try:
+        Y = np.asfortranarray(rng.standard_normal((24, K)).astype(dt))  # A %*% t(Y)
+        out = np.empty((m, 24), dtype=dt, order="F")
+        assert drv.gluedrv_gpu_csr_product(box, 0, f32, _p(Y), 24, K, _p(out)) == 0
+        assert rel_err(out, getattr(port, "tcrossprod_csr_dense_" + sfx)(p, j, x, Y, 1)) <= tol
+        ref_out = np.empty((m, 24), dtype=dt, order="F")
+        assert drv.gluedrv_sparse_tdense(f32, _p(p), m, _p(j), _p(x), j.size, _p(Y), 24, K, _p(ref_out)) == 0
+        assert np.array_equal(out, ref_out)  # same bits as the level-1 export
+        X = np.asfortranarray(rng.standard_normal((17, K)).astype(dt))  # X %*% t(A)
+        out2 = np.empty((17, m), dtype=dt, order="F")
+        assert drv.gluedrv_gpu_csr_product(box, 1, f32, _p(X), 17, K, _p(out2)) == 0
+        assert rel_err(out2, getattr(port, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, 1, K)) <= tol
+        Z = np.asfortranarray(rng.standard_normal((m, 9)).astype(dt))  # t(A) %*% Z, twice (the second uses the kept CSC)
+        out3, out3b = np.empty((K, 9), dtype=dt, order="F"), np.empty((K, 9), dtype=dt, order="F")
+        assert drv.gluedrv_gpu_csr_product(box, 2, f32, _p(Z), m, 9, _p(out3)) == 0
+        assert drv.gluedrv_gpu_csr_product(box, 2, f32, _p(Z), m, 9, _p(out3b)) == 0
+        p2, i2, x2 = port.csr2csc(m, K, p, j, x)
+        want = getattr(port, "matmul_dense_csc_" + sfx)(np.asfortranarray(Z.T), p2, i2, x2).T
+        assert rel_err(out3, want) <= tol and np.array_equal(out3, out3b)
+        if not f32:
+            y = rng.standard_normal(K)
+            outv = np.empty(m)
+            assert drv.gluedrv_gpu_csr_dvec(box, _p(y), K, _p(outv)) == 0
+            assert rel_err(outv, port.matmul_csr_dvec_numeric(p, j, x, y, 1)) <= FP64_TOL
+            assert drv.gluedrv_gpu_csr_dvec(box, _p(y), K - 1, _p(outv)) == 1
+            assert drv.gluedrv_last_error().decode() == "Matrix dimensions do not match."
+        # dimension errors carry the reference's message
+        assert drv.gluedrv_gpu_csr_product(box, 0, f32, _p(Y), 24, K - 1, _p(out)) == 1
+        assert drv.gluedrv_last_error().decode() == "Matrix dimensions do not match."
+        # explicit free (gpu.free(x) in R): later products raise instead of touching freed device memory
+        assert drv.gluedrv_gpu_csr_free(box) == 0
+        assert drv.gluedrv_gpu_csr_product(box, 0, f32, _p(Y), 24, K, _p(out)) == 1
+        assert "freed" in drv.gluedrv_last_error().decode()
+    finally:
+        drv.gluedrv_gpu_csr_drop(box)  # the R object is collected: the finalizer finds nothing left to release
+    # an invalid matrix is rejected at construction with the library's message
+    jb = j.copy()
+    jb[3] = K
+    assert not drv.gluedrv_as_gpu_csr(_p(p), m, _p(jb), _p(x), j.size, K, 1, 0)
+    assert "column index" in drv.gluedrv_last_error().decode()
+    n = C.c_int(0)
+    assert drv.gluedrv_configure(1, 0, C.byref(n)) == 0 and n.value == 1
