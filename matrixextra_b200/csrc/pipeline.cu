@@ -327,7 +327,7 @@ struct CsrStream {
     bool stage_x = false, stage_j = false;
     // column ids packed by the host threads (2 / 2.5 / 3 bytes per entry) and unpacked on the device: decided per
     // chunk (pack_mode 1: while the link is the bottleneck; 2: always; 3: two chunks out of three)
-    bool pack_j = false;
+    bool pack_j = false, pack_pageable = false;
     int pack_mode = 0, hi_bits = -1;
     std::vector<char> chunk_packed; // [C]
     int pack_buf_last[3] = {-1, -1, -1}; // the last packed chunk that used d_pack[b]
@@ -378,10 +378,13 @@ struct CsrStream {
         // host_pack = 2 packs every chunk whatever the size (tests).
         hi_bits = index_pack_hi_bits(K);
         pack_mode = (int)options().host_pack;
-        pack_j = stage && hi_bits >= 0 && nnz > 0 &&
-                 (pack_mode == 2 || pack_mode == 3 ||
-                  (pack_mode == 1 && !narrow_on_host && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
         stage_j = nnz > 0 && stage && !host_is_pinned(j); // unpacked ids are bounced through the slot
+        // pageable ids have to be read and rewritten by the host threads anyway (the bounce): packing them instead
+        // costs no extra pass, writes 2 - 3 bytes per entry instead of 4 and shortens the upload — always on for them
+        pack_pageable = pack_mode == 1 && stage_j && nnz >= ((int64_t)1 << 20);
+        pack_j = stage && hi_bits >= 0 && nnz > 0 &&
+                 (pack_mode == 2 || pack_mode == 3 || pack_pageable ||
+                  (pack_mode == 1 && !narrow_on_host && nnz >= ((int64_t)1 << 20) && host_threads() >= 8));
         auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
         x_part = stage_x ? up(plan.max_chunk_nnz * (narrow_on_host ? sizeof(float) : sizeof(double))) : 0;
         size_t in_slot = x_part + std::max(pack_j ? up(packed_index_bytes(plan.max_chunk_nnz, hi_bits)) : 0,
@@ -473,7 +476,7 @@ struct CsrStream {
             // The first two chunks queue behind the dense operand.
             // (pack_mode 3, tests: a fixed mix — two chunks out of three)
             const int lag = (int)std::min<long>(std::max<long>(options().host_pack_lag, 1), 8);
-            const bool pk = pack_j && (pack_mode == 2 || (pack_mode == 3 ? c % 3 != 1
+            const bool pk = pack_j && (pack_mode == 2 || pack_pageable || (pack_mode == 3 ? c % 3 != 1
                                                          : (c < lag || cudaEventQuery(ev_h2d[(size_t)(c - lag)]) == cudaErrorNotReady)));
             cudaGetLastError(); // cudaErrorNotReady is an answer, not an error
             chunk_packed[(size_t)c] = pk;

@@ -277,10 +277,12 @@ def test_results_are_allocated_from_the_page_locked_pool(rx, lib, port):
     assert stats()[0] == live1 and np.array_equal(view, heap[:, 3])
     del view
     gc.collect()
-    live2, free2, _ = stats()
+    live2, free2, blocks2 = stats()
     assert live2 == live0 and free2 >= heap.nbytes  # ... handed back when the array is collected ...
     again = rx.tcrossprod_csr_dense_numeric(p, j, x, Y)
-    assert again.ctypes.data == addr and np.array_equal(again, heap)  # ... and reused by the next result of that size
+    assert np.array_equal(again, heap)
+    assert stats() == (live1, free2 - (live1 - live0), blocks2)  # ... and a free block is reused by the next result of that size
+    del addr
     small = rx.matmul_csr_dvec_numeric(p, j, x, np.ones(K))  # 240 KB: stays on the ordinary heap
     assert stats()[0] == live1
     del again, small
