@@ -551,7 +551,14 @@ int mxg_trim(void)
     cudaMemPool_t pool;
     MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
     MXG_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
-    if (dev >= 0 && dev < 64 && g_dev[dev].ready) MXG_TRY(pinned_arena_release(&g_dev[dev]));
+    if (dev >= 0 && dev < 64 && g_dev[dev].ready) {
+        MXG_TRY(pinned_arena_release(&g_dev[dev]));
+        if (g_dev[dev].share_buf) {
+            cudaFree(g_dev[dev].share_buf);
+            g_dev[dev].share_buf = nullptr;
+            g_dev[dev].share_bytes = 0;
+        }
+    }
     return MXG_OK;
 }
 

@@ -138,6 +138,10 @@ struct DeviceState {
     cudaStream_t p2p = nullptr; // pulls of the other devices' dense-operand slices over NVLink (multi-device calls)
     std::vector<cudaEvent_t> ev_pool; // timing-disabled events reused by mxg_dev_spmm_push
     std::vector<cudaStream_t> push_streams; // one per destination of mxg_dev_spmm_push
+    // this device's copy of the dense operand of a multi-device call (cudaMalloc: visible to the peers that pull slices
+    // out of it), grow-only, released by mxg_trim
+    void *share_buf = nullptr;
+    size_t share_bytes = 0;
     // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
     void *pin_base = nullptr;
     size_t pin_bytes = 0;

@@ -694,7 +694,21 @@ int pipeline_spmm(DeviceState *st, int dtype, int out_layout, int b_layout, int 
     // dense operand first: every chunk needs all of it.  Device copy is rows-contiguous [K][ld_b].
     const size_t ld_b = round_up(nz, vec);
     char *d_B = nullptr, *d_Out = nullptr, *d_tmp = nullptr;
-    MXG_TRY(sc.alloc((void **)&d_B, Kz * ld_b * s));
+    if (share) {
+        // one device of a multi-device call: the operand's copy lives in the device's peer-visible buffer
+        const size_t need = std::max<size_t>(Kz * ld_b * s, 16);
+        if (st->share_bytes < need) {
+            MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
+            if (st->share_buf) MXG_CUDA_TRY(cudaFree(st->share_buf));
+            st->share_buf = nullptr;
+            st->share_bytes = 0;
+            MXG_CUDA_TRY(cudaMalloc(&st->share_buf, need));
+            st->share_bytes = need;
+        }
+        d_B = static_cast<char *>(st->share_buf);
+    } else {
+        MXG_TRY(sc.alloc((void **)&d_B, Kz * ld_b * s));
+    }
     const size_t ld_o = out_layout == MXG_ROWS_CONTIGUOUS ? round_up(nz, vec) : rows;
     MXG_TRY(sc.alloc((void **)&d_Out, out_layout == MXG_ROWS_CONTIGUOUS ? rows * ld_o * s : rows * nz * s));
     if (K > 0 && b_layout == MXG_COLS_CONTIGUOUS) MXG_TRY(sc.alloc((void **)&d_tmp, Kz * nz * s));

@@ -53,8 +53,6 @@ int set_devices(int n)
         MXG_CUDA_TRY(cudaSetDevice(g_devs[g]));
         DeviceState *st;
         MXG_TRY(current_state(&st)); // streams + pool settings
-        cudaMemPool_t pool;
-        MXG_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_devs[g]));
         for (int q = 0; q < n; q++) {
             if (q == g) continue;
             int can = 0;
@@ -63,18 +61,13 @@ int set_devices(int n)
                 peer = false;
                 continue;
             }
+            // peer access covers cudaMalloc'ed memory: the devices' copies of a shared dense operand live in such a
+            // buffer (DeviceState::share_buf).  The default memory pool is left alone on purpose: making IT
+            // peer-accessible (cudaMemPoolSetAccess) made later multi-GB cudaMallocAsync calls fail with "out of
+            // memory" on a box with 176 GB free.
             const cudaError_t e = cudaDeviceEnablePeerAccess(g_devs[q], 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer = false;
             cudaGetLastError();
-            // stream-ordered (pool) allocations of device g readable by device q: the slices of the dense operand
-            cudaMemAccessDesc desc = {};
-            desc.location.type = cudaMemLocationTypeDevice;
-            desc.location.id = g_devs[q];
-            desc.flags = cudaMemAccessFlagsProtReadWrite;
-            if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) {
-                cudaGetLastError();
-                peer = false;
-            }
         }
     }
     MXG_CUDA_TRY(cudaSetDevice(cur));
@@ -154,8 +147,13 @@ int run_on_devices(int G, Body body)
         d2h += down[(size_t)g];
     }
     set_last_call_bytes(h2d, d2h);
+    // report the root cause: a device that gave up because a peer had failed says so, the peer says why
+    int first = -1;
     for (int g = 0; g < G; g++)
-        if (rc[(size_t)g] != MXG_OK) return fail(rc[(size_t)g], "device %d: %s", g_devs[g], err[(size_t)g].c_str());
+        if (rc[(size_t)g] != MXG_OK && (first < 0 || (err[(size_t)first].find("another device failed") != std::string::npos &&
+                                                      err[(size_t)g].find("another device failed") == std::string::npos)))
+            first = g;
+    if (first >= 0) return fail(rc[(size_t)first], "device %d: %s", g_devs[first], err[(size_t)first].c_str());
     return MXG_OK;
 }
 
