@@ -141,9 +141,12 @@ struct RadixIO {
 // shared memory of a scatter CTA: the tile's records + tables sized by the digit of the pass (128 bins: 69 KB with
 // float64 values, three CTAs per SM; 1024 bins: 104 KB, two)
 __host__ __device__ constexpr int radix_stride(int nbins) { return nbins < 2 ? 2 : nbins; }
+// the tile is re-ordered as whole RECORDS: (key, row, value) in one 16-byte slot (8 bytes without values, 16 + 4 when both
+// value types travel), so that an entry costs one shared-memory store and one load instead of three of each
+__host__ __device__ constexpr size_t radix_rec_bytes(bool h64, bool h32) { return (h64 || h32) ? 16 : 8; }
 constexpr size_t radix_smem_bytes(bool h64, bool h32, int nbins)
 {
-    return (size_t)RS_TILE * (4 + 4 + (h64 ? 8 : 0) + (h32 ? 4 : 0)) + sizeof(rs_cnt_t) * RS_WARPS * radix_stride(nbins) +
+    return (size_t)RS_TILE * (radix_rec_bytes(h64, h32) + ((h64 && h32) ? 4 : 0)) + sizeof(rs_cnt_t) * RS_WARPS * radix_stride(nbins) +
            sizeof(int) * 2 * radix_stride(nbins);
 }
 
@@ -153,12 +156,12 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_radix_scatter(size_
                                                                  const int32_t *__restrict__ offs, int ntiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_x64 = reinterpret_cast<double *>(smem_raw);                                   // [RS_TILE] if H64
-    int *s_key = reinterpret_cast<int *>(smem_raw + (H64 ? (size_t)RS_TILE * 8 : 0));       // [RS_TILE]
-    int *s_row = s_key + RS_TILE;                                                            // [RS_TILE]
-    float *s_x32 = reinterpret_cast<float *>(s_row + RS_TILE);                               // [RS_TILE] if H32
+    constexpr int REC = (int)radix_rec_bytes(H64, H32);                                      // bytes per record slot
+    constexpr int RW = REC / 4;                                                              // ints per record
+    int *s_rec = reinterpret_cast<int *>(smem_raw);                                          // [RS_TILE][RW]: key, row, value bits
+    float *s_x32 = reinterpret_cast<float *>(smem_raw + (size_t)RS_TILE * REC);              // [RS_TILE] only if H64 && H32
     const int stride = radix_stride(nbins);                                                  // table rows are nbins wide
-    int *dig_off = reinterpret_cast<int *>(s_row + RS_TILE + (H32 ? RS_TILE : 0));           // [stride] tile-local digit starts
+    int *dig_off = reinterpret_cast<int *>(smem_raw + (size_t)RS_TILE * (REC + ((H64 && H32) ? 4 : 0))); // [stride] tile-local digit starts
     int *gdelta = dig_off + stride;                                                          // [stride] global - local
     rs_cnt_t *wcnt = reinterpret_cast<rs_cnt_t *>(gdelta + stride);                          // [RS_WARPS][stride]
 
@@ -253,29 +256,46 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_radix_scatter(size_
         if (e < n) {
             const int d = (key[s] >> shift) & mask;
             const int pos = dig_off[d] + my_cnt[d] + rank[s];
-            s_key[pos] = key[s];
-            s_row[pos] = __ldg(io.rows_in + e);
-            if (H64) s_x64[pos] = __ldg(io.x64_in + e);
-            if (H32) s_x32[pos] = __ldg(io.x32_in + e);
+            const int row = __ldg(io.rows_in + e);
+            if (H64) {
+                const double xv = __ldg(io.x64_in + e);
+                *reinterpret_cast<int4 *>(s_rec + (size_t)pos * RW) = make_int4(key[s], row, __double2loint(xv), __double2hiint(xv));
+                if (H32) s_x32[pos] = __ldg(io.x32_in + e);
+            } else if (H32) {
+                *reinterpret_cast<int4 *>(s_rec + (size_t)pos * RW) = make_int4(key[s], row, __float_as_int(__ldg(io.x32_in + e)), 0);
+            } else {
+                *reinterpret_cast<int2 *>(s_rec + (size_t)pos * RW) = make_int2(key[s], row);
+            }
         }
     }
     __syncthreads();
     const int tile_n = (int)((n - t0) < (size_t)RS_TILE ? (n - t0) : (size_t)RS_TILE);
     for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
-        const int k = s_key[i];
+        int k, row;
+        if (H64 || H32) {
+            const int4 r = *reinterpret_cast<const int4 *>(s_rec + (size_t)i * RW);
+            k = r.x;
+            row = r.y;
+            const int dst = i + gdelta[(k >> shift) & mask];
+            if (H64) io.x64_out[dst] = __hiloint2double(r.w, r.z);
+            else io.x32_out[dst] = __int_as_float(r.z);
+            if (H64 && H32) io.x32_out[dst] = s_x32[i];
+        } else {
+            const int2 r = *reinterpret_cast<const int2 *>(s_rec + (size_t)i * RW);
+            k = r.x;
+            row = r.y;
+        }
         const int dst = i + gdelta[(k >> shift) & mask];
         if (io.keys_out) io.keys_out[dst] = k;
-        io.rows_out[dst] = s_row[i];
-        if (H64) io.x64_out[dst] = s_x64[i];
-        if (H32) io.x32_out[dst] = s_x32[i];
+        io.rows_out[dst] = row;
         // Last pass: the input was sorted by the lower digits and the re-order above is stable, so the tile is now
         // sorted by the whole column id.  The first entry of every run of equal ids adds the run length to the
         // column's count: one global atomic per (tile, column) instead of one per stored entry.
-        if (io.col_count != nullptr && (i == 0 || s_key[i - 1] != k)) {
+        if (io.col_count != nullptr && (i == 0 || s_rec[(size_t)(i - 1) * RW] != k)) {
             int a = i + 1, b = tile_n; // first position after i whose key differs
             while (a < b) {
                 const int mid = (a + b) >> 1;
-                if (s_key[mid] == k) a = mid + 1;
+                if (s_rec[(size_t)mid * RW] == k) a = mid + 1;
                 else b = mid;
             }
             atomicAdd(&io.col_count[k], a - i);
