@@ -896,12 +896,19 @@ def strong_cfg5(args, dist, rank, world):
     from matrixextra_b200.sharded import PipelinedColumnMajorGather
     pipe = PipelinedColumnMajorGather(A, n, MXG_F32, torch.float32, dist, rank, world, slices=8)
     step_pipe = lambda: pipe.step(dense)  # noqa: E731
+
+    def step_pipe_after():  # the same pipeline behind the whole product instead of behind its slices
+        pipe.overlap_product = False
+        pipe.step(dense)
+        pipe.overlap_product = True
     for _ in range(2):
         step()
         step_pipe()
+        step_pipe_after()
     steps = 3
     ms_push = timed(step, steps)
     ms_pipe = timed(step_pipe, steps)
+    ms_pipe_after = timed(step_pipe_after, steps)
     ms_compute = timed(compute, steps)
     step()
     step_pipe()
@@ -917,7 +924,7 @@ def strong_cfg5(args, dist, rank, world):
     same_r = torch.equal(out_all.view(n, world, mg), want)
     flag2 = torch.tensor([1 if same_r else 0], device="cuda")
     dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
-    ms_step = min(ms_push, ms_pipe, ms_nccl)
+    ms_step = min(ms_push, ms_pipe, ms_pipe_after, ms_nccl)
     del pipe
     t = torch.tensor([A.nnz], device="cuda", dtype=torch.int64)
     dist.all_reduce(t)
@@ -931,8 +938,12 @@ def strong_cfg5(args, dist, rank, world):
             "scaling": "strong", "rows_per_gpu": mg, "nnz_total": nnz_all, "steps": steps,
             "ms_per_step": ms_step, "GFLOPs": 2.0 * nnz_all * n / ms_step / 1e6,
             "compute_only_ms": ms_compute, "nccl_after_compute_ms": ms_nccl, "nccl_after_compute_without_rearrangement_ms": ms_nccl_raw,
-            "variants_ms_per_step": {"push": ms_push, "pipelined_nccl": ms_pipe, "nccl_after_compute": ms_nccl},
-            "how": {ms_pipe: "product in 8 row slices into this GPU's rows of the global column-major result; behind every slice "
+            "variants_ms_per_step": {"push": ms_push, "pipelined_nccl": ms_pipe, "pipelined_nccl_after_product": ms_pipe_after,
+                                     "nccl_after_compute": ms_nccl},
+            "how": {ms_pipe_after: "the whole product into this GPU's rows of the global column-major result, then 8 row slices "
+                                   "packed (copy engine), all-gathered with NCCL and unpacked into the result (copy engines) in a "
+                                   "three-stage pipeline (sharded.PipelinedColumnMajorGather, overlap_product=False)",
+                    ms_pipe: "product in 8 row slices into this GPU's rows of the global column-major result; behind every slice "
                              "one stream packs it (copy engine) and all-gathers it with NCCL, another unpacks the received slices "
                              "into the result (copy engines) while the next slice is computed (sharded.PipelinedColumnMajorGather)",
                     ms_push: "product in ~16 row slices per GPU into the global column-major result; every finished slice pushed "

@@ -235,9 +235,12 @@ class PipelinedColumnMajorGather:
         engines; the rank's own slice is already in place),
     while the next slice is being computed: the step costs about max(product, all-gather) instead of their sum."""
 
-    def __init__(self, A, n, dtype, torch_dtype, dist, rank, world, slices=8):
+    def __init__(self, A, n, dtype, torch_dtype, dist, rank, world, slices=8, overlap_product=True):
+        """overlap_product=False: the whole product first, then the slices are packed / gathered / unpacked in a pipeline of
+        their own (the exchange no longer competes with the product for HBM and SMs, but nothing hides the product)."""
         import torch
         self.A, self.n, self.dtype, self.dist, self.rank, self.world = A, n, dtype, dist, rank, world
+        self.overlap_product = overlap_product
         m = A.m
         self.bounds = [m * k // slices for k in range(slices + 1)]
         rows_max = max(self.bounds[k + 1] - self.bounds[k] for k in range(slices))
@@ -266,7 +269,10 @@ class PipelinedColumnMajorGather:
         def copy2d(dst, dpitch, src, spitch, width, height, stream):
             _lib.call("mxg_dev_copy_2d", C.c_void_p(dst), dpitch, C.c_void_p(src), spitch, width, height, C.c_void_p(stream.cuda_stream))
 
-        if A.n_pieces > 0:
+        if not self.overlap_product:
+            _lib.call("mxg_dev_spmm", A._h, int(self.dtype), MXG_COLS_CONTIGUOUS, 0, int(n), C.c_void_p(B_t.data_ptr()), int(n),
+                      C.c_void_p(origin), int(ldc), C.c_void_p(main.cuda_stream))
+        elif A.n_pieces > 0:
             A.spmm_rows(B_t, origin, n, self.dtype, MXG_COLS_CONTIGUOUS, ldc, pieces=True)
         self.comm.wait_stream(main)
         self.unpack.wait_stream(main)
@@ -274,7 +280,8 @@ class PipelinedColumnMajorGather:
         for k in range(S):
             r0, r1 = self.bounds[k], self.bounds[k + 1]
             rows = r1 - r0
-            A.spmm_rows(B_t, origin, n, self.dtype, MXG_COLS_CONTIGUOUS, ldc, r0, r1)
+            if self.overlap_product:
+                A.spmm_rows(B_t, origin, n, self.dtype, MXG_COLS_CONTIGUOUS, ldc, r0, r1)
             self.ev_done[k].record(main)
             b = k % 2
             send = self.pack[b][: n * rows]
