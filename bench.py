@@ -448,6 +448,10 @@ def run_ours(args):
         _lib.set_option("spmm_bulk", 1)
         step_peer(keep_option=True)
 
+    def step_bulk_cta():
+        _lib.set_option("spmm_bulk", 2)
+        step_peer(keep_option=True)
+
     def step_peer(keep_option=False):
         if not keep_option:
             _lib.set_option("spmm_bulk", 0)
@@ -490,6 +494,7 @@ def run_ours(args):
             variants["peer"] = step_peer
         if op == "dense_tcsr":
             variants["bulk"] = step_bulk
+            variants["bulk_cta"] = step_bulk_cta
         if op != "spmv":
             variants["push"] = step_push
         if op == "dense_tcsr" and args.allgather in ("auto", "mcast"):
@@ -577,6 +582,8 @@ def run_ours(args):
     fused_text = {"mcast": "fused into the product kernel (NVLS multicast stores)",
                   "bulk": "fused into the product kernel (finished rows parked in shared memory and shipped to every GPU as "
                           "cp.async.bulk copies over NVLink)",
+                  "bulk_cta": "fused into the product kernel (a CTA's 32 finished rows parked in shared memory and shipped to every "
+                              "GPU as one cp.async.bulk copy each over NVLink)",
                   "peer": "fused into the product kernel (NVLink peer stores)",
                   "push": "finished row slices pushed by the copy engines over NVLink while the next slice is computed",
                   None: "by NCCL"}[how_fused]
@@ -933,7 +940,7 @@ def strong_cfg5(args, dist, rank, world):
     del out_all
     peer.close(dist)
     A.free()
-    one_gpu_ms = 163.0 * sc
+    one_gpu_ms = 163.0 * sc  # `others.cfg5` of the N = 1 line re-measures it on every run
     return {"workload": wl["desc"] + f" row-sharded over {world} GPUs" + ("" if sc == 1.0 else f" (scaled x{sc})"),
             "scaling": "strong", "rows_per_gpu": mg, "nnz_total": nnz_all, "steps": steps,
             "ms_per_step": ms_step, "GFLOPs": 2.0 * nnz_all * n / ms_step / 1e6,
@@ -973,6 +980,9 @@ def quick_kernel_bench(name, args):
     tdt = torch.float32 if f32 else torch.float64
     mdt = MXG_F32 if f32 else MXG_F64
     keep = MXG_KEEP_F64 if (wl["op"] == "spmv" or not f32) else MXG_KEEP_F32
+    need = wl["nnz"] * (4 + s) + s * K * n + s * m * n + (8 << 30)
+    if torch.cuda.mem_get_info()[0] < need:
+        return {"workload": wl["desc"], "skipped": f"needs {need / 1e9:.0f} GB of device memory"}
     A = DeviceCSR.synth(m, K, wl["nnz"], wl["row_model"], wl["col_model"], seed=wl["seed"], keep=keep)
     g = torch.Generator(device="cuda").manual_seed(4242)
     op = wl["op"]
@@ -1000,7 +1010,7 @@ def quick_kernel_bench(name, args):
             t.free()
         ms_t = _time_ms(tr, 3, 2)
         extra = {"transpose_ms": ms_t, "transpose_GBps": (24 * A.nnz + 4 * (m + K + 2)) / ms_t / 1e6}
-    ms = _time_ms(fn, min(args.steps, 20) if name == "cfg5" else args.steps, 3)
+    ms = _time_ms(fn, min(args.steps, 5) if name == "cfg5" else args.steps, 3)
     nnz = A.nnz
     w = w_alg_bytes(K if op == "crossprod" else m, m if op == "crossprod" else K, nnz, n, s)
     peak, _ = measured_peaks()
@@ -1087,10 +1097,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink rows/nnz (debugging only; invalid as a bench value)")
-    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer", "bulk", "push"],
+    ap.add_argument("--allgather", default="auto", choices=["auto", "mcast", "peer", "bulk", "bulk_cta", "push"],
                     help="all-gather of the step at N > 1: NVLS multicast stores / peer stores from the product kernel, "
                          "copy-engine pushes of finished row slices, or the fastest of them")
-    ap.add_argument("--others", default="cfg2,k64f64,cfg4", help="extra kernel-only configs reported at N=1 ('' to skip)")
+    ap.add_argument("--others", default="cfg2,k64f64,cfg4,cfg5", help="extra kernel-only configs reported at N=1 ('' to skip)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-strong", action="store_true", help="N > 1: skip the row-sharded cfg5 record")

@@ -473,7 +473,26 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
         }
     }
 
-    if (BULK && nr > 0) {
+    if (BULK && g.bulk == 2) {
+        // CTA-wide variant (option spmm_bulk = 2): the four warps' rows are one contiguous block of every destination —
+        // one bulk copy of up to 32 rows (8 KB for fp32 n = 64) per destination, issued by warp 0 once every warp is done
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int cta_row0 = rb * SPMM_WARPS * SPMM_CM_RPW;
+        const int cta_rows = min(SPMM_WARPS * SPMM_CM_RPW, g.m - cta_row0);
+        if (warp == 0 && lane <= g.n_extra && cta_rows > 0) {
+            T *base = Out;
+#pragma unroll
+            for (int d = 0; d < MXG_MAX_DST - 1; d++)
+                if (lane == d + 1) base = static_cast<T *>(g.extra[d]);
+            T *dst = base + (size_t)cta_row0 * g.ldc;
+            const unsigned bytes = (unsigned)(cta_rows * NB * (int)sizeof(T));
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(stage);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else if (BULK && nr > 0) {
         // the warp's nr rows are nr * NB contiguous elements of every destination: one bulk copy per destination,
         // issued by one lane each (generic proxy writes -> async proxy reads need the proxy fence)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -754,7 +773,8 @@ static int spmm_typed(const mxg_csr_s *A, const T *d_x, int out_layout, int n, c
     args.n_extra = n_dst - 1;
     args.mcast = mcast;
     // several destinations of a rows-contiguous result whose rows are stored back to back: bulk copies from shared memory
-    args.bulk = (n_dst > 1 && !mcast && !colmajor && vec && ldc == (size_t)n && options().spmm_bulk != 0) ? 1 : 0;
+    args.bulk = (n_dst > 1 && !mcast && !colmajor && vec && ldc == (size_t)n && options().spmm_bulk != 0)
+                    ? (options().spmm_bulk == 2 ? 2 : 1) : 0;
     for (int d = 0; d < MXG_MAX_DST - 1; d++) args.extra[d] = d + 1 < n_dst ? d_outs[d + 1] : nullptr;
     args.piece = A->piece;
     args.n_pieces = part == 1 ? 0 : A->n_pieces;

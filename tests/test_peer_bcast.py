@@ -28,7 +28,7 @@ def test_multiple_local_destinations_hold_identical_bits():
         for layout in (MXG_ROWS_CONTIGUOUS, MXG_COLS_CONTIGUOUS):
             want = torch.empty(A.m * n, device="cuda", dtype=tdt)
             A.spmm(B, want, n, dtype, layout)
-            for bulk in (1, 0):
+            for bulk in (1, 2, 0):  # warp-wide bulk copies, CTA-wide bulk copies, register stores
                 _lib.set_option("spmm_bulk", bulk)
                 for n_dst in (3, 8):
                     outs = [torch.full((A.m * n,), float("nan"), device="cuda", dtype=tdt) for _ in range(n_dst)]
