@@ -153,6 +153,12 @@ constexpr int SPMM_WARPS = SPMM_THREADS / 32;
 #define SPMM_MINB 8 // resident CTAs per SM the register allocation must allow (8 => 64 registers)
 #endif
 constexpr int SPMM_CM_RPW = 8; // rows per warp of a column-major CTA tile (tile = 32 rows)
+// rows per warp of a BULK CTA: as many as keep the CTA's staging tile within 32 KB, 8 .. 16 (fp32 n = 64: 16 rows per
+// warp, 64 rows = 16 KB per bulk copy and destination)
+__host__ __device__ constexpr int spmm_bulk_rpw(int nb, int elem_bytes)
+{
+    return (32768 / (SPMM_WARPS * nb * elem_bytes)) >= 16 ? 16 : ((32768 / (SPMM_WARPS * nb * elem_bytes)) <= 8 ? 8 : (32768 / (SPMM_WARPS * nb * elem_bytes)));
+}
 
 // Entries pos .. pos + cnt - 1 (cnt <= 32, one per lane in jj / xx) of the current row.
 template <typename T, int V, int LPR, int CPL, int U>
@@ -256,7 +262,7 @@ struct SpmmArgs {
 // MULTI (row-major results only): the launch writes more than the local result — peer copies (g.extra) or an NVLS
 // multicast address (g.mcast).  A separate instantiation so that the single-destination kernel keeps the exact
 // instruction schedule it was tuned with (the shared version cost the fp64 variant 17 %).
-// BULK (a MULTI variant for results whose rows are exactly one column block wide, ldc == n == NB): a warp's SPMM_CM_RPW
+// BULK (a MULTI variant for results whose rows are exactly one column block wide, ldc == n == NB): a warp's SPMM_BULK_RPW
 // finished rows are parked in its slice of shared memory — they are contiguous in the rows-contiguous result — and
 // shipped to every destination (the local result and the peer-mapped results of the other GPUs) as ONE bulk
 // asynchronous copy each (cp.async.bulk.global.shared::cta: the TMA unit streams 2 - 4 KB per destination over NVLink)
@@ -270,7 +276,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
     constexpr int TLD = BR + 1;
     __shared__ T tile[COLMAJOR ? NB * TLD : 1];
     __shared__ unsigned char s_write[COLMAJOR ? BR : 1]; // tile rows this launch has to write
-    __shared__ __align__(128) T stage[BULK ? BR * NB : 1]; // [warp][row of the warp][column]
+    constexpr int BRPW = spmm_bulk_rpw(NB, (int)sizeof(T));
+    __shared__ __align__(128) T stage[BULK ? SPMM_WARPS * BRPW * NB : 1]; // [warp][row of the warp][column]
 
     const int32_t *__restrict__ p = g.p;
     const int32_t *__restrict__ j = g.j;
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
     }
 
     const int rb = blockIdx.x - g.piece_blocks;
-    const int rpw = (COLMAJOR || BULK) ? SPMM_CM_RPW : g.rpw;
+    const int rpw = COLMAJOR ? SPMM_CM_RPW : (BULK ? BRPW : g.rpw);
     const int row0 = (rb * SPMM_WARPS + warp) * rpw;
     const int nr = min(rpw, g.m - row0); // rows this warp owns (<= 0: none)
 
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                                     for (int i = 0; i < V; i++) tile[(col[c] - col0 + i) * TLD + rl] = acc[c].v[i];
                                 }
                         } else if (BULK) {
-                            T *srow = stage + (size_t)(warp * SPMM_CM_RPW + r) * NB;
+                            T *srow = stage + (size_t)(warp * BRPW + r) * NB;
 #pragma unroll
                             for (int c = 0; c < CPL; c++)
                                 if (cok[c]) st_pack<T, V>(srow + (col[c] - col0), acc[c]);
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                 }
                 if (BULK && skip && sub == 0) {
                     // a long row: written by the fix-up launch afterwards; its slot must not ship stale shared memory
-                    T *srow = stage + (size_t)(warp * SPMM_CM_RPW + r) * NB;
+                    T *srow = stage + (size_t)(warp * BRPW + r) * NB;
 #pragma unroll
                     for (int c = 0; c < CPL; c++)
                         if (cok[c]) st_pack<T, V>(srow + (col[c] - col0), acc[c]); // acc is zero: nothing was gathered
@@ -478,8 +485,8 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
         // one bulk copy of up to 32 rows (8 KB for fp32 n = 64) per destination, issued by warp 0 once every warp is done
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        const int cta_row0 = rb * SPMM_WARPS * SPMM_CM_RPW;
-        const int cta_rows = min(SPMM_WARPS * SPMM_CM_RPW, g.m - cta_row0);
+        const int cta_row0 = rb * SPMM_WARPS * BRPW;
+        const int cta_rows = min(SPMM_WARPS * BRPW, g.m - cta_row0);
         if (warp == 0 && lane <= g.n_extra && cta_rows > 0) {
             T *base = Out;
 #pragma unroll
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(SPMM_THREADS, MB) k_spmm(const SpmmArgs g)
                 if (lane == d + 1) base = static_cast<T *>(g.extra[d]);
             T *dst = base + (size_t)row0 * g.ldc;
             const unsigned bytes = (unsigned)(nr * NB * (int)sizeof(T));
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(stage + (size_t)warp * SPMM_CM_RPW * NB);
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(stage + (size_t)warp * BRPW * NB);
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory stays valid until it has been read
@@ -641,7 +648,7 @@ static int dispatch_geom(int lpr, int cpl, SpmmArgs &args, cudaStream_t stream)
     if (rpw > 31) rpw = 31;
     // bulk copies ship exactly one column block per row: the row must be one block wide (and whole vectors)
     if (args.bulk && (COLMAJOR || V == 1 || args.n != lpr * V * cpl)) args.bulk = 0;
-    if (args.bulk) rpw = SPMM_CM_RPW;
+    if (args.bulk) rpw = spmm_bulk_rpw(lpr * V * cpl, (int)sizeof(T));
     args.rpw = rpw;
     args.piece_blocks = ceil_div_i(args.n_pieces, SPMM_WARPS);
     const int row_blocks = ceil_div_i(args.m, SPMM_WARPS * rpw);
