@@ -59,12 +59,12 @@ WORKLOADS = {
 # capture, `roofline.traffic` is reported as null instead of a stale number (tools/ncu_summary.py prints the entry to
 # paste here after a new capture).
 NCU_TRAFFIC = {
-    "cfg3": dict(bytes=15.633024e9 + 0.566459e9, kernel="k_spmm<float, 4, 8, 2, 4, 0, 0, 6, 0, 0>", src="spmm.cu",
-                 src_sha16="37c5b62dfee80289", capture="profiles/r02_v4_spmm_f32_k64_cfg3.ncu.txt"),
-    "k64f64": dict(bytes=39.131083e9 + 1.029803e9, kernel="k_spmm<double, 2, 16, 2, 4, 1, 0, 5, 0, 0>", src="spmm.cu",
-                   src_sha16="37c5b62dfee80289", capture="profiles/r02_v4_spmm_f64_k64.ncu.txt"),
-    "cfg2": dict(bytes=1.220713e9 + 0.019561e9, kernel="k_spmv<0, double, 16>", src="spmv.cu",
-                 src_sha16="b7a13919e41675af", capture="profiles/r02_v4_spmv_f64_cfg2.ncu.txt"),
+    "cfg3": dict(bytes=15.616967e9 + 0.565772e9, kernel="k_spmm<float, 4, 8, 2, 4, 0, 0, 6, 0, 0>", src="spmm.cu",
+                 src_sha16="67d601880a394fe5", capture="profiles/r02_v5_spmm_f32_k64_cfg3.ncu.txt"),
+    "k64f64": dict(bytes=39.134754e9 + 1.028319e9, kernel="k_spmm<double, 2, 16, 2, 4, 1, 0, 5, 0, 0>", src="spmm.cu",
+                   src_sha16="67d601880a394fe5", capture="profiles/r02_v5_spmm_f64_k64.ncu.txt"),
+    "cfg2": dict(bytes=1.220682e9 + 0.018391e9, kernel="k_spmv<0, double, 16>", src="spmv.cu",
+                 src_sha16="b7a13919e41675af", capture="profiles/r02_v5_spmv_f64_cfg2.ncu.txt"),
 }
 
 

@@ -1,5 +1,6 @@
 """CPU tests of the host-side mirror of R/matmul.R: dispatch table, dimension checks and their
 messages, class handling — everything that runs before the first CUDA call."""
+import os
 import numpy as np
 import pytest
 
@@ -219,3 +220,21 @@ def test_chunk_plan_follows_the_rule(forced):
     finally:
         _lib.set_option("pipe_chunk_nnz", old[0])
         _lib.set_option("piece", old[1])
+
+
+def test_bench_traffic_table_is_tied_to_the_current_kernel_sources():
+    """bench.py's roofline.traffic comes from committed ncu captures; every entry names the capture, the kernel and the
+    SHA-256 of the source it was captured from.  A source that changed since must yield null, never a stale number — and
+    the committed table is expected to be current (re-capture with tools/gpu_session.sh ncufull after touching a kernel)."""
+    import bench
+    for wl, e in bench.NCU_TRAFFIC.items():
+        assert os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), e["capture"])), e["capture"]
+        nbytes, why = bench.ncu_traffic(wl)
+        assert nbytes == e["bytes"] and e["src_sha16"] in why, (wl, why)
+    saved = dict(bench.NCU_TRAFFIC["cfg3"])
+    try:
+        bench.NCU_TRAFFIC["cfg3"]["src_sha16"] = "0" * 16
+        nbytes, why = bench.ncu_traffic("cfg3")
+        assert nbytes is None and "another version" in why
+    finally:
+        bench.NCU_TRAFFIC["cfg3"] = saved
