@@ -752,6 +752,15 @@ def e2e_single(args, wl, rx, _lib, p_h, j_h, x_h, d_h, nnz_all, nth):
             o_w = _pinned(np.empty(res_w.size, dtype=res_w.dtype)).reshape(res_w.shape, order="F")
             t_wp, _ = _wall(lambda: (fn(d_p, h, nth, out=o_w) if op == "dense_tcsr" else fn(h, d_p, nth, out=o_w)), k_e2e)
             e2e["warm_handle"]["pinned"] = rec(t_wp, _lib_bytes(_lib), note="page-locked dense operand and result buffer")
+            # A/B on this box: the same two calls with the operand and the result crossing PCIe in one piece
+            call_wp = lambda: (fn(d_p, h, nth, out=o_w) if op == "dense_tcsr" else fn(h, d_p, nth, out=o_w))  # noqa: E731
+            _lib.set_option("host_colsplit", 0)
+            call_wp()
+            t_wp1, _ = _wall(call_wp, k_e2e)
+            _lib.set_option("host_colsplit", 1)
+            e2e["warm_handle"]["pinned"]["one_piece_ms_per_step"] = t_wp1 * 1e3
+            e2e["warm_handle"]["pinned"]["note"] += ("; the operand and the result cross PCIe as two column halves so that the directions overlap "
+                                                      "(option host_colsplit; `one_piece_ms_per_step` = the same call with it off, on this box)")
             del o_w
         rx.gpu_csr_free(h)
         del res_w

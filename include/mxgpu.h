@@ -107,7 +107,12 @@ int mxg_get_devices(int *n);
  *             "host_arena_max_mb" (largest page-locked arena the library may hold, 4096; beyond it the driver's own
  *             copies are used), "host_result_pool_mb" (page-locked result memory handed out by mxg_host_alloc, 4096),
  *             "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
- *             freshly allocated R matrix is otherwise filled at page-fault speed, 1);
+ *             freshly allocated R matrix is otherwise filled at page-fault speed, 1),
+ *             "host_colsplit" (products on a device-resident CSR with host operands, rows-contiguous both: the dense
+ *             operand goes up and the result comes down as two column halves, so the second upload and both kernels
+ *             hide behind the first download; 1 = only for a page-locked dense operand and where each output element is
+ *             summed in the same order as in the full-width product (bit-identical results: rows of 256 bytes),
+ *             2 = wherever a half row is >= 128 bytes, 0 = off);
  *   several devices : "multi_min_nnz" (level-1 calls below this many stored entries stay on one device, 4 Mi),
  *             "multi_pageable" (0 = calls whose CSR arrays are pageable stay on one device: they are bound by the host
  *             threads' bounce copies, which more devices do not speed up; 1 = spread them too),

@@ -75,6 +75,9 @@ struct Options {
     long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
     long host_result_pool_mb = 4096; // page-locked result memory the glue's allocator hook may hold (mxg_host_alloc)
     long host_thp = 1;             // ask for transparent huge pages on large pageable result buffers before their first touch
+    long host_colsplit = 1;        // warm products (device-resident CSR, host operands): the dense operand and the result cross PCIe as two column
+                                   // halves so that uploads and downloads overlap; 1 = page-locked operand and unchanged summation order only,
+                                   // 2 = wherever the halves are >= 128 bytes wide, 0 = off
     long cache_mb = 0;             // level-1 operand cache (device-resident CSR + dense operands keyed on the host arrays); 0 = off
 };
 Options &options();

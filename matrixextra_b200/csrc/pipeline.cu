@@ -907,6 +907,127 @@ int handle_chunks(mxg_csr_s *A, cudaStream_t stream)
     return MXG_OK;
 }
 
+// Sub-teams per warp the SpMM kernel runs an n-column product of packed, 16-byte aligned operands with (the team
+// geometry of spmm.cu: spmm_typed / dispatch_geom).  A row's entries are dealt to the sub-teams round-robin and the
+// sub-team sums are combined by a tree, so two products whose sub-team counts agree sum every output element in the
+// same order.  0 = not predictable from here (scalar path, forced geometry).
+static int spmm_subteams(size_t n, size_t s)
+{
+    const size_t V = 16 / s;
+    if (n == 0 || n % V != 0 || options().spmm_lpr > 0 || options().spmm_cpl != 0) return 0;
+    const size_t nvec = n / V;
+    size_t lpr = 4;
+    while (lpr < nvec && lpr < 32) lpr *= 2;
+    if (lpr >= 8 && nvec > 8 && !(lpr == 32 && nvec > 32)) lpr /= 2; // two vectors per lane on a half-width team
+    return (int)(32 / lpr);
+}
+
+// The warm product in two column halves (host_colsplit).  PCIe is full duplex but the plain warm call uses one direction
+// at a time: the result needs ALL of the dense operand.  Cut by columns, half 0 of the result can leave while half 1 of
+// the operand arrives: 2-D copies of >= 128-byte lines at the caller's pitch run at link speed in both directions
+// (tools/dma2d_probe.cu: 51.4 / 52.2 GB/s for 128-byte lines at a 256-byte pitch, against 55.6 / 56.5 GB/s for whole
+// rows: the copies alone take 13.1 ms in this schedule and 13.6 ms in one piece).  Timeline for cfg3 fp32 n = 64:
+//   h2d    | B[:, :32] 2.5 ms | B[:, 32:] 2.5 ms |
+//   kernel |                  | half 0, chunk by chunk | half 1 ...
+//   d2h    |                    | Out[:, :32] 4.9 ms ............| Out[:, 32:] 4.9 ms |
+// Both halves are packed on the device ([K][n/2] and [m][n/2]): the kernels see ordinary n/2-column products.
+static int handle_spmm_host_split(DeviceState *st, mxg_csr_s *A, int dtype, int n, const void *B, size_t ldb, void *Out, size_t ldc,
+                                  const std::vector<int32_t> &chunk_row, size_t max_rows)
+{
+    const size_t s = dtype == MXG_F64 ? 8 : 4;
+    const size_t rows = (size_t)A->m, Kz = (size_t)A->K, nh = (size_t)n / 2;
+    const int C = (int)chunk_row.size() - 1, U = 2 * C;
+    Scratch sc(st);
+    const bool stage = options().host_stage != 0;
+    const bool stage_B = stage && !host_is_pinned(B);
+    bool stage_out = stage && !host_is_pinned(Out);
+    if (stage_out) host_prepare_result(Out, ((rows - 1) * ldc + (size_t)n) * s);
+    char *d_Bh[2] = {nullptr, nullptr}, *d_Oh[2] = {nullptr, nullptr};
+    for (int h = 0; h < 2; h++) {
+        MXG_TRY(sc.alloc((void **)&d_Bh[h], Kz * nh * s));
+        MXG_TRY(sc.alloc((void **)&d_Oh[h], rows * nh * s));
+    }
+    auto up = [](size_t v) { return (v + 4095) & ~(size_t)4095; };
+    const int S = (int)std::min<long>(std::max<long>(options().pipe_slots, 3), 8);
+    const size_t in_slot = stage_B ? (size_t)16 << 20 : 0;
+    const size_t out_slot_bytes = stage_out ? up(max_rows * nh * s) : 0;
+    InRing ring;
+    char *out_base = nullptr;
+    if (in_slot + out_slot_bytes > 0) {
+        char *base = nullptr;
+        if (pinned_arena(st, (size_t)S * (in_slot + out_slot_bytes), &base) != MXG_OK) {
+            cudaGetLastError();
+            last_error_ref().clear();
+            stage_out = false; // the driver's own copies still work
+        } else {
+            if (in_slot) MXG_TRY(ring.init(sc, base, in_slot, S));
+            out_base = base + (size_t)S * in_slot;
+        }
+    }
+    std::vector<cudaEvent_t> ev_done((size_t)U), ev_out((size_t)(stage_out ? U : 0));
+    for (int u = 0; u < U; u++) MXG_TRY(sc.event(&ev_done[(size_t)u]));
+    for (size_t u = 0; u < ev_out.size(); u++) MXG_TRY(sc.event(&ev_out[u]));
+    auto out_slot = [&](int u) { return out_base + (size_t)(u % S) * out_slot_bytes; };
+    MXG_TRY(chain(sc, st->stream, st->h2d)); // the buffers exist in stream order of st->stream
+
+    // unit u = (half u / C, chunk u % C): the order in which result blocks leave the device
+    auto upload = [&](int h) -> int {
+        const char *src = static_cast<const char *>(B) + (size_t)h * nh * s;
+        MXG_TRY(upload_lines(ring.enabled() ? &ring : nullptr, d_Bh[h], nh * s, src, ldb * s, nh * s, Kz, st->h2d));
+        return chain(sc, st->h2d, st->stream);
+    };
+    auto compute = [&](int h) -> int { // long rows first, then the row chunks in download order
+        if (A->n_pieces > 0)
+            MXG_TRY(launch_spmm_rows(A, dtype, MXG_ROWS_CONTIGUOUS, (int)nh, d_Bh[h], nh, d_Oh[h], nh, 0, 0, /*pieces=*/1, st->stream));
+        for (int c = 0; c < C; c++) {
+            MXG_TRY(launch_spmm_rows(A, dtype, MXG_ROWS_CONTIGUOUS, (int)nh, d_Bh[h], nh, d_Oh[h], nh, chunk_row[(size_t)c],
+                                     chunk_row[(size_t)c + 1], /*pieces=*/0, st->stream));
+            MXG_CUDA_TRY(cudaEventRecord(ev_done[(size_t)(h * C + c)], st->stream));
+        }
+        return MXG_OK;
+    };
+    auto host_block = [&](int u) { // where unit u lives in the caller's result
+        const size_t r0 = (size_t)chunk_row[(size_t)(u % C)];
+        return static_cast<char *>(Out) + (r0 * ldc + (size_t)(u / C) * nh) * s;
+    };
+    auto download = [&](int u) -> int {
+        const int h = u / C, c = u % C;
+        const size_t r0 = (size_t)chunk_row[(size_t)c], nr = (size_t)chunk_row[(size_t)c + 1] - r0;
+        MXG_CUDA_TRY(cudaStreamWaitEvent(st->d2h, ev_done[(size_t)u], 0));
+        const char *d_o = d_Oh[h] + r0 * nh * s;
+        if (stage_out) {
+            MXG_TRY(copy_rows(out_slot(u), nh * s, d_o, nh * s, nh * s, nr, cudaMemcpyDeviceToHost, st->d2h));
+            MXG_CUDA_TRY(cudaEventRecord(ev_out[(size_t)u], st->d2h));
+        } else {
+            MXG_TRY(copy_rows(host_block(u), ldc * s, d_o, nh * s, nh * s, nr, cudaMemcpyDeviceToHost, st->d2h));
+        }
+        return MXG_OK;
+    };
+    auto drain = [&](int u) -> int {
+        if (!stage_out) return MXG_OK;
+        const size_t nr = (size_t)chunk_row[(size_t)(u % C) + 1] - (size_t)chunk_row[(size_t)(u % C)];
+        MXG_CUDA_TRY(cudaEventSynchronize(ev_out[(size_t)u]));
+        host_copy_2d(host_block(u), ldc * s, out_slot(u), nh * s, nh * s, nr);
+        return MXG_OK;
+    };
+    // A pageable operand is packed by THIS thread (upload blocks while the host threads fill the ring), so everything of
+    // half 0 that needs no draining is put on the streams before half 1 is touched: the device then computes and
+    // downloads half 0 while the host packs half 1.
+    MXG_TRY(upload(0));
+    MXG_TRY(compute(0));
+    const int pre = stage_out ? std::min(S - 1, C) : C; // downloads that fit the free output slots
+    for (int u = 0; u < pre; u++) MXG_TRY(download(u));
+    MXG_TRY(upload(1));
+    MXG_TRY(compute(1));
+    for (int u = pre; u < U + S - 1; u++) {
+        if (stage_out && u >= S - 1 && u - (S - 1) < U) MXG_TRY(drain(u - (S - 1)));
+        if (u < U) MXG_TRY(download(u));
+    }
+    MXG_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    MXG_CUDA_TRY(cudaStreamSynchronize(st->d2h));
+    return MXG_OK;
+}
+
 int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, int b_layout, int n, const void *B, size_t ldb,
                      void *Out, size_t ldc, const void *d_B_resident, void **d_B_keep)
 {
@@ -942,6 +1063,17 @@ int handle_spmm_host(DeviceState *st, mxg_csr_s *A, int dtype, int out_layout, i
     const int C = (int)chunk_row.size() - 1;
     size_t max_rows = 0;
     for (int c = 0; c < C; c++) max_rows = std::max(max_rows, (size_t)(chunk_row[(size_t)c + 1] - chunk_row[(size_t)c]));
+
+    // Two column halves where that lets the directions of the link overlap.  By default (1) only where it changes no bit of
+    // the result and the dense operand is page-locked: a pageable operand is packed into the ring by the host threads,
+    // and packing half rows reads every row of it twice (measured, cfg3: 13.6 instead of 14.7 ms page-locked, 15.7
+    // instead of 15.1 ms pageable).
+    const long colsplit = options().host_colsplit;
+    if (colsplit != 0 && out_layout == MXG_ROWS_CONTIGUOUS && b_layout == MXG_ROWS_CONTIGUOUS && !d_B_resident && !d_B_keep && K > 0 &&
+        A->nnz > 0 && nz % (2 * vec) == 0 && nz / 2 * s >= 128 && rows * nz * s >= ((size_t)32 << 20) &&
+        (colsplit == 2 ||
+         (host_is_pinned(B) && spmm_subteams(nz, s) != 0 && spmm_subteams(nz, s) == spmm_subteams(nz / 2, s))))
+        return handle_spmm_host_split(st, A, dtype, n, B, ldb, Out, ldc, chunk_row, max_rows);
 
     Scratch sc(st);
     const bool stage = options().host_stage != 0;

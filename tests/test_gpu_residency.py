@@ -36,6 +36,8 @@ def lib():
     _lib.set_option("host_result_pool_mb", 4096)
     _lib.set_option("piece", 1024)
     _lib.set_option("pipe_chunk_nnz", 0)
+    _lib.set_option("host_colsplit", 1)
+    _lib.set_option("pipe_slots", 4)
 
 
 def _bytes(lib):
@@ -307,3 +309,49 @@ def test_results_are_allocated_from_the_page_locked_pool(rx, lib, port):
         lib.call("mxg_host_alloc", 65 << 20, C.byref(a))  # beyond the cap: the caller falls back
     lib.call("mxg_trim")
     assert stats()[1] == 0
+
+
+@pytest.mark.parametrize("dt,n", [(np.float32, 64), (np.float64, 32), (np.float64, 64), (np.float32, 48)])
+def test_warm_product_in_two_column_halves(rx, lib, port, dt, n):
+    """host_colsplit: a result of >= 32 MiB leaves as two column halves so that the link's directions overlap
+    (pipeline.cu: handle_spmm_host_split).  Default mode: taken only where every element is summed in the same order
+    (256-byte rows: fp32 n = 64, fp64 n = 32) and then bit-identical to the unsplit product; mode 2 splits fp64 n = 64
+    as well (other team geometry: equal within the tolerance only); 96-byte halves (fp32 n = 48) are never split.
+    Every mix of pageable / page-locked operand and result, with long rows (pieces) present."""
+    import torch
+    lib.set_option("piece", 64)
+    m, K = 180_000, 4000
+    p, j, x = powerlaw_csr(m, K, 12, seed=21, cap=3000)
+    sfx = _sfx(dt)
+    call = getattr(rx, "gpu_csr_dense_tcrossprod_" + sfx)
+    h = rx.as_gpu_csr(p, j, x, K, keep_float64=True, keep_float32=True)
+    try:
+        X = np.asfortranarray(np.random.default_rng(n).standard_normal((n, K)).astype(dt))  # (n x K): X %*% t(A)
+        assert n * m * X.itemsize >= 32 << 20
+        lib.set_option("host_colsplit", 0)
+        whole = call(X, h, out=np.empty((n, m), dtype=dt, order="F"))
+        want = getattr(port, "tcrossprod_dense_csr_" + sfx)(X, p, j, x, None, K)
+        assert rel_err(whole, want) <= _tol(dt)
+        t_dt = torch.float32 if dt == np.float32 else torch.float64
+        Xp = torch.empty(n * K, dtype=t_dt).pin_memory().numpy().reshape((n, K), order="F")
+        Xp[...] = X
+        for mode in (1, 2):
+            lib.set_option("host_colsplit", mode)
+            for pin_x, pin_out in ((False, False), (True, True), (False, True), (True, False)):
+                out = (torch.full((n * m,), float("nan"), dtype=t_dt).pin_memory().numpy().reshape((n, m), order="F") if pin_out
+                       else np.full((n, m), np.nan, dtype=dt, order="F"))
+                got = call(Xp if pin_x else X, h, out=out)
+                assert _bytes(lib) == (X.nbytes, n * m * X.itemsize)
+                if mode == 1 or n * X.itemsize != 512:
+                    assert np.array_equal(got, whole), (mode, pin_x, pin_out)
+                else:  # fp64 n = 64 in mode 2: two 32-column products on 4 sub-teams instead of one on 2
+                    assert not np.isnan(got).any() and rel_err(got, want) <= _tol(dt)
+                    assert np.array_equal(got[:, np.diff(p) <= 1], whole[:, np.diff(p) <= 1])  # nothing to re-order there
+        # fewer output slots than chunks and more: the ring of page-locked slots wraps in both
+        lib.set_option("host_colsplit", 2)
+        for slots in (3, 8):
+            lib.set_option("pipe_slots", slots)
+            got = call(X, h, out=np.full((n, m), np.nan, dtype=dt, order="F"))
+            assert rel_err(got, want) <= _tol(dt) and not np.isnan(got).any()
+    finally:
+        rx.gpu_csr_free(h)
