@@ -137,7 +137,16 @@ int run_on_devices(int G, Body body)
         last_call_bytes(&up[(size_t)g], &down[(size_t)g]);
     };
     std::vector<std::thread> threads;
-    for (int g = 1; g < G; g++) threads.emplace_back(work, g);
+    threads.reserve((size_t)G);
+    int started = 1;
+    try {
+        for (; started < G; started++) threads.emplace_back(work, started);
+    } catch (...) { // no thread to be had: the blocks without one fail here, so that nobody waits for them (DenseShare)
+        for (int g = started; g < G; g++) {
+            rc[(size_t)g] = body(g, nullptr, fail(MXG_ERR_CUDA, "multi-device call: could not start a host thread for device %d", g_devs[g]));
+            err[(size_t)g] = last_error_ref();
+        }
+    }
     work(0);
     for (std::thread &t : threads) t.join();
     cudaSetDevice(cur);
@@ -284,8 +293,23 @@ size_t handle_bytes(const mxg_csr_s *h)
     return b;
 }
 
+// entries are released on the device that holds them, whichever device the caller has made current since
+struct OnDevice {
+    int prev = -1;
+    explicit OnDevice(int dev)
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+    }
+    ~OnDevice()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 void drop_csr(std::list<CsrEntry>::iterator it)
 {
+    OnDevice on(it->device);
     g_cache_bytes -= it->bytes;
     csr_handle_free(it->h);
     g_csr_cache.erase(it);
@@ -293,6 +317,7 @@ void drop_csr(std::list<CsrEntry>::iterator it)
 
 void drop_dense(std::list<DenseEntry>::iterator it)
 {
+    OnDevice on(it->device);
     g_cache_bytes -= it->bytes;
     cudaFreeAsync(it->d_B, it->stream);
     g_dense_cache.erase(it);
