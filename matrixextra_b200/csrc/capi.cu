@@ -189,8 +189,9 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
         if (b_layout == MXG_ROWS_CONTIGUOUS && ldb < n) return fail(MXG_ERR_ARG, "dense operand: ldb < n");
         if (b_layout == MXG_COLS_CONTIGUOUS && ldb < K) return fail(MXG_ERR_ARG, "dense operand: ldb < K");
     }
-    void *d_B = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_B, std::max<size_t>(K * ld * s, 16), stream));
+    StreamBuf buf, tmp; // handed back on every failure below
+    MXG_CUDA_TRY(buf.alloc(K * ld * s, stream));
+    void *d_B = buf.ptr;
     if (K > 0 && n > 0) {
         if (b_layout == MXG_ROWS_CONTIGUOUS) {
             if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
@@ -202,8 +203,8 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
                 MXG_CUDA_TRY(cudaMemcpy2DAsync(d_B, ld * s, B, ldb * s, n * s, K, cudaMemcpyHostToDevice, stream));
             }
         } else {
-            void *d_tmp = nullptr;
-            MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, K * n * s, stream));
+            MXG_CUDA_TRY(tmp.alloc(K * n * s, stream));
+            void *d_tmp = tmp.ptr;
             if (ldb == K) {
                 DeviceState *st = nullptr;
                 MXG_TRY(current_state(&st));
@@ -214,9 +215,9 @@ static int upload_dense_rows(int dtype, int b_layout, size_t K, size_t n, const 
             if (ld != n) MXG_CUDA_TRY(cudaMemsetAsync(d_B, 0, K * ld * s, stream));
             // d_tmp is n rows of K contiguous -> d_B is K rows of n contiguous
             MXG_TRY(launch_transpose_dense((int)s, n, K, d_tmp, K, d_B, ld, stream));
-            MXG_CUDA_TRY(cudaFreeAsync(d_tmp, stream));
         }
     }
+    buf.release();
     *d_out = d_B;
     *ld_out = ld;
     return MXG_OK;
@@ -675,12 +676,11 @@ int mxg_dev_spmm(mxg_csr_t A, int dtype, int out_layout, int b_layout, int n, co
     // column-major dense operand: K5 into a temporary rows-contiguous copy first
     const size_t sz = dtype == MXG_F64 ? 8 : 4;
     const size_t ld = round_up((size_t)n, 16 / sz);
-    void *d_tmp = nullptr;
-    MXG_CUDA_TRY(cudaMallocAsync(&d_tmp, (size_t)A->K * ld * sz, s));
-    if (ld != (size_t)n) MXG_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, (size_t)A->K * ld * sz, s));
-    MXG_TRY(launch_transpose_dense((int)sz, (size_t)n, (size_t)A->K, d_B, ldb, d_tmp, ld, s));
-    MXG_TRY(launch_spmm(A, dtype, out_layout, n, d_tmp, ld, d_Out, ldc, s));
-    MXG_CUDA_TRY(cudaFreeAsync(d_tmp, s));
+    StreamBuf tmp; // freed in stream order behind the product, on every path
+    MXG_CUDA_TRY(tmp.alloc((size_t)A->K * ld * sz, s));
+    if (ld != (size_t)n) MXG_CUDA_TRY(cudaMemsetAsync(tmp.ptr, 0, (size_t)A->K * ld * sz, s));
+    MXG_TRY(launch_transpose_dense((int)sz, (size_t)n, (size_t)A->K, d_B, ldb, tmp.ptr, ld, s));
+    MXG_TRY(launch_spmm(A, dtype, out_layout, n, tmp.ptr, ld, d_Out, ldc, s));
     return MXG_OK;
 }
 
@@ -1071,18 +1071,16 @@ int mxg_spmv_csr(int ytype, int m, int K, const int32_t *p, const int32_t *j, co
     if (m > 0) {
         const size_t ys = ytype == MXG_Y_NUMERIC ? 8 : 4;
         const size_t os = ytype == MXG_Y_FLOAT32 ? 4 : 8;
-        void *d_y = nullptr, *d_out = nullptr;
         cudaStream_t s = st->stream;
         auto body = [&]() -> int {
             if (!out) return fail(MXG_ERR_ARG, "output is NULL");
             if (K > 0 && !y) return fail(MXG_ERR_ARG, "vector is NULL");
-            MXG_CUDA_TRY(cudaMallocAsync(&d_y, std::max<size_t>((size_t)K * ys, 16), s));
-            MXG_CUDA_TRY(cudaMallocAsync(&d_out, (size_t)m * os, s));
-            if (K > 0) MXG_CUDA_TRY(cudaMemcpyAsync(d_y, y, (size_t)K * ys, cudaMemcpyHostToDevice, s));
-            MXG_TRY(launch_spmv(A, ytype, d_y, d_out, s));
-            MXG_CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)m * os, cudaMemcpyDeviceToHost, s));
-            MXG_CUDA_TRY(cudaFreeAsync(d_y, s));
-            MXG_CUDA_TRY(cudaFreeAsync(d_out, s));
+            StreamBuf d_y, d_out;
+            MXG_CUDA_TRY(d_y.alloc((size_t)K * ys, s));
+            MXG_CUDA_TRY(d_out.alloc((size_t)m * os, s));
+            if (K > 0) MXG_CUDA_TRY(cudaMemcpyAsync(d_y.ptr, y, (size_t)K * ys, cudaMemcpyHostToDevice, s));
+            MXG_TRY(launch_spmv(A, ytype, d_y.ptr, d_out.ptr, s));
+            MXG_CUDA_TRY(cudaMemcpyAsync(out, d_out.ptr, (size_t)m * os, cudaMemcpyDeviceToHost, s));
             MXG_CUDA_TRY(cudaStreamSynchronize(s));
             return MXG_OK;
         };

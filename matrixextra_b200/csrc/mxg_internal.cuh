@@ -263,6 +263,30 @@ int peer_barrier_failed(int *failed);
 int csr_build_stats(mxg_csr_s *h, int validate, cudaStream_t stream);
 int convert_f64_to_f32(const double *d_src, float *d_dst, size_t n, cudaStream_t stream);
 int exclusive_scan_i32(const int32_t *d_in, int32_t *d_out, size_t n, cudaStream_t stream); // out[i] = sum in[0..i)
+// one stream-ordered device buffer that is handed back on every exit path unless release()d to the caller
+struct StreamBuf {
+    void *ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    StreamBuf() = default;
+    StreamBuf(const StreamBuf &) = delete;
+    StreamBuf &operator=(const StreamBuf &) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t s)
+    {
+        stream = s;
+        return cudaMallocAsync(&ptr, bytes > 16 ? bytes : 16, s);
+    }
+    void *release()
+    {
+        void *q = ptr;
+        ptr = nullptr;
+        return q;
+    }
+    ~StreamBuf()
+    {
+        if (ptr) cudaFreeAsync(ptr, stream);
+    }
+};
+
 // workspace of the long-row partial sums for ONE product: leased on the call's stream, released when the lease dies
 // (stream-ordered, i.e. behind the fix-up launch that reads it)
 struct PartialLease {
