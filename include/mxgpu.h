@@ -108,6 +108,9 @@ int mxg_get_devices(int *n);
  *             copies are used), "host_result_pool_mb" (page-locked result memory handed out by mxg_host_alloc, 4096),
  *             "host_thp" (madvise(MADV_HUGEPAGE) on a large pageable result before its first touch: a
  *             freshly allocated R matrix is otherwise filled at page-fault speed, 1),
+ *             "host_pin_register" (a NEW page-locked block — staging arena, result pool — is huge-page backed anonymous
+ *             memory touched by the host threads and registered with the driver, 5 - 10 x faster to create than a
+ *             cudaHostAlloc block of that size, 1; 0 = cudaHostAlloc),
  *             "host_colsplit" (products on a device-resident CSR with host operands, rows-contiguous both: the dense
  *             operand goes up and the result comes down as two column halves, so the second upload and both kernels
  *             hide behind the first download; 1 = only for a page-locked dense operand and where each output element is

@@ -445,6 +445,7 @@ static long *option_slot(const char *name)
     if (!strcmp(name, "host_narrow")) return &o.host_narrow;
     if (!strcmp(name, "host_stage")) return &o.host_stage;
     if (!strcmp(name, "host_colsplit")) return &o.host_colsplit;
+    if (!strcmp(name, "host_pin_register")) return &o.host_pin_register;
     if (!strcmp(name, "host_pack")) return &o.host_pack;
     if (!strcmp(name, "host_pack_lag")) return &o.host_pack_lag;
     if (!strcmp(name, "pipe_slots")) return &o.pipe_slots;

@@ -324,39 +324,79 @@ bool host_is_pinned(const void *ptr)
     return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
 }
 
+// ------------------------------------------------------------------------------------------------
+// A new page-locked block.  cudaHostAlloc creates and pins its pages 4 KiB at a time, on one thread: 120 - 360 ms for
+// 256 MiB on the B200 host — ten times what a product of that size takes.  Cheaper (tools/pinalloc_probe.cu,
+// profiles/r02_pinned_block_alloc_probe.jsonl): map anonymous memory, ask for transparent huge pages, touch it with the
+// host threads (one fault per 2 MiB) and register it with the driver — 20 ms for 256 MiB, 42 - 95 ms for 512 MiB, the
+// same 57 GB/s as a DMA target.  Where the mapping or the registration is refused, cudaHostAlloc it is.
+// ------------------------------------------------------------------------------------------------
+int pinned_block_alloc(size_t bytes, PinnedBlock *blk)
+{
+    const size_t huge = (size_t)2 << 20;
+    const size_t want = (std::max<size_t>(bytes, 1) + huge - 1) & ~(huge - 1);
+    *blk = PinnedBlock();
+    if (options().host_pin_register != 0) {
+        const size_t map_len = want + huge;
+        void *q = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (q != MAP_FAILED) {
+            char *al = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(q) + huge - 1) & ~(uintptr_t)(huge - 1));
+            madvise(al, want, MADV_HUGEPAGE); // advisory: 4 KiB pages otherwise
+            HostPool::get().run(want / huge, host_threads(), [&](size_t t) {
+                for (size_t o = 0; o < huge; o += 4096) al[t * huge + o] = 0;
+            });
+            if (cudaHostRegister(al, want, cudaHostRegisterPortable) == cudaSuccess) {
+                blk->ptr = al;
+                blk->bytes = want;
+                blk->map_base = q;
+                blk->map_len = map_len;
+                return MXG_OK;
+            }
+            cudaGetLastError();
+            munmap(q, map_len);
+        }
+    }
+    void *h = nullptr;
+    if (cudaHostAlloc(&h, want, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MXG_ERR_CUDA, "cudaHostAlloc of %zu MiB failed", want >> 20);
+    }
+    blk->ptr = h;
+    blk->bytes = want;
+    return MXG_OK;
+}
+
+void pinned_block_free(PinnedBlock *blk)
+{
+    if (!blk->ptr) return;
+    if (blk->map_base) {
+        cudaHostUnregister(blk->ptr);
+        munmap(blk->map_base, blk->map_len);
+    } else {
+        cudaFreeHost(blk->ptr);
+    }
+    cudaGetLastError();
+    *blk = PinnedBlock();
+}
+
 int pinned_arena(DeviceState *st, size_t bytes, char **base)
 {
     const long cap_mb = options().host_arena_max_mb;
     if (cap_mb > 0 && bytes > ((size_t)cap_mb << 20))
         return fail(MXG_ERR_CUDA, "staging arena of %zu MiB exceeds host_arena_max_mb = %ld", bytes >> 20, cap_mb);
-    if (bytes > st->pin_bytes) {
-        if (st->pin_base) {
-            MXG_CUDA_TRY(cudaFreeHost(st->pin_base));
-            st->pin_base = nullptr;
-            st->pin_bytes = 0;
-        }
+    if (bytes > st->pin.bytes) {
+        pinned_block_free(&st->pin);
         const size_t want = (bytes + ((size_t)1 << 22) - 1) & ~(((size_t)1 << 22) - 1);
-        MXG_CUDA_TRY(cudaHostAlloc(&st->pin_base, want, cudaHostAllocDefault));
-        st->pin_bytes = want;
-        // touch every page now, in parallel: the first DMA must not pay for it
-        char *b = static_cast<char *>(st->pin_base);
-        const size_t grain = (size_t)1 << 21;
-        HostPool::get().run((want + grain - 1) / grain, host_threads(), [&](size_t t) {
-            const size_t a = t * grain, e = std::min(want, a + grain);
-            memset(b + a, 0, e - a);
-        });
+        MXG_TRY(pinned_block_alloc(want, &st->pin));
+        // every page is touched already (by the host threads, or by cudaHostAlloc): the first DMA does not pay for it
     }
-    *base = static_cast<char *>(st->pin_base);
+    *base = static_cast<char *>(st->pin.ptr);
     return MXG_OK;
 }
 
 int pinned_arena_release(DeviceState *st)
 {
-    if (st->pin_base) {
-        MXG_CUDA_TRY(cudaFreeHost(st->pin_base));
-        st->pin_base = nullptr;
-        st->pin_bytes = 0;
-    }
+    pinned_block_free(&st->pin);
     return MXG_OK;
 }
 
@@ -367,7 +407,7 @@ int pinned_arena_release(DeviceState *st)
 // exist yet, and filling it is bound by the kernel's page zeroing (19 - 26 GB/s on the 16-core B200 host, against a
 // 52 GB/s link; profiles/r02_host_first_touch_probe.jsonl) on top of a bounce through a page-locked slot.  R lets a
 // package supply the allocator of a vector (Rf_allocVector3 + R_allocator_t), so the glue allocates large results HERE:
-// a pool of cudaHostAlloc'ed blocks that are recycled when R's garbage collector frees the matrix.  The device then
+// a pool of page-locked blocks (pinned_block_alloc above) that are recycled when R's garbage collector frees the matrix.  The device then
 // writes the result straight into the R object — no slot, no host copy, no first touch.
 // Blocks are rounded up to 2 MiB and reused for requests they fit with at most 25 % waste; the pool holds at most
 // option "host_result_pool_mb" (4096) of free + live blocks, beyond which mxg_host_alloc fails and the glue falls back to
@@ -375,7 +415,8 @@ int pinned_arena_release(DeviceState *st)
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct PoolBlock {
-    void *ptr;
+    PinnedBlock mem;
+    void *ptr; // = mem.ptr
     size_t bytes;
     unsigned long long stamp;
 };
@@ -409,19 +450,16 @@ int result_pool_alloc(size_t bytes, void **out)
         size_t oldest = 0;
         for (size_t i = 1; i < g_rp_free.size(); i++)
             if (g_rp_free[i].stamp < g_rp_free[oldest].stamp) oldest = i;
-        cudaFreeHost(g_rp_free[oldest].ptr);
+        pinned_block_free(&g_rp_free[oldest].mem);
         g_rp_bytes -= g_rp_free[oldest].bytes;
         g_rp_free.erase(g_rp_free.begin() + (long)oldest);
     }
     if (g_rp_bytes + want > cap) return fail(MXG_ERR_CUDA, "host_alloc: result pool is full (%zu MiB live)", g_rp_bytes >> 20);
-    void *q = nullptr;
-    if (cudaHostAlloc(&q, want, cudaHostAllocPortable) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(MXG_ERR_CUDA, "host_alloc: cudaHostAlloc of %zu MiB failed", want >> 20);
-    }
-    g_rp_live.push_back(PoolBlock{q, want, 0});
+    PinnedBlock mem;
+    MXG_TRY(pinned_block_alloc(want, &mem));
+    g_rp_live.push_back(PoolBlock{mem, mem.ptr, want, 0});
     g_rp_bytes += want;
-    *out = q;
+    *out = mem.ptr;
     return MXG_OK;
 }
 
@@ -456,8 +494,8 @@ void result_pool_stats(size_t *live_bytes, size_t *free_bytes, int *blocks)
 void result_pool_trim()
 {
     std::lock_guard<std::mutex> lk(g_rp_mu);
-    for (const PoolBlock &b : g_rp_free) {
-        cudaFreeHost(b.ptr);
+    for (PoolBlock &b : g_rp_free) {
+        pinned_block_free(&b.mem);
         g_rp_bytes -= b.bytes;
     }
     g_rp_free.clear();

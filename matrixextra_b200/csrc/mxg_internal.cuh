@@ -74,6 +74,8 @@ struct Options {
     long multi_pageable = 0;       // ... and calls whose CSR arrays are pageable stay on one device too (they are bound by the host threads)
     long multi_dense_share = 1;    // ... the dense operand crosses PCIe once (a slice per device) and is completed over NVLink
     long host_result_pool_mb = 4096; // page-locked result memory the glue's allocator hook may hold (mxg_host_alloc)
+    long host_pin_register = 1;    // new page-locked blocks (arena, result pool): huge-page backed anonymous memory + cudaHostRegister (5 - 10 x faster
+                                   // to create than cudaHostAlloc); 0 = cudaHostAlloc
     long host_thp = 1;             // ask for transparent huge pages on large pageable result buffers before their first touch
     long host_colsplit = 1;        // warm products (device-resident CSR, host operands): the dense operand and the result cross PCIe as two column
                                    // halves so that uploads and downloads overlap; 1 = page-locked operand and unchanged summation order only,
@@ -133,6 +135,16 @@ namespace mxg {
 
 // per-device state of the host-buffer (level-1) entry points: three streams so that uploads, kernels and
 // downloads of consecutive row chunks overlap (PCIe is full duplex)
+// a page-locked host block: huge-page backed anonymous memory registered with the driver, or a cudaHostAlloc block
+struct PinnedBlock {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    void *map_base = nullptr; // non-NULL: mmap'ed + cudaHostRegister'ed (ptr is the 2 MiB-aligned interior)
+    size_t map_len = 0;
+};
+int pinned_block_alloc(size_t bytes, PinnedBlock *blk);
+void pinned_block_free(PinnedBlock *blk);
+
 struct DeviceState {
     bool ready = false;
     cudaStream_t stream = nullptr; // kernels (and everything of the non-pipelined calls)
@@ -146,8 +158,7 @@ struct DeviceState {
     void *share_buf = nullptr;
     size_t share_bytes = 0;
     // page-locked staging arena of the streamed path (hoststage.cu), grow-only, released by mxg_trim
-    void *pin_base = nullptr;
-    size_t pin_bytes = 0;
+    PinnedBlock pin; // the page-locked staging arena (grow-only; hoststage.cu)
 };
 int current_state(DeviceState **out);
 

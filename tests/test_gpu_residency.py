@@ -355,3 +355,49 @@ def test_warm_product_in_two_column_halves(rx, lib, port, dt, n):
             assert rel_err(got, want) <= _tol(dt) and not np.isnan(got).any()
     finally:
         rx.gpu_csr_free(h)
+
+
+@pytest.mark.parametrize("register", [1, 0])
+def test_page_locked_blocks_of_both_kinds(rx, lib, port, register):
+    """host_pin_register: new page-locked blocks (result pool, staging arena) are huge-page backed anonymous memory
+    registered with the driver (1) or cudaHostAlloc blocks (0).  Either kind is page-locked to the library (DMA in place,
+    no bounce), recycled by the pool, and released by mxg_trim; the products are the same bits."""
+    import gc
+    gc.collect()
+    lib.call("mxg_trim")  # drop the arena and the free pool blocks of earlier tests: the next ones are of this kind
+    lib.set_option("host_pin_register", register)
+    try:
+        m, K, n = 40000, 3000, 32
+        p, j, x = powerlaw_csr(m, K, 10, seed=91, cap=1500)
+        Y = np.asfortranarray(np.random.default_rng(91).standard_normal((n, K)))
+        a = C.c_void_p()
+        lib.call("mxg_host_alloc", 9 << 20, C.byref(a))
+        buf = np.frombuffer((C.c_char * (9 << 20)).from_address(a.value), dtype=np.uint8)
+        buf[:] = 7  # every page is there and writable
+        assert a.value % (2 << 20) == 0 or register == 0
+        import torch
+        t = torch.empty(9 << 20, dtype=torch.uint8, device="cuda")
+        try:
+            rt = C.CDLL("libcudart.so.12")
+        except OSError:
+            rt = None
+        if rt is not None:
+            attr = (C.c_int * 16)()
+            assert rt.cudaPointerGetAttributes(attr, a) == 0 and attr[0] == 1  # cudaMemoryTypeHost: page-locked to the driver
+        lib.call("mxg_host_free", a)
+        del t, buf
+        res = rx.tcrossprod_csr_dense_numeric(p, j, x, Y)  # 10 MB result: the freed 10 MiB block, DMA'd into directly
+        up, down = _bytes(lib)
+        assert down == res.nbytes + 4
+        assert rel_err(res, port.tcrossprod_csr_dense_numeric(p, j, x, Y)) <= FP64_TOL
+        heap = rx.tcrossprod_csr_dense_numeric(p, j, x, Y, out=np.empty((m, n), order="F"))  # through the arena's slots
+        assert np.array_equal(res, heap)
+        del res
+        gc.collect()
+        lib.call("mxg_trim")
+        live, free, blocks = C.c_size_t(), C.c_size_t(), C.c_int()
+        lib.call("mxg_host_pool_stats", C.byref(live), C.byref(free), C.byref(blocks))
+        assert free.value == 0
+    finally:
+        lib.set_option("host_pin_register", 1)
+        lib.call("mxg_trim")
