@@ -336,6 +336,11 @@ int pinned_block_alloc(size_t bytes, PinnedBlock *blk)
     const size_t huge = (size_t)2 << 20;
     const size_t want = (std::max<size_t>(bytes, 1) + huge - 1) & ~(huge - 1);
     *blk = PinnedBlock();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { // nothing to map and touch memory for
+        cudaGetLastError();
+        return fail(MXG_ERR_CUDA, "no CUDA device: no page-locked memory to be had");
+    }
     if (options().host_pin_register != 0) {
         const size_t map_len = want + huge;
         void *q = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);

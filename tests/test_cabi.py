@@ -122,6 +122,12 @@ def test_new_entry_points_fail_loudly_without_a_device():
     n = C.c_int(0)
     _lib.call("mxg_get_devices", C.byref(n))
     assert n.value == 1
+    # no page-locked result memory either: the glue's allocator hook then falls back to an ordinary block
+    ptr = C.c_void_p()
+    with pytest.raises(_lib.MxgError) as ei:
+        _lib.call("mxg_host_alloc", 64 << 20, C.byref(ptr))
+    assert ei.value.code == _lib.MXG_ERR_CUDA and not ptr.value
+    assert rx._pooled_empty((1 << 20, 8), np.float64) is None
 
 
 def test_r_side_artefacts_are_files_and_apply():
