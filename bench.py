@@ -92,9 +92,16 @@ def ncu_traffic(workload):
 
 def bench_config(wl, world, nnz):
     """`config` of the JSON line — identical in the GPU arm and the reference arm (same workload, same partition)."""
+    s = 4 if wl["dtype"] == "f32" else 8
+    out_rows = wl["K"] if wl["op"] == "csrT_dense" else wl["m"]
+    step_bytes = int(nnz) * (4 + s) + s * wl["K"] * wl["n"] + s * out_rows * wl["n"]
     return {"workload": wl["desc"], "rows_per_gpu": wl["m"], "cols": wl["K"], "nnz_per_gpu": int(nnz), "n": wl["n"],
             "parallelism": (f"row-block shards x{world}, replicated dense operand, all-gather of the output row blocks"
-                            if world > 1 else "single GPU")}
+                            if world > 1 else "single GPU"),
+            # timing rule: flush L2 between timed steps, or use inputs larger than L2 — which one this workload is
+            "l2_between_steps": (f"no flush: the operands of one step ({step_bytes / 1e6:.0f} MB) exceed the 126 MB L2 several times over"
+                                 if step_bytes > 2 * 126e6 else
+                                 f"NOT flushed: the operands of one step ({step_bytes / 1e6:.0f} MB) fit the 126 MB L2 — a warm-cache parity config, not a bench line")}
 
 
 def w_alg_bytes(m, K, nnz, n, s):
